@@ -1,0 +1,192 @@
+/*
+ * mrfa_b200.h -- C ABI of libmrfa_b200.so: hand-written sm_100a kernels for the MRFA
+ * per-frame-pair motion-refinement hot path.
+ *
+ * The reference (JialeTao/MRFA) is pure Python: its "FFI" for this path is the Python symbol
+ * table of modules/util.py, modules/raft.py and modules/dense_motion.py.  Each entry point
+ * below names the reference lines it replaces.  The Python binding that sits above this ABI
+ * is mrfa_b200/_lib.py (ctypes) + mrfa_b200/ops.py (torch.library custom ops).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory
+ *     (outputs and workspaces are allocated by the caller and passed in); the library never
+ *     allocates, frees or retains pointers and keeps no mutable global state;
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*) on the current device;
+ *     no call synchronises;
+ *   - return value: 0 = success; < 0 = argument error (MRFA_E_*); > 0 = a cudaError_t;
+ *   - tensors are dense row-major ("contiguous") unless explicit element strides are passed;
+ *   - all floating point is IEEE fp32 (no fast-math); the correlation volume is bf16.
+ */
+#ifndef MRFA_B200_H_
+#define MRFA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRFA_B200_ABI_VERSION 1
+
+#define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
+#define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
+#define MRFA_E_ALIGN    (-3)   /* pointer not aligned as documented                    */
+#define MRFA_E_DRIVER   (-4)   /* cuTensorMapEncodeTiled entry point unavailable       */
+
+typedef void* mrfa_stream_t;   /* cudaStream_t */
+
+int         mrfa_abi_version(void);
+const char* mrfa_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * Sampling conventions for the bilinear warps
+ * ------------------------------------------------------------------------------------- */
+enum {
+  MRFA_COORD_NORM_ACF = 0, /* normalised grid, align_corners=False: bare F.grid_sample(x, grid)
+                              raft.py:166,168,271  dense_motion.py:83                         */
+  MRFA_COORD_NORM_ACT = 1, /* normalised grid, align_corners=True: dense_motion.py:241        */
+  MRFA_COORD_PIXEL    = 2  /* pixel coordinates: util.bilinear_sampler util.py:26-38 (replays
+                              the 2*x/(W-1)-1 normalisation and the un-normalisation in fp32)  */
+};
+enum { MRFA_PAD_ZEROS = 0, MRFA_PAD_REFLECTION = 1 /* model.py:48 */ };
+
+/* grid element (n,y,x,c) lives at grid[n*sn + y*sy + x*sx + c*sc]: lets the kernels consume
+ * both (N,Ho,Wo,2) grids and channel-planar flow fields (B,2,R,R) viewed through permute.   */
+typedef struct {
+  int64_t sn, sy, sx, sc;
+} mrfa_grid_strides_t;
+
+/* a6/a8/a9/a17: out[n,c,y,x] = bilinear(in[n / in_batch_div, c], grid[n,y,x]).
+ * in (N/in_batch_div, C, H, W); out (N, C, Ho, Wo).  If add_identity != 0 the pixel index
+ * (x, y) is added to the grid value first (fuses `flow + coords_grid`, raft.py:247,260,302).
+ * in_batch_div > 1 reads one input for several grids (fuses the `.repeat` of
+ * dense_motion.py:80-81 / :238-239).                                                        */
+int mrfa_grid_sample_fwd(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out,
+                         int N, int C, int H, int W, int Ho, int Wo, int in_batch_div,
+                         int coord_mode, int padding_mode, int add_identity, mrfa_stream_t stream);
+
+/* Backward of the above.  grad_in must be ZERO-FILLED by the caller (scatter-add target);
+ * grad_grid is written densely as (N,Ho,Wo,2).  Either may be NULL to skip it.               */
+int mrfa_grid_sample_bwd(const float* grad_out, const float* in, const float* grid, mrfa_grid_strides_t gs,
+                         float* grad_in, float* grad_grid,
+                         int N, int C, int H, int W, int Ho, int Wo, int in_batch_div,
+                         int coord_mode, int padding_mode, int add_identity, mrfa_stream_t stream);
+
+/* Two warps of the same feature map in one pass: refined (pixel flow + identity, raft.py:247)
+ * and coarse/prior (normalised grid, align_corners=False, raft.py:271).  flow (B,2,Ho,Wo)
+ * planar; prior_grid (B,Ho,Wo,2).  Reads `in` once from HBM.                                */
+int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid,
+                       float* out_refined, float* out_coarse,
+                       int N, int C, int H, int W, mrfa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Coordinate grids and key-point heat-maps
+ * ------------------------------------------------------------------------------------- */
+/* a10 util.coords_grid util.py:53-56 -> (B,2,ht,wd), channel 0 = x, 1 = y (bit-exact).       */
+int mrfa_coords_grid(float* out, int batch, int ht, int wd, mrfa_stream_t stream);
+/* a11 util.make_coordinate_grid util.py:90-108 -> (h,w,2), x = 2*(j/(w-1))-1 (bit-exact).    */
+int mrfa_make_coordinate_grid(float* out, int h, int w, mrfa_stream_t stream);
+/* a12 util.kp2gaussian util.py:59-87: out[p,y,x] = exp((-0.5*|g-kp[p]|^2)/variance) (+ add).
+ * kp (P,2); out (P,h,w).  `add` is NULL or a (add_period,h,w) tensor added with index
+ * p % add_period (fuses `+ self.pos_embedding`, raft.py:177-178).                            */
+int mrfa_kp2gaussian(const float* kp, const float* add, int add_period, float* out,
+                     int P, int h, int w, float variance, mrfa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Prior dense motion (a12-a15): heat-map difference, K+1 sparse motions, K+1 warped sources
+ * ------------------------------------------------------------------------------------- */
+/* DenseMotionNetwork.create_heatmap_representations / create_sparse_motions /
+ * create_deformed_source_image dense_motion.py:36-85 in ONE pass over the (K+1) x h x w plane.
+ *   kp_d, kp_s (B,K,2); jac_d, jac_s (B,K,2,2) or both NULL; bg_param (B,3,3) or NULL;
+ *   source (B,C,h,w);
+ *   motions  (B,K+1,h,w,2)            <- sparse motions, channel 0 = background
+ *   hg_input (B,(K+1)*(C+1),h,w)      <- per k: [heat-map, deformed source (C planes)], the
+ *                                         exact layout the hourglass consumes (:118-120)
+ * variance is kp_variance (0.01).  The deformed source is sampled with align_corners=False.  */
+int mrfa_dense_motion_prior(const float* kp_d, const float* kp_s, const float* jac_d, const float* jac_s,
+                            const float* bg_param, const float* source,
+                            float* motions, float* hg_input,
+                            int B, int K, int C, int h, int w, float variance, mrfa_stream_t stream);
+
+/* TPS.__init__(mode='kp') util.py:355-383: per (b,g) solve the (n+3)x(n+3) system, n == 5.
+ * kp_1, kp_2 (B*G,5,2) -> theta (B*G,2,3), control_params (B*G,5,2).                        */
+int mrfa_tps_solve(const float* kp_1, const float* kp_2, float* theta, float* control_params,
+                   int BG, mrfa_stream_t stream);
+
+/* TPSDenseMotionNetwork.create_heatmap_representations / create_transformations /
+ * create_deformed_source_image dense_motion.py:200-243 in one pass.
+ *   kp_d, kp_s (B,G*5,2); theta (B,G,2,3); control_params (B,G,5,2) from mrfa_tps_solve
+ *   (control points are kp_d); bg_param (B,3,3) or NULL; source (B,C,h,w);
+ *   motions  (B,G+1,h,w,2);
+ *   hg_input (B, (G*5+1) + (G+1)*C, h, w): heat-maps first, then deformed sources (:274-275),
+ *   sampled with align_corners=True.                                                         */
+int mrfa_tps_motion_prior(const float* kp_d, const float* kp_s, const float* theta, const float* control_params,
+                          const float* bg_param, const float* source,
+                          float* motions, float* hg_input,
+                          int B, int G, int C, int h, int w, float variance, mrfa_stream_t stream);
+
+/* a16 raft.py:189-190: flow[b,c,y,x] = (h-1)*(deformation[b,y,x,c]+1)/2 - (c ? y : x).
+ * deformation (B,h,w,2) -> flow (B,2,h,w); `hm1` is self.h - 1 for both axes.                */
+int mrfa_prior_to_flow(const float* deformation, float* flow, int B, int h, int w, float hm1,
+                       mrfa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * All-pairs structure correlation (a1-a4): pack -> tcgen05 GEMM with fused scale + pyramid
+ * ------------------------------------------------------------------------------------- */
+/* Row layout of the packed driving operand / of the volume: the driving plane at the basic
+ * resolution (h x w rows), followed by its 2x, 4x, 8x average-pooled versions.  Pooling the
+ * driving dims of the volume (raft.py:219) commutes with the contraction, so pooled query
+ * rows give the pooled volume rows directly.
+ *   rows_total = hw + hw/4 + hw/16 + hw/64 ; row offset of pool level l (k=2^l) is
+ *   sum_{m<l} hw/4^m.                                                                        */
+int64_t mrfa_corr_rows_total(int h, int w);
+int64_t mrfa_corr_row_offset(int h, int w, int pool_log2);
+
+/* fp32 NCHW features -> bf16 K-major GEMM operands (fuses the rearranges raft.py:183-184, the
+ * fp32->bf16 cast and the driving-side average pooling raft.py:219).
+ *   q_d, k_s (B,C,h,w) fp32;  a_op (B, rows_total, C) bf16;  b_op (B, h*w, C) bf16.
+ * C % 64 == 0, h and w multiples of 8.                                                       */
+int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op,
+                   int B, int C, int h, int w, mrfa_stream_t stream);
+
+/* volume0[b,i,j]  = scale * sum_c a_op[b,i,c] * b_op[b,j,c]            (B, rows_total, h*w)  bf16
+ * volume1[b,i,j'] = mean over the 2x2 source block j' of the above      (B, rows_total, hw/4) bf16
+ * (raft.py:185 einsum * self.scale; CorrBlock.__init__ raft.py:20 avg_pool2d level 1).
+ * tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), operands by TMA, 128 x (2w | 128)
+ * tiles so the source-side 2x2 pool is tile-local.  Requirements: C % 64 == 0, C <= 512,
+ * w in {8,16,32,64,128}, (h*w) % 128 == 0, all pointers 16-byte aligned (cudaMalloc).
+ * num_sms: SM count of the device (grid size of the persistent kernel); <= 0 -> 148.        */
+int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume0, void* volume1,
+                     int B, int C, int h, int w, float scale, int num_sms, mrfa_stream_t stream);
+
+/* Generic CorrBlock.__init__ level build for the drop-in API (raft.py:19-21):
+ * out (P,1,H/2,W/2) = avg_pool2d(in (P,1,H,W), 2, 2), fp32.                                  */
+int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pyramid lookup (a5 CorrBlock.__call__ raft.py:23-48)
+ * ------------------------------------------------------------------------------------- */
+/* out[b, lvl*(2r+1)^2 + a*(2r+1) + b', q] = bilinear(level_lvl[map(b,q)], (x/2^lvl + a - r,
+ * y/2^lvl + b' - r)), zeros padding, align_corners=True pixel convention (util.py:26-38).
+ *   coords (B,2,Q) planar (channel 0 = x) in level-0 pixels, Q = h1*w1 queries per sample;
+ *   the map of query (b,q) is level0 + (b*map_batch_stride + row_offset + q) * H*W, i.e.
+ *   reference `corr` (B*Q,1,H,W) has map_batch_stride = Q, row_offset = 0; a pyramid volume
+ *   from mrfa_corr_volume has map_batch_stride = rows_total, row_offset = pooled-level offset.
+ *   level1 is the 2x2-pooled map (H/2 x W/2) with the same indexing.
+ *   elem_bf16: 0 -> fp32 maps, 1 -> bf16 maps.   out (B, 2*(2r+1)^2, Q) fp32.  radius <= 4.  */
+int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16,
+                         const float* coords, float* out,
+                         int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
+                         int radius, mrfa_stream_t stream);
+
+/* Backward: grad_level0/1 (fp32, same indexing as the maps, ZERO-FILLED by the caller, may be
+ * NULL) receive the scatter-add; grad_coords (B,2,Q) is written.                             */
+int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* level1, int elem_bf16,
+                         const float* coords, float* grad_level0, float* grad_level1, float* grad_coords,
+                         int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
+                         int radius, mrfa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRFA_B200_H_ */

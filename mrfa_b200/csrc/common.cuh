@@ -1,0 +1,114 @@
+// Shared device helpers for libmrfa_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/mrfa_b200.h"
+
+#define MRFA_CHECK_ARG(cond) do { if (!(cond)) return MRFA_E_BADARG; } while (0)
+#define MRFA_CHECK_SHAPE(cond) do { if (!(cond)) return MRFA_E_SHAPE; } while (0)
+#define MRFA_LAUNCH_RESULT() ((int)cudaGetLastError())
+
+static inline cudaStream_t as_stream(mrfa_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+namespace mrfa {
+
+// ---- coordinate conventions ---------------------------------------
+// Replays the exact fp32 operation order of the reference so results stay inside 1e-5:
+//  PIXEL   : g = 2*x/(W-1) - 1            (util.py:30-31), then align_corners=True un-normalise
+//  NORM_ACT: ((g + 1) / 2) * (size - 1)   (ATen grid_sampler_unnormalize, align_corners)
+//  NORM_ACF: ((g + 1) * size - 1) / 2
+template <int MODE>
+__device__ __forceinline__ float to_pixel(float g, int size) {
+  if (MODE == MRFA_COORD_PIXEL) {
+    g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, g), (float)(size - 1)), 1.f);
+    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  } else if (MODE == MRFA_COORD_NORM_ACT) {
+    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  } else {
+    return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 2.f);
+  }
+}
+
+// d(pixel)/d(grid value) for the backward pass.
+template <int MODE>
+__device__ __forceinline__ float to_pixel_grad(int size) {
+  if (MODE == MRFA_COORD_PIXEL) return 1.f;
+  if (MODE == MRFA_COORD_NORM_ACT) return (float)(size - 1) / 2.f;
+  return (float)size / 2.f;
+}
+
+// ATen reflect_coordinates + clip (padding_mode="reflection"), returns d(out)/d(in) in *mult.
+__device__ __forceinline__ float reflect_coord(float x, int twice_low, int twice_high, float* mult) {
+  if (twice_low == twice_high) { *mult = 0.f; return 0.f; }
+  float mn = (float)twice_low / 2.f;
+  float span = (float)(twice_high - twice_low) / 2.f;
+  float m = 1.f;
+  x = x - mn;
+  if (x < 0.f) { x = -x; m = -1.f; }
+  float extra = fmodf(x, span);
+  int flips = (int)floorf(x / span);
+  if (flips % 2 == 0) { *mult = m; return extra + mn; }
+  *mult = -m;
+  return span - extra + mn;
+}
+
+template <int MODE, int PAD>
+__device__ __forceinline__ float source_index(float g, int size, float* mult) {
+  float p = to_pixel<MODE>(g, size);
+  float m = to_pixel_grad<MODE>(size);
+  if (PAD == MRFA_PAD_REFLECTION) {
+    float r;
+    if (MODE == MRFA_COORD_NORM_ACF) p = reflect_coord(p, -1, 2 * size - 1, &r);
+    else p = reflect_coord(p, 0, 2 * (size - 1), &r);
+    m *= r;
+    if (p <= 0.f) { p = 0.f; m = 0.f; }                      // clip_coordinates_set_grad
+    else if (p >= (float)(size - 1)) { p = (float)(size - 1); m = 0.f; }
+  }
+  *mult = m;
+  return p;
+}
+
+// Four bilinear taps of one sample: flat offsets inside an H x W plane (clamped to a legal
+// address) and weights (zeroed for out-of-image taps = zeros padding).
+struct Taps {
+  int o_nw, o_ne, o_sw, o_se;
+  float w_nw, w_ne, w_sw, w_se;
+};
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
+  Taps t;
+  // clamp so the int conversion is defined for wild / non-finite coordinates
+  float fx = floorf(ix), fy = floorf(iy);
+  bool finite = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);   // false for NaN / inf
+  int x0 = finite ? (int)fx : -2;
+  int y0 = finite ? (int)fy : -2;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  float ax = ix - fx, ay = iy - fy;                          // == ix - ix_nw
+  float bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;          // == ix_se - ix
+  bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+  bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+  int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+  int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  t.o_nw = cy0 * W + cx0; t.o_ne = cy0 * W + cx1;
+  t.o_sw = cy1 * W + cx0; t.o_se = cy1 * W + cx1;
+  t.w_nw = (finite & vx0 & vy0) ? bx * by : 0.f;
+  t.w_ne = (finite & vx1 & vy0) ? ax * by : 0.f;
+  t.w_sw = (finite & vx0 & vy1) ? bx * ay : 0.f;
+  t.w_se = (finite & vx1 & vy1) ? ax * ay : 0.f;
+  return t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// identity grid value, bit-exact with util.make_coordinate_grid: 2*(j/(n-1)) - 1
+__device__ __forceinline__ float norm_coord(int j, int n) {
+  return __fsub_rn(__fmul_rn(2.f, __fdiv_rn((float)j, (float)(n - 1))), 1.f);
+}
+
+}  // namespace mrfa

@@ -1,0 +1,553 @@
+// All-pairs structure correlation (K1+K2+K3 of SURVEY.md; raft.py:183-185, :208, :219, :235-236,
+// CorrBlock.__init__ raft.py:12-21).
+//
+//   corr_pack    fp32 NCHW conv outputs -> bf16 K-major GEMM operands, with the driving-side
+//                average pooling (raft.py:219) applied to the *operand* (pooling commutes with
+//                the contraction), so one GEMM yields every driving resolution.
+//   corr_volume  persistent warp-specialised tcgen05 GEMM: A tile (128 rows x C) stationary in
+//                shared memory, B tiles streamed by TMA through an mbarrier ring, fp32
+//                accumulators double-buffered in TMEM, epilogue fuses the 1/sqrt(C) scale, the
+//                bf16 cast and the source-side 2x2 average pool (level 1 of the pyramid) and
+//                writes each row as whole 32-byte sectors.  The transposed copies of the
+//                reference (raft.py:208,235-236) never exist: row i of the volume *is* the
+//                h x w map that query i looks up.
+//
+// Roofline: the output (rows_total x hw x 1.25 bf16) makes the kernel HBM-write-bound once the
+// operands sit in L2; algorithmic FLOPs = 2 * hw * hw * C per pair.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace mrfa {
+
+// ============================================================================================
+// pack
+// ============================================================================================
+constexpr int kPackRows = 8;        // spatial rows per tile (covers the 8x8 pooling block)
+constexpr int kPackCh = 32;         // channels per tile
+constexpr int kPackThreads = 256;
+
+__device__ __forceinline__ int64_t level_row_offset(int hw, int lvl) {
+  int64_t off = 0;
+  for (int m = 0; m < lvl; ++m) off += hw >> (2 * m);
+  return off;
+}
+
+// grid: (tiles_y * tiles_x, 2 * C/32, B); blockIdx.y < C/32 -> q_d (all levels), else k_s
+__global__ void __launch_bounds__(kPackThreads)
+corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, __nv_bfloat16* __restrict__ a_op,
+                 __nv_bfloat16* __restrict__ b_op, int C, int h, int w, int tile_w, int64_t rows_total) {
+  extern __shared__ float tile[];                      // [kPackCh][kPackRows * tile_w + 1]
+  const int cblocks = C / kPackCh;
+  const bool is_q = blockIdx.y < cblocks;
+  const int c0 = (is_q ? blockIdx.y : blockIdx.y - cblocks) * kPackCh;
+  const int b = blockIdx.z;
+  const int tiles_x = w / tile_w;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * kPackRows, x0 = tx * tile_w;
+  const int hw = h * w;
+  const int cs = kPackRows * tile_w + 1;               // channel stride in smem (odd)
+  const float* src = (is_q ? q_d : k_s) + ((int64_t)b * C + c0) * hw;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  // load: (c, y) segments of tile_w contiguous floats
+  const int segs = kPackCh * kPackRows;
+  for (int s = warp; s < segs; s += kPackThreads / 32) {
+    const int c = s / kPackRows, y = s - c * kPackRows;
+    for (int x = lane; x < tile_w; x += 32)
+      tile[c * cs + y * tile_w + x] = __ldg(src + (int64_t)c * hw + (y0 + y) * w + x0 + x);
+  }
+  __syncthreads();
+
+  __nv_bfloat16* dst = is_q ? a_op + (int64_t)b * rows_total * C : b_op + (int64_t)b * hw * C;
+  // level 0: one pixel per warp-iteration, lane = channel -> 64-byte row pieces
+  const int npix = kPackRows * tile_w;
+  for (int p = warp; p < npix; p += kPackThreads / 32) {
+    const int y = p / tile_w, x = p - y * tile_w;
+    const int64_t row = (int64_t)(y0 + y) * w + x0 + x;
+    dst[row * C + c0 + lane] = __float2bfloat16_rn(tile[lane * cs + p]);
+  }
+  if (!is_q) return;
+  // pooled driving levels k = 2, 4, 8 (F.avg_pool2d: row-major window sum / k^2)
+#pragma unroll
+  for (int lvl = 1; lvl <= 3; ++lvl) {
+    const int k = 1 << lvl;
+    const int pw = tile_w / k, ph = kPackRows / k;
+    const int64_t off = level_row_offset(hw, lvl);
+    const int wl = w / k;
+    for (int p = warp; p < pw * ph; p += kPackThreads / 32) {
+      const int py = p / pw, px = p - py * pw;
+      float acc = 0.f;
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) acc += tile[lane * cs + (py * k + dy) * tile_w + px * k + dx];
+      const int64_t row = off + (int64_t)(y0 / k + py) * wl + x0 / k + px;
+      dst[row * C + c0 + lane] = __float2bfloat16_rn(acc / (float)(k * k));
+    }
+  }
+}
+
+// ============================================================================================
+// tcgen05 GEMM
+// ============================================================================================
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                            // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;                      // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kMaxKBlocks = 8;                         // C <= 512
+constexpr uint32_t kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB per K block
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): rows of 128 bytes,
+// 8-row groups 1024 bytes apart (SBO), descriptor version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int kW> struct GemmCfg {
+  static constexpr int kBlockN = (kW == 128) ? 256 : 128;
+  static constexpr uint32_t kBStageBytes = kBlockN * kBlockK * 2;
+  static constexpr int kTmemCols = 2 * kBlockN;
+};
+
+struct GemmSmemPlan {
+  int a_bufs, b_stages;
+  uint32_t bytes;
+};
+
+static GemmSmemPlan plan_smem(int kblocks, uint32_t b_stage_bytes) {
+  const uint32_t budget = 227 * 1024 - 2048;           // alignment slack + barriers
+  GemmSmemPlan p;
+  const uint32_t a_one = kblocks * kATileBytes;
+  p.a_bufs = (2 * a_one + 3 * b_stage_bytes <= budget) ? 2 : 1;
+  int stages = (int)((budget - p.a_bufs * a_one) / b_stage_bytes);
+  p.b_stages = stages > 8 ? 8 : stages;
+  p.bytes = p.a_bufs * a_one + p.b_stages * b_stage_bytes + 2048;
+  return p;
+}
+
+struct GemmParams {
+  int B, kblocks, m_blocks, n_tiles, n_split, a_bufs, b_stages;
+  int64_t rows_total;
+  int N;               // hw
+  float scale;
+};
+
+template <int kW>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+corr_volume_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   __nv_bfloat16* __restrict__ vol0, __nv_bfloat16* __restrict__ vol1, const GemmParams prm) {
+  using Cfg = GemmCfg<kW>;
+  constexpr int kBlockN = Cfg::kBlockN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                                   // [a_bufs][kblocks][16 KiB]
+  uint8_t* smem_b = smem_a + (size_t)prm.a_bufs * prm.kblocks * kATileBytes;  // [b_stages][kBStageBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)prm.b_stages * Cfg::kBStageBytes);
+  uint64_t* a_full = bars;              // [2]
+  uint64_t* a_empty = bars + 2;         // [2]
+  uint64_t* t_full = bars + 4;          // [2]
+  uint64_t* t_empty = bars + 6;         // [2]
+  uint64_t* b_full = bars + 8;          // [b_stages]
+  uint64_t* b_empty = bars + 8 + 8;     // [b_stages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);        // one arrive per epilogue warp
+    }
+    for (int i = 0; i < prm.b_stages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_unit = prm.n_tiles / prm.n_split;
+  const int64_t units = (int64_t)prm.B * prm.m_blocks * prm.n_split;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int split = (int)(u % prm.n_split);
+        const int m_blk = (int)((u / prm.n_split) % prm.m_blocks);
+        const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+        const int abuf = it % prm.a_bufs;
+        const uint32_t aphase = (uint32_t)(it / prm.a_bufs) & 1u;
+        mbar_wait(&a_empty[abuf], aphase ^ 1u);
+        mbar_expect_tx(&a_full[abuf], (uint32_t)prm.kblocks * kATileBytes);
+        for (int kb = 0; kb < prm.kblocks; ++kb)
+          tma_load_3d(smem_a + ((size_t)abuf * prm.kblocks + kb) * kATileBytes, &map_a, &a_full[abuf], kb * kBlockK,
+                      m_blk * kBlockM, b);
+        for (int t = 0; t < tiles_per_unit; ++t) {
+          const int nt = split * tiles_per_unit + t;
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&b_full[stage], Cfg::kBStageBytes);
+            tma_load_3d(smem_b + (size_t)stage * Cfg::kBStageBytes, &map_b, &b_full[stage], kb * kBlockK, nt * kBlockN, b);
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      uint32_t tcount = 0;
+      for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int abuf = it % prm.a_bufs;
+        const uint32_t aphase = (uint32_t)(it / prm.a_bufs) & 1u;
+        mbar_wait(&a_full[abuf], aphase);
+        tcgen05_fence_after();
+        for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+          const uint32_t acc = tcount & 1u;
+          const uint32_t acc_phase = (tcount >> 1) & 1u;
+          mbar_wait(&t_empty[acc], acc_phase ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kBlockN;
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + ((size_t)abuf * prm.kblocks + kb) * kATileBytes);
+            const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * Cfg::kBStageBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * kUmmaK * 2);
+              const uint64_t db = umma_desc_sw128(b_addr + k * kUmmaK * 2);
+              tcgen05_mma_bf16(tmem_d, da, db, idesc, (uint32_t)((kb | k) != 0));
+            }
+            tcgen05_commit(&b_empty[stage]);            // frees the B stage when these MMAs retire
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+          tcgen05_commit(&t_full[acc]);                 // accumulator ready for the epilogue
+        }
+        tcgen05_commit(&a_empty[abuf]);                 // A buffer reusable
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const int ew = warp - 4;                            // == warp % 4: TMEM lane quarter
+    const float scale = prm.scale;
+    const float scale4 = prm.scale * 0.25f;
+    const int N = prm.N, N4 = prm.N / 4;
+    uint32_t tcount = 0;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+      const int split = (int)(u % prm.n_split);
+      const int m_blk = (int)((u / prm.n_split) % prm.m_blocks);
+      const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+      const int64_t row = (int64_t)m_blk * kBlockM + ew * 32 + lane;
+      const bool row_ok = row < prm.rows_total;
+      __nv_bfloat16* out0 = vol0 + ((int64_t)b * prm.rows_total + row) * N;
+      __nv_bfloat16* out1 = vol1 + ((int64_t)b * prm.rows_total + row) * N4;
+      for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+        const int nt = split * tiles_per_unit + t;
+        const uint32_t acc = tcount & 1u;
+        const uint32_t acc_phase = (tcount >> 1) & 1u;
+        mbar_wait(&t_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
+        __nv_bfloat16* o0 = out0 + (int64_t)nt * kBlockN;
+        __nv_bfloat16* o1 = out1 + (int64_t)nt * (kBlockN / 4);
+        if constexpr (kW >= 32) {
+          // source rows p (cols [g*2W, g*2W+W)) and p+1 (cols + W): pair 32-column chunks
+          constexpr int kGroups = kBlockN / (2 * kW);
+#pragma unroll 1
+          for (int g = 0; g < kGroups; ++g) {
+#pragma unroll 1
+            for (int c = 0; c < kW; c += 32) {
+              const int col0 = g * 2 * kW + c, col1 = col0 + kW;
+              uint32_t v0[32], v1[32];
+              tmem_ld_32x32(taddr + col0, v0);
+              tmem_ld_32x32(taddr + col1, v1);
+              tmem_ld_wait();
+              if (row_ok) {
+                uint32_t p0[16], p1[16], pl[8];
+                float pooled[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
+                  const float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
+                  p0[j] = pack_bf16(a0 * scale, a1 * scale);
+                  p1[j] = pack_bf16(b0 * scale, b1 * scale);
+                  pooled[j] = ((a0 + a1) + (b0 + b1)) * scale4;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
+                const uint32_t (&q0)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p0[0]);
+                const uint32_t (&q1)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p0[8]);
+                const uint32_t (&q2)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p1[0]);
+                const uint32_t (&q3)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p1[8]);
+                st_global_v8(o0 + col0, q0);
+                st_global_v8(o0 + col0 + 16, q1);
+                st_global_v8(o0 + col1, q2);
+                st_global_v8(o0 + col1 + 16, q3);
+                st_global_v8(o1 + g * (kW / 2) + c / 2, pl);
+              }
+            }
+          }
+        } else {
+          // W in {8, 16}: a 32-column chunk holds 32/(2W) complete row pairs
+          constexpr int kGroups = 32 / (2 * kW);
+          constexpr int kHalf = kW / 2;
+#pragma unroll 1
+          for (int c = 0; c < kBlockN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              uint32_t p[16], pl[4];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                p[j] = pack_bf16(__uint_as_float(v[2 * j]) * scale, __uint_as_float(v[2 * j + 1]) * scale);
+              float pooled[8];
+#pragma unroll
+              for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+                for (int j = 0; j < kHalf; ++j) {
+                  const int i0 = g * 2 * kW + 2 * j, i1 = i0 + kW;
+                  pooled[g * kHalf + j] = ((__uint_as_float(v[i0]) + __uint_as_float(v[i0 + 1])) +
+                                           (__uint_as_float(v[i1]) + __uint_as_float(v[i1 + 1]))) * scale4;
+                }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
+              const uint32_t (&q0)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p[0]);
+              const uint32_t (&q1)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&p[8]);
+              st_global_v8(o0 + c, q0);
+              st_global_v8(o0 + c + 16, q1);
+              st_global_v4(o1 + c / 4, pl[0], pl[1], pl[2], pl[3]);
+            }
+          }
+        }
+        // all of this warp's TMEM reads of the accumulator are complete
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  // resolved once per process; the pointer is immutable afterwards (no mutable library state)
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int make_operand_map(CUtensorMap* map, const void* base, int C, int64_t rows, int B, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MRFA_E_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MRFA_E_DRIVER;
+}
+
+template <int kW>
+static int launch_corr_volume(const void* a_op, const void* b_op, void* v0, void* v1, int B, int C, int h, int w,
+                              float scale, int num_sms, cudaStream_t st) {
+  using Cfg = GemmCfg<kW>;
+  GemmParams prm;
+  prm.B = B;
+  prm.kblocks = C / kBlockK;
+  prm.N = h * w;
+  prm.rows_total = mrfa_corr_rows_total(h, w);
+  prm.m_blocks = (int)cdiv64(prm.rows_total, kBlockM);
+  prm.n_tiles = prm.N / Cfg::kBlockN;
+  prm.scale = scale;
+  const GemmSmemPlan plan = plan_smem(prm.kblocks, Cfg::kBStageBytes);
+  prm.a_bufs = plan.a_bufs;
+  prm.b_stages = plan.b_stages;
+  // split the N range of a row block until there are enough units to fill the machine twice
+  int n_split = 1;
+  while ((int64_t)B * prm.m_blocks * n_split < 2ll * num_sms && n_split * 2 <= prm.n_tiles &&
+         prm.n_tiles % (n_split * 2) == 0)
+    n_split *= 2;
+  prm.n_split = n_split;
+
+  CUtensorMap map_a, map_b;
+  int rc = make_operand_map(&map_a, a_op, C, prm.rows_total, B, kBlockM);
+  if (rc) return rc;
+  rc = make_operand_map(&map_b, b_op, C, prm.N, B, Cfg::kBlockN);
+  if (rc) return rc;
+
+  auto kern = corr_volume_kernel<kW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t units = (int64_t)B * prm.m_blocks * n_split;
+  const unsigned grid = (unsigned)(units < num_sms ? units : num_sms);
+  kern<<<grid, kGemmThreads, plan.bytes, st>>>(map_a, map_b, static_cast<__nv_bfloat16*>(v0),
+                                               static_cast<__nv_bfloat16*>(v1), prm);
+  return MRFA_LAUNCH_RESULT();
+}
+
+}  // namespace mrfa
+
+using namespace mrfa;
+
+extern "C" int64_t mrfa_corr_rows_total(int h, int w) {
+  const int64_t hw = (int64_t)h * w;
+  return hw + hw / 4 + hw / 16 + hw / 64;
+}
+
+extern "C" int64_t mrfa_corr_row_offset(int h, int w, int pool_log2) {
+  const int64_t hw = (int64_t)h * w;
+  int64_t off = 0;
+  for (int m = 0; m < pool_log2; ++m) off += hw >> (2 * m);
+  return off;
+}
+
+extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op, int B, int C, int h, int w,
+                              mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(q_d && k_s && a_op && b_op && B >= 0 && C > 0 && h > 0 && w > 0);
+  MRFA_CHECK_SHAPE(C % kPackCh == 0 && h % 8 == 0 && w % 8 == 0 && B <= 65535);
+  MRFA_CHECK_SHAPE(w <= 32 || w % 32 == 0);
+  if (B == 0) return 0;
+  const int tile_w = w < 32 ? w : 32;
+  dim3 grid((unsigned)((h / kPackRows) * (w / tile_w)), (unsigned)(2 * C / kPackCh), (unsigned)B);
+  const size_t smem = (size_t)kPackCh * (kPackRows * tile_w + 1) * sizeof(float);
+  corr_pack_kernel<<<grid, kPackThreads, smem, as_stream(stream)>>>(
+      q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), C, h, w, tile_w,
+      mrfa_corr_rows_total(h, w));
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume0, void* volume1, int B, int C, int h,
+                                int w, float scale, int num_sms, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(a_op && b_op && volume0 && volume1 && B >= 0 && C > 0 && h > 0 && w > 0);
+  MRFA_CHECK_SHAPE(C % kBlockK == 0 && C / kBlockK <= kMaxKBlocks && h % 8 == 0);
+  if ((reinterpret_cast<uintptr_t>(a_op) | reinterpret_cast<uintptr_t>(b_op) | reinterpret_cast<uintptr_t>(volume0) |
+       reinterpret_cast<uintptr_t>(volume1)) & 31)
+    return MRFA_E_ALIGN;
+  if (B == 0) return 0;
+  if (num_sms <= 0) num_sms = 148;
+  cudaStream_t st = as_stream(stream);
+  const int N = h * w;
+  switch (w) {
+    case 8: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<8>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 16: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<16>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 32: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<32>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 64: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<64>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 128: MRFA_CHECK_SHAPE(N % 256 == 0); return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    default: return MRFA_E_SHAPE;
+  }
+}

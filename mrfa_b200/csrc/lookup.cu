@@ -1,0 +1,280 @@
+// Correlation pyramid lookup (K4 of SURVEY.md, CorrBlock.__call__ raft.py:23-48) and the
+// generic level-1 build (raft.py:19-21).
+//
+// Per query the (2r+1)^2 window of a level shares one fractional offset, so its bilinear taps
+// live in an (2r+2)^2 integer footprint.  A block takes 32 consecutive queries of one sample:
+//   phase 1  warp-per-query gather of the two footprints (each footprint row is one 16/32-byte
+//            contiguous piece of that query's own volume row) into shared memory;
+//   phase 2  lane-per-query evaluation of the 2*(2r+1)^2 outputs from shared memory, so every
+//            store is a 128-byte line of the (B, 98, Q) output.
+// HBM-bound: algorithmic bytes per query = 2 levels * 64 * elt + 8 (coords) + 98*4 (out).
+#include "common.cuh"
+
+namespace mrfa {
+
+constexpr int kQPB = 32;              // queries per block
+constexpr int kLookupThreads = 128;
+constexpr int kMaxR = 4;
+
+template <typename T> __device__ __forceinline__ float ld_elem(const T* p);
+template <> __device__ __forceinline__ float ld_elem<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_elem<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
+
+struct QueryGeom {
+  int x0, y0;       // integer position of footprint cell (0,0)
+  float fx, fy;     // shared fractional offsets
+};
+
+// centre of the window on level `lvl`, replaying util.bilinear_sampler's coordinate round trip
+__device__ __forceinline__ QueryGeom query_geom(float cx, float cy, int lvl, int Hl, int Wl, int r) {
+  const float s = (lvl == 0) ? 1.f : 2.f;
+  const float px = to_pixel<MRFA_COORD_PIXEL>(__fdiv_rn(cx, s), Wl);
+  const float py = to_pixel<MRFA_COORD_PIXEL>(__fdiv_rn(cy, s), Hl);
+  QueryGeom g;
+  const bool fin = (fabsf(px) < 1e8f) && (fabsf(py) < 1e8f);
+  const float flx = floorf(px), fly = floorf(py);
+  g.x0 = fin ? (int)flx - r : -(1 << 20);
+  g.y0 = fin ? (int)fly - r : -(1 << 20);
+  g.fx = fin ? px - flx : 0.f;
+  g.fy = fin ? py - fly : 0.f;
+  return g;
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(kLookupThreads)
+corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level1, const float* __restrict__ coords,
+                       float* __restrict__ out, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset) {
+  constexpr int n = 2 * R + 1, F = n + 1, FF = F * F;
+  constexpr int kStride = 2 * FF + 1;                 // odd -> conflict-free lane-per-query reads
+  __shared__ float foot[kQPB * kStride];
+  __shared__ float frac[kQPB][4];
+
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int H1 = H / 2, W1 = W / 2;
+
+  // ---- phase 1: gather footprints -------------------------------------------------------
+  for (int qi = warp; qi < kQPB; qi += kLookupThreads / 32) {
+    const int q = q0 + qi;
+    if (q >= Q) break;
+    const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
+    const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
+    const int64_t map = (int64_t)b * map_batch_stride + row_offset + q;
+#pragma unroll
+    for (int lvl = 0; lvl < 2; ++lvl) {
+      const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
+      const QueryGeom g = query_geom(cx, cy, lvl, Hl, Wl, R);
+      const T* base = (lvl ? level1 : level0) + map * ((int64_t)Hl * Wl);
+      if (lane == 0) { frac[qi][2 * lvl] = g.fx; frac[qi][2 * lvl + 1] = g.fy; }
+#pragma unroll
+      for (int e = lane; e < FF; e += 32) {
+        const int fy_ = e / F, fx_ = e - fy_ * F;
+        const int yy = g.y0 + fy_, xx = g.x0 + fx_;
+        float v = 0.f;
+        if (yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) v = ld_elem<T>(base + (int64_t)yy * Wl + xx);
+        foot[qi * kStride + lvl * FF + e] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: lane = query, warps stride over the output channels ----------------------
+  const int q = q0 + lane;
+  if (q >= Q) return;
+  const float* fq = foot + lane * kStride;
+  float* dst = out + (int64_t)b * (2 * n * n) * Q + q;
+#pragma unroll
+  for (int lvl = 0; lvl < 2; ++lvl) {
+    const float fx = frac[lane][2 * lvl], fy = frac[lane][2 * lvl + 1];
+    // same evaluation order as ATen: nw, ne, sw, se
+    const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
+    for (int k = warp; k < n * n; k += kLookupThreads / 32) {
+      const int a = k / n, bb = k - a * n;             // channel a*n+b: x offset a-r, y offset b-r
+      const float* c = fq + lvl * FF + bb * F + a;
+      float acc = c[0] * w_nw;
+      acc = fmaf(c[1], w_ne, acc);
+      acc = fmaf(c[F], w_sw, acc);
+      acc = fmaf(c[F + 1], w_se, acc);
+      __stcs(dst + (int64_t)(lvl * n * n + k) * Q, acc);
+    }
+  }
+}
+
+// Backward: footprint-cell gradients are assembled by a gather over the (at most four) window
+// taps that touch a cell -- the overlapping-tap pre-reduction -- and leave the block as one
+// red.global per in-image cell (128 instead of 392 atomics per query); coordinate gradients
+// are reduced over the channel axis with warp shuffles.
+template <typename T, int R>
+__global__ void __launch_bounds__(kLookupThreads)
+corr_lookup_bwd_kernel(const float* __restrict__ grad_out, const T* __restrict__ level0,
+                       const T* __restrict__ level1, const float* __restrict__ coords,
+                       float* __restrict__ grad_level0, float* __restrict__ grad_level1,
+                       float* __restrict__ grad_coords, int Q, int H, int W, int64_t map_batch_stride,
+                       int64_t row_offset) {
+  constexpr int n = 2 * R + 1, F = n + 1, FF = F * F, NN = n * n;
+  constexpr int kGoStride = 2 * NN + 1;
+  constexpr int kWarps = kLookupThreads / 32;
+  __shared__ float go[kQPB * kGoStride];
+  __shared__ float foot[kWarps][FF];
+
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int H1 = H / 2, W1 = W / 2;
+
+  // stage grad_out: lanes along q (coalesced), warps along channels
+  for (int k = warp; k < 2 * NN; k += kWarps) {
+    const int q = q0 + lane;
+    go[lane * kGoStride + k] = (q < Q) ? __ldg(grad_out + ((int64_t)b * 2 * NN + k) * Q + q) : 0.f;
+  }
+  __syncthreads();
+
+  for (int qi = warp; qi < kQPB; qi += kWarps) {          // warp per query
+    const int q = q0 + qi;
+    if (q >= Q) break;
+    const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
+    const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
+    const int64_t map = (int64_t)b * map_batch_stride + row_offset + q;
+    const float* gq = go + qi * kGoStride;
+    float gcx = 0.f, gcy = 0.f;
+#pragma unroll
+    for (int lvl = 0; lvl < 2; ++lvl) {
+      const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
+      const QueryGeom g = query_geom(cx, cy, lvl, Hl, Wl, R);
+      const float fx = g.fx, fy = g.fy;
+      const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
+      float* gl = lvl ? grad_level1 : grad_level0;
+      const T* base = (lvl ? level1 : level0) + map * ((int64_t)Hl * Wl);
+      __syncwarp();
+      for (int e = lane; e < FF; e += 32) {
+        const int fy_ = e / F, fx_ = e - fy_ * F;
+        const int yy = g.y0 + fy_, xx = g.x0 + fx_;
+        const bool inside = yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
+        // (1) scatter into the map: cell (fy_, fx_) collects window taps (b',a) in
+        //     {(fy_,fx_), (fy_,fx_-1), (fy_-1,fx_), (fy_-1,fx_-1)}; channel index = a*n + b'
+        if (gl != nullptr && inside) {
+          float acc = 0.f;
+          if (fy_ < n && fx_ < n) acc = fmaf(gq[lvl * NN + fx_ * n + fy_], w_nw, acc);
+          if (fy_ < n && fx_ >= 1) acc = fmaf(gq[lvl * NN + (fx_ - 1) * n + fy_], w_ne, acc);
+          if (fy_ >= 1 && fx_ < n) acc = fmaf(gq[lvl * NN + fx_ * n + (fy_ - 1)], w_sw, acc);
+          if (fy_ >= 1 && fx_ >= 1) acc = fmaf(gq[lvl * NN + (fx_ - 1) * n + (fy_ - 1)], w_se, acc);
+          if (acc != 0.f) atomicAdd(gl + map * ((int64_t)Hl * Wl) + (int64_t)yy * Wl + xx, acc);
+        }
+        // (2) stage the map values for the coordinate gradient (zero outside the image)
+        if (grad_coords != nullptr) foot[warp][e] = inside ? ld_elem<T>(base + (int64_t)yy * Wl + xx) : 0.f;
+      }
+      if (grad_coords != nullptr) {
+        __syncwarp();
+        const float inv = lvl ? 0.5f : 1.f;                 // d(c / 2^lvl)/dc
+        for (int k = lane; k < NN; k += 32) {
+          const int a = k / n, bb = k - a * n;
+          const float* c = &foot[warp][bb * F + a];
+          const float dpx = (c[1] - c[0]) * (1.f - fy) + (c[F + 1] - c[F]) * fy;
+          const float dpy = (c[F] - c[0]) * (1.f - fx) + (c[F + 1] - c[1]) * fx;
+          const float gk = gq[lvl * NN + k] * inv;
+          gcx = fmaf(gk, dpx, gcx);
+          gcy = fmaf(gk, dpy, gcy);
+        }
+      }
+    }
+    if (grad_coords != nullptr) {
+      gcx = warp_sum(gcx);
+      gcy = warp_sum(gcy);
+      if (lane == 0) {
+        grad_coords[((int64_t)b * 2 + 0) * Q + q] = gcx;
+        grad_coords[((int64_t)b * 2 + 1) * Q + q] = gcy;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avg_pool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t P, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = P * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int64_t p = i / ((int64_t)Wo * Ho);
+    const float* s = in + (p * H + 2 * y) * W + 2 * x;
+    // ATen avg_pool2d accumulates row-major over the window, then divides by the pool size
+    float acc = __fadd_rn(__fadd_rn(__fadd_rn(__ldg(s), __ldg(s + 1)), __ldg(s + W)), __ldg(s + W + 1));
+    out[i] = __fdiv_rn(acc, 4.f);
+  }
+}
+
+}  // namespace mrfa
+
+using namespace mrfa;
+
+template <typename T>
+static int launch_lookup_fwd(const void* l0, const void* l1, const float* coords, float* out, int B, int Q, int H,
+                             int W, int64_t mbs, int64_t ro, int radius, cudaStream_t st) {
+  dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
+  const T* a = static_cast<const T*>(l0);
+  const T* b = static_cast<const T*>(l1);
+  switch (radius) {
+    case 1: corr_lookup_fwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
+    case 2: corr_lookup_fwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
+    case 3: corr_lookup_fwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
+    case 4: corr_lookup_fwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
+    default: return MRFA_E_SHAPE;
+  }
+  return MRFA_LAUNCH_RESULT();
+}
+
+template <typename T>
+static int launch_lookup_bwd(const float* go, const void* l0, const void* l1, const float* coords, float* g0,
+                             float* g1, float* gc, int B, int Q, int H, int W, int64_t mbs, int64_t ro, int radius,
+                             cudaStream_t st) {
+  dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
+  const T* a = static_cast<const T*>(l0);
+  const T* b = static_cast<const T*>(l1);
+  switch (radius) {
+    case 1: corr_lookup_bwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 2: corr_lookup_bwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 3: corr_lookup_bwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 4: corr_lookup_bwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    default: return MRFA_E_SHAPE;
+  }
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16, const float* coords,
+                                    float* out, int B, int Q, int H, int W, int64_t map_batch_stride,
+                                    int64_t row_offset, int radius, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(level0 && level1 && coords && out);
+  MRFA_CHECK_ARG(B >= 0 && Q > 0 && H >= 2 && W >= 2 && map_batch_stride >= 0 && row_offset >= 0);
+  MRFA_CHECK_SHAPE(radius >= 1 && radius <= kMaxR && B <= 65535);
+  if (B == 0) return 0;
+  if (elem_bf16)
+    return launch_lookup_fwd<__nv_bfloat16>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+  return launch_lookup_fwd<float>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+}
+
+extern "C" int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* level1, int elem_bf16,
+                                    const float* coords, float* grad_level0, float* grad_level1, float* grad_coords,
+                                    int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
+                                    int radius, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(grad_out && level0 && level1 && coords);
+  MRFA_CHECK_ARG((grad_level0 == nullptr) == (grad_level1 == nullptr));
+  MRFA_CHECK_ARG(grad_level0 || grad_coords);
+  MRFA_CHECK_ARG(B >= 0 && Q > 0 && H >= 2 && W >= 2 && map_batch_stride >= 0 && row_offset >= 0);
+  MRFA_CHECK_SHAPE(radius >= 1 && radius <= kMaxR && B <= 65535);
+  if (B == 0) return 0;
+  if (elem_bf16)
+    return launch_lookup_bwd<__nv_bfloat16>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+  return launch_lookup_bwd<float>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+}
+
+extern "C" int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(in && out && P >= 0 && H >= 2 && W >= 2);
+  if (P == 0) return 0;
+  int64_t blocks = cdiv64(P * (H / 2) * (W / 2), 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  avg_pool2x2_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(in, out, P, H, W);
+  return MRFA_LAUNCH_RESULT();
+}

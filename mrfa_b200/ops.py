@@ -1,0 +1,469 @@
+"""torch custom ops (`torch.ops.mrfa.*`) over the C ABI of libmrfa_b200.so.
+
+Each op has a CUDA implementation (a ctypes call that launches hand-written sm_100a kernels on
+the current stream), a fake implementation (shape inference) and, where the reference
+differentiates through it, an autograd formula.  There is no CPU implementation on purpose:
+calling an op with CPU tensors raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import GridStrides, check, lib
+
+_c = _lib.ctypes
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else _c.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: Tensor, name: str, dtype=torch.float32) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"mrfa_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"mrfa_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _grid_strides(grid: Tensor) -> GridStrides:
+    s = grid.stride()
+    return GridStrides(s[0], s[1], s[2], s[3])
+
+
+_SM_COUNT = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+# ------------------------------------------------------------------------------------------
+# bilinear warps
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("mrfa::grid_sample", mutates_args=(), device_types="cuda")
+def grid_sample(inp: Tensor, grid: Tensor, coord_mode: int, padding_mode: int, add_identity: bool,
+                in_batch_div: int) -> Tensor:
+    inp = _req(inp, "input")
+    if not grid.is_cuda or grid.dtype != torch.float32 or grid.dim() != 4 or grid.shape[-1] != 2:
+        raise RuntimeError("mrfa_b200: grid must be a CUDA float32 tensor of logical shape (N,Ho,Wo,2)")
+    N, Ho, Wo, _ = grid.shape
+    Nin, C, H, W = inp.shape
+    if Nin * in_batch_div != N:
+        raise RuntimeError(f"mrfa_b200: grid batch {N} != input batch {Nin} * {in_batch_div}")
+    out = torch.empty((N, C, Ho, Wo), device=inp.device, dtype=torch.float32)
+    with torch.cuda.device(inp.device):
+        check(lib.mrfa_grid_sample_fwd(_p(inp), _p(grid), _grid_strides(grid), _p(out), N, C, H, W, Ho, Wo,
+                                       in_batch_div, coord_mode, padding_mode, int(add_identity), _stream()),
+              "mrfa_grid_sample_fwd")
+    return out
+
+
+@grid_sample.register_fake
+def _(inp, grid, coord_mode, padding_mode, add_identity, in_batch_div):
+    return inp.new_empty((grid.shape[0], inp.shape[1], grid.shape[1], grid.shape[2]))
+
+
+@torch.library.custom_op("mrfa::grid_sample_bwd", mutates_args=(), device_types="cuda")
+def grid_sample_bwd(grad_out: Tensor, inp: Tensor, grid: Tensor, coord_mode: int, padding_mode: int,
+                    add_identity: bool, in_batch_div: int, need_input: bool, need_grid: bool) -> Tuple[Tensor, Tensor]:
+    grad_out = _req(grad_out, "grad_out")
+    inp = _req(inp, "input")
+    N, Ho, Wo, _ = grid.shape
+    _, C, H, W = inp.shape
+    g_in = torch.zeros_like(inp) if need_input else inp.new_empty(0)
+    g_grid = torch.empty((N, Ho, Wo, 2), device=inp.device, dtype=torch.float32) if need_grid else inp.new_empty(0)
+    with torch.cuda.device(inp.device):
+        check(lib.mrfa_grid_sample_bwd(_p(grad_out), _p(inp), _p(grid), _grid_strides(grid),
+                                       _p(g_in) if need_input else None, _p(g_grid) if need_grid else None,
+                                       N, C, H, W, Ho, Wo, in_batch_div, coord_mode, padding_mode, int(add_identity),
+                                       _stream()), "mrfa_grid_sample_bwd")
+    return g_in, g_grid
+
+
+@grid_sample_bwd.register_fake
+def _(grad_out, inp, grid, coord_mode, padding_mode, add_identity, in_batch_div, need_input, need_grid):
+    return (torch.empty_like(inp) if need_input else inp.new_empty(0),
+            inp.new_empty(tuple(grid.shape)) if need_grid else inp.new_empty(0))
+
+
+def _gs_setup(ctx, inputs, output):
+    inp, grid, coord_mode, padding_mode, add_identity, in_batch_div = inputs
+    ctx.save_for_backward(inp, grid)
+    ctx.cfg = (coord_mode, padding_mode, add_identity, in_batch_div)
+
+
+def _gs_backward(ctx, grad_out):
+    inp, grid = ctx.saved_tensors
+    need_input, need_grid = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    g_in, g_grid = torch.ops.mrfa.grid_sample_bwd(grad_out, inp, grid, *ctx.cfg, need_input, need_grid)
+    return (g_in if need_input else None, g_grid if need_grid else None, None, None, None, None)
+
+
+grid_sample.register_autograd(_gs_backward, setup_context=_gs_setup)
+
+
+@torch.library.custom_op("mrfa::dual_warp", mutates_args=(), device_types="cuda")
+def dual_warp(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Tensor]:
+    inp, flow, prior_grid = _req(inp, "input"), _req(flow, "flow"), _req(prior_grid, "prior_grid")
+    N, C, H, W = inp.shape
+    if tuple(flow.shape) != (N, 2, H, W) or tuple(prior_grid.shape) != (N, H, W, 2):
+        raise RuntimeError("mrfa_b200: dual_warp expects flow (N,2,H,W) and prior_grid (N,H,W,2) at the feature size")
+    out_r, out_c = torch.empty_like(inp), torch.empty_like(inp)
+    with torch.cuda.device(inp.device):
+        check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, _stream()),
+              "mrfa_dual_warp_fwd")
+    return out_r, out_c
+
+
+@dual_warp.register_fake
+def _(inp, flow, prior_grid):
+    return torch.empty_like(inp), torch.empty_like(inp)
+
+
+def _dw_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _dw_backward(ctx, g_r, g_c):
+    inp, flow, prior = ctx.saved_tensors
+    ni, nf, npg = ctx.needs_input_grad
+    gi = gf = gp = None
+    a, b = torch.ops.mrfa.grid_sample_bwd(g_r, inp, flow.permute(0, 2, 3, 1), _lib.COORD_PIXEL, _lib.PAD_ZEROS, True, 1,
+                                          ni, nf)
+    c, d = torch.ops.mrfa.grid_sample_bwd(g_c, inp, prior, _lib.COORD_NORM_ACF, _lib.PAD_ZEROS, False, 1, ni, npg)
+    if ni:
+        gi = a + c
+    if nf:
+        gf = b.permute(0, 3, 1, 2)
+    if npg:
+        gp = d
+    return gi, gf, gp
+
+
+dual_warp.register_autograd(_dw_backward, setup_context=_dw_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# grids / heat-maps (no autograd needed for the grids; kp2gaussian differentiates w.r.t. kp)
+# ------------------------------------------------------------------------------------------
+def coords_grid_cuda(batch: int, ht: int, wd: int, device) -> Tensor:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("mrfa_b200: coords_grid needs a CUDA device (there is no CPU fallback)")
+    out = torch.empty((batch, 2, ht, wd), device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        check(lib.mrfa_coords_grid(_p(out), batch, ht, wd, _stream()), "mrfa_coords_grid")
+    return out
+
+
+def make_coordinate_grid_cuda(h: int, w: int, device) -> Tensor:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("mrfa_b200: make_coordinate_grid needs a CUDA device (there is no CPU fallback)")
+    out = torch.empty((h, w, 2), device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        check(lib.mrfa_make_coordinate_grid(_p(out), h, w, _stream()), "mrfa_make_coordinate_grid")
+    return out
+
+
+@torch.library.custom_op("mrfa::kp2gaussian", mutates_args=(), device_types="cuda")
+def kp2gaussian(kp: Tensor, add: Optional[Tensor], h: int, w: int, variance: float) -> Tensor:
+    kp = _req(kp, "kp")
+    P = kp.numel() // 2
+    period = 0
+    if add is not None:
+        add = _req(add, "add")
+        period = add.numel() // (h * w)
+    out = torch.empty(tuple(kp.shape[:-1]) + (h, w), device=kp.device, dtype=torch.float32)
+    with torch.cuda.device(kp.device):
+        check(lib.mrfa_kp2gaussian(_p(kp), _p(add), period, _p(out), P, h, w, variance, _stream()), "mrfa_kp2gaussian")
+    return out
+
+
+@kp2gaussian.register_fake
+def _(kp, add, h, w, variance):
+    return kp.new_empty(tuple(kp.shape[:-1]) + (h, w))
+
+
+def _kp2g_setup(ctx, inputs, output):
+    kp, add, h, w, variance = inputs
+    ctx.save_for_backward(kp)
+    ctx.cfg = (add is not None and tuple(add.shape), h, w, variance)
+
+
+def _kp2g_backward(ctx, g):
+    (kp,) = ctx.saved_tensors
+    add_shape, h, w, variance = ctx.cfg
+    gk = ga = None
+    if ctx.needs_input_grad[0]:
+        # d/dkp exp(-0.5*|x-kp|^2/var) = gauss * (x-kp)/var ; tiny, recomputed with the grid kernel
+        grid = make_coordinate_grid_cuda(h, w, kp.device)
+        diff = grid.view((1,) * (kp.dim() - 1) + (h, w, 2)) - kp.view(tuple(kp.shape[:-1]) + (1, 1, 2))
+        gauss = torch.exp(-0.5 * (diff ** 2).sum(-1) / variance)
+        gk = ((g * gauss).unsqueeze(-1) * diff / variance).sum(dim=(-3, -2))
+    if ctx.needs_input_grad[1] and add_shape:
+        ga = g.reshape((-1,) + add_shape).sum(0)
+    return gk, ga, None, None, None
+
+
+kp2gaussian.register_autograd(_kp2g_backward, setup_context=_kp2g_setup)
+
+
+@torch.library.custom_op("mrfa::prior_to_flow", mutates_args=(), device_types="cuda")
+def prior_to_flow(deformation: Tensor, hm1: float) -> Tensor:
+    deformation = _req(deformation, "deformation")
+    B, h, w, _ = deformation.shape
+    out = torch.empty((B, 2, h, w), device=deformation.device, dtype=torch.float32)
+    with torch.cuda.device(deformation.device):
+        check(lib.mrfa_prior_to_flow(_p(deformation), _p(out), B, h, w, hm1, _stream()), "mrfa_prior_to_flow")
+    return out
+
+
+@prior_to_flow.register_fake
+def _(deformation, hm1):
+    B, h, w, _ = deformation.shape
+    return deformation.new_empty((B, 2, h, w))
+
+
+def _p2f_setup(ctx, inputs, output):
+    ctx.hm1 = inputs[1]
+
+
+def _p2f_backward(ctx, g):
+    return g.permute(0, 2, 3, 1) * (ctx.hm1 / 2.0), None
+
+
+prior_to_flow.register_autograd(_p2f_backward, setup_context=_p2f_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# prior dense motion
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("mrfa::dense_motion_prior", mutates_args=(), device_types="cuda")
+def dense_motion_prior(kp_d: Tensor, kp_s: Tensor, jac_d: Optional[Tensor], jac_s: Optional[Tensor],
+                       bg_param: Optional[Tensor], source: Tensor, variance: float) -> Tuple[Tensor, Tensor]:
+    kp_d, kp_s, source = _req(kp_d, "kp_driving"), _req(kp_s, "kp_source"), _req(source, "source")
+    jac_d = None if jac_d is None else _req(jac_d, "jac_driving")
+    jac_s = None if jac_s is None else _req(jac_s, "jac_source")
+    bg_param = None if bg_param is None else _req(bg_param, "bg_param")
+    B, K, _ = kp_d.shape
+    _, C, h, w = source.shape
+    motions = torch.empty((B, K + 1, h, w, 2), device=source.device, dtype=torch.float32)
+    hg_input = torch.empty((B, (K + 1) * (C + 1), h, w), device=source.device, dtype=torch.float32)
+    with torch.cuda.device(source.device):
+        check(lib.mrfa_dense_motion_prior(_p(kp_d), _p(kp_s), _p(jac_d), _p(jac_s), _p(bg_param), _p(source),
+                                          _p(motions), _p(hg_input), B, K, C, h, w, variance, _stream()),
+              "mrfa_dense_motion_prior")
+    return motions, hg_input
+
+
+@dense_motion_prior.register_fake
+def _(kp_d, kp_s, jac_d, jac_s, bg_param, source, variance):
+    B, K, _ = kp_d.shape
+    _, C, h, w = source.shape
+    return source.new_empty((B, K + 1, h, w, 2)), source.new_empty((B, (K + 1) * (C + 1), h, w))
+
+
+@torch.library.custom_op("mrfa::tps_solve", mutates_args=(), device_types="cuda")
+def tps_solve(kp_1: Tensor, kp_2: Tensor) -> Tuple[Tensor, Tensor]:
+    kp_1, kp_2 = _req(kp_1, "kp_1"), _req(kp_2, "kp_2")
+    B, G, n, _ = kp_1.shape
+    if n != 5:
+        raise RuntimeError("mrfa_b200: tps_solve is specialised for 5 control points per transformation")
+    theta = torch.empty((B, G, 2, 3), device=kp_1.device, dtype=torch.float32)
+    params = torch.empty((B, G, n, 2), device=kp_1.device, dtype=torch.float32)
+    with torch.cuda.device(kp_1.device):
+        check(lib.mrfa_tps_solve(_p(kp_1), _p(kp_2), _p(theta), _p(params), B * G, _stream()), "mrfa_tps_solve")
+    return theta, params
+
+
+@tps_solve.register_fake
+def _(kp_1, kp_2):
+    B, G, n, _ = kp_1.shape
+    return kp_1.new_empty((B, G, 2, 3)), kp_1.new_empty((B, G, n, 2))
+
+
+@torch.library.custom_op("mrfa::tps_motion_prior", mutates_args=(), device_types="cuda")
+def tps_motion_prior(kp_d: Tensor, kp_s: Tensor, theta: Tensor, control_params: Tensor, bg_param: Optional[Tensor],
+                     source: Tensor, variance: float) -> Tuple[Tensor, Tensor]:
+    kp_d, kp_s, source = _req(kp_d, "kp_driving"), _req(kp_s, "kp_source"), _req(source, "source")
+    theta, control_params = _req(theta, "theta"), _req(control_params, "control_params")
+    bg_param = None if bg_param is None else _req(bg_param, "bg_param")
+    B, G = theta.shape[:2]
+    _, C, h, w = source.shape
+    motions = torch.empty((B, G + 1, h, w, 2), device=source.device, dtype=torch.float32)
+    hg_input = torch.empty((B, G * 5 + 1 + (G + 1) * C, h, w), device=source.device, dtype=torch.float32)
+    with torch.cuda.device(source.device):
+        check(lib.mrfa_tps_motion_prior(_p(kp_d), _p(kp_s), _p(theta), _p(control_params), _p(bg_param), _p(source),
+                                        _p(motions), _p(hg_input), B, G, C, h, w, variance, _stream()),
+              "mrfa_tps_motion_prior")
+    return motions, hg_input
+
+
+@tps_motion_prior.register_fake
+def _(kp_d, kp_s, theta, control_params, bg_param, source, variance):
+    B, G = theta.shape[:2]
+    _, C, h, w = source.shape
+    return source.new_empty((B, G + 1, h, w, 2)), source.new_empty((B, G * 5 + 1 + (G + 1) * C, h, w))
+
+
+# ------------------------------------------------------------------------------------------
+# correlation volume + pyramid, lookup
+# ------------------------------------------------------------------------------------------
+def corr_rows_total(h: int, w: int) -> int:
+    return int(lib.mrfa_corr_rows_total(h, w))
+
+
+def corr_row_offset(h: int, w: int, pool_log2: int) -> int:
+    return int(lib.mrfa_corr_row_offset(h, w, pool_log2))
+
+
+@torch.library.custom_op("mrfa::corr_pyramid", mutates_args=(), device_types="cuda")
+def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
+    """(B,C,h,w) x2 -> volume0 (B, rows_total, h*w) bf16, volume1 (B, rows_total, h*w/4) bf16."""
+    q_d, k_s = _req(q_d, "q_d"), _req(k_s, "k_s")
+    B, C, h, w = q_d.shape
+    rows = corr_rows_total(h, w)
+    dev = q_d.device
+    a_op = torch.empty((B, rows, C), device=dev, dtype=torch.bfloat16)
+    b_op = torch.empty((B, h * w, C), device=dev, dtype=torch.bfloat16)
+    vol0 = torch.empty((B, rows, h * w), device=dev, dtype=torch.bfloat16)
+    vol1 = torch.empty((B, rows, (h * w) // 4), device=dev, dtype=torch.bfloat16)
+    with torch.cuda.device(dev):
+        st = _stream()
+        check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, st), "mrfa_corr_pack")
+        check(lib.mrfa_corr_volume(_p(a_op), _p(b_op), _p(vol0), _p(vol1), B, C, h, w, scale, sm_count(dev), st),
+              "mrfa_corr_volume")
+    return vol0, vol1
+
+
+@corr_pyramid.register_fake
+def _(q_d, k_s, scale):
+    B, C, h, w = q_d.shape
+    rows = h * w + (h * w) // 4 + (h * w) // 16 + (h * w) // 64
+    return (q_d.new_empty((B, rows, h * w), dtype=torch.bfloat16),
+            q_d.new_empty((B, rows, (h * w) // 4), dtype=torch.bfloat16))
+
+
+def corr_pack_debug(q_d: Tensor, k_s: Tensor) -> Tuple[Tensor, Tensor]:
+    """Packed bf16 operands only (test / profiling helper)."""
+    q_d, k_s = _req(q_d, "q_d"), _req(k_s, "k_s")
+    B, C, h, w = q_d.shape
+    a_op = torch.empty((B, corr_rows_total(h, w), C), device=q_d.device, dtype=torch.bfloat16)
+    b_op = torch.empty((B, h * w, C), device=q_d.device, dtype=torch.bfloat16)
+    with torch.cuda.device(q_d.device):
+        check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, _stream()), "mrfa_corr_pack")
+    return a_op, b_op
+
+
+@torch.library.custom_op("mrfa::avg_pool2x2", mutates_args=(), device_types="cuda")
+def avg_pool2x2(x: Tensor) -> Tensor:
+    x = _req(x, "x")
+    H, W = x.shape[-2:]
+    P = x.numel() // (H * W)
+    out = torch.empty(tuple(x.shape[:-2]) + (H // 2, W // 2), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib.mrfa_avg_pool2x2(_p(x), _p(out), P, H, W, _stream()), "mrfa_avg_pool2x2")
+    return out
+
+
+@avg_pool2x2.register_fake
+def _(x):
+    return x.new_empty(tuple(x.shape[:-2]) + (x.shape[-2] // 2, x.shape[-1] // 2))
+
+
+def _ap_setup(ctx, inputs, output):
+    ctx.shape = tuple(inputs[0].shape)
+
+
+def _ap_backward(ctx, g):
+    H, W = ctx.shape[-2:]
+    up = (g * 0.25).repeat_interleave(2, dim=-2).repeat_interleave(2, dim=-1)
+    if up.shape[-2] != H or up.shape[-1] != W:
+        up = torch.nn.functional.pad(up, (0, W - up.shape[-1], 0, H - up.shape[-2]))
+    return up
+
+
+avg_pool2x2.register_autograd(_ap_backward, setup_context=_ap_setup)
+
+
+@torch.library.custom_op("mrfa::corr_lookup", mutates_args=(), device_types="cuda")
+def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, map_batch_stride: int,
+                row_offset: int, radius: int) -> Tensor:
+    """coords (B,2,h1,w1) -> (B, 2*(2r+1)^2, h1, w1).  level maps fp32 or bf16 (see the header)."""
+    coords = _req(coords, "coords")
+    if level0.dtype != level1.dtype or level0.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("mrfa_b200: correlation levels must both be float32 or both bfloat16")
+    if not (level0.is_cuda and level0.is_contiguous() and level1.is_contiguous()):
+        raise RuntimeError("mrfa_b200: correlation levels must be contiguous CUDA tensors")
+    B, _, h1, w1 = coords.shape
+    n = 2 * radius + 1
+    out = torch.empty((B, 2 * n * n, h1, w1), device=coords.device, dtype=torch.float32)
+    with torch.cuda.device(coords.device):
+        check(lib.mrfa_corr_lookup_fwd(_p(level0), _p(level1), int(level0.dtype == torch.bfloat16), _p(coords), _p(out),
+                                       B, h1 * w1, H, W, map_batch_stride, row_offset, radius, _stream()),
+              "mrfa_corr_lookup_fwd")
+    return out
+
+
+@corr_lookup.register_fake
+def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius):
+    B, _, h1, w1 = coords.shape
+    return coords.new_empty((B, 2 * (2 * radius + 1) ** 2, h1, w1))
+
+
+@torch.library.custom_op("mrfa::corr_lookup_bwd", mutates_args=(), device_types="cuda")
+def corr_lookup_bwd(grad_out: Tensor, level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int,
+                    map_batch_stride: int, row_offset: int, radius: int, need_levels: bool,
+                    need_coords: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    grad_out, coords = _req(grad_out, "grad_out"), _req(coords, "coords")
+    B, _, h1, w1 = coords.shape
+    dev = coords.device
+    g0 = torch.zeros(level0.shape, device=dev, dtype=torch.float32) if need_levels else coords.new_empty(0)
+    g1 = torch.zeros(level1.shape, device=dev, dtype=torch.float32) if need_levels else coords.new_empty(0)
+    gc = torch.empty_like(coords) if need_coords else coords.new_empty(0)
+    with torch.cuda.device(dev):
+        check(lib.mrfa_corr_lookup_bwd(_p(grad_out), _p(level0), _p(level1), int(level0.dtype == torch.bfloat16),
+                                       _p(coords), _p(g0) if need_levels else None, _p(g1) if need_levels else None,
+                                       _p(gc) if need_coords else None, B, h1 * w1, H, W, map_batch_stride,
+                                       row_offset, radius, _stream()), "mrfa_corr_lookup_bwd")
+    return g0, g1, gc
+
+
+@corr_lookup_bwd.register_fake
+def _(grad_out, level0, level1, coords, H, W, map_batch_stride, row_offset, radius, need_levels, need_coords):
+    f = lambda t: coords.new_empty(tuple(t.shape)) if need_levels else coords.new_empty(0)
+    return f(level0), f(level1), torch.empty_like(coords) if need_coords else coords.new_empty(0)
+
+
+def _cl_setup(ctx, inputs, output):
+    level0, level1, coords, H, W, mbs, ro, radius = inputs
+    ctx.save_for_backward(level0, level1, coords)
+    ctx.cfg = (H, W, mbs, ro, radius)
+
+
+def _cl_backward(ctx, g):
+    level0, level1, coords = ctx.saved_tensors
+    need_levels = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+    need_coords = ctx.needs_input_grad[2]
+    g0, g1, gc = torch.ops.mrfa.corr_lookup_bwd(g, level0, level1, coords, *ctx.cfg, need_levels, need_coords)
+    return (g0.to(level0.dtype) if ctx.needs_input_grad[0] else None,
+            g1.to(level1.dtype) if ctx.needs_input_grad[1] else None,
+            gc if need_coords else None, None, None, None, None, None)
+
+
+corr_lookup.register_autograd(_cl_backward, setup_context=_cl_setup)

@@ -1,0 +1,189 @@
+"""RaftFlow: the coarse-to-fine non-prior motion refinement decoder (reference:
+modules/raft.py:50-311), with the correlation volume / pyramid / lookup and every feature warp
+running on the hand-written kernels.  Same constructor kwargs (config/vox1.yaml:45-64), forward
+signature, return values and state_dict keys as the reference class.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import sampling
+from .blocks import Hourglass, OcclusionAwareGenerator
+from .corr import CorrPyramid
+
+
+def _resize(x, size):
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+
+
+class BasicMotionEncoder(nn.Module):
+    """raft.py:50-68: (flow, correlation features) -> 128-channel motion feature."""
+
+    def __init__(self, num_levels=2, radius=3):
+        super().__init__()
+        planes = num_levels * (2 * radius + 1) ** 2
+        self.convc1 = nn.Conv2d(planes, 128, 1, padding=0)
+        self.convc2 = nn.Conv2d(128, 96, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 96, 128 - 2, 3, padding=1)
+
+    def forward(self, delta_flow, corr):
+        c = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        f = F.relu(self.convf2(F.relu(self.convf1(delta_flow))))
+        y = F.relu(self.conv(torch.cat([c, f], dim=1)))
+        return torch.cat([y, delta_flow], dim=1)
+
+
+class RefineFlow(nn.Module):
+    """raft.py:70-87: motion feature + warped-source context -> (d_flow(2) ++ d_occ(1))."""
+
+    def __init__(self):
+        super().__init__()
+        self.convc1 = nn.Conv2d(192, 128, 3, padding=1)
+        self.conv1 = nn.Conv2d(256, 128, 3, padding=1)
+        self.conv2 = nn.Conv2d(128, 2, 3, padding=1)
+        self.convo1 = nn.Conv2d(256, 128, 3, padding=1)
+        self.convo2 = nn.Conv2d(128, 1, 3, padding=1)
+
+    def forward(self, m_f, warp_f):
+        inp = torch.cat([m_f, F.relu(self.convc1(warp_f))], dim=1)
+        flow = self.conv2(F.relu(self.conv1(inp)))
+        occ = self.convo2(F.relu(self.convo1(inp)))
+        return torch.cat([flow, occ], dim=1), inp
+
+
+class RaftFlow(nn.Module):
+    def __init__(self, prior_only=False, num_kp=10, dim=256, size=256, generator=None, driving_encoder=None,
+                 source_encoder=None):
+        super().__init__()
+        self.scale = dim ** -0.5
+        self.size = size
+        self.h = self.w = size // 4                       # basic flow resolution of the prior
+        self.prior_only = prior_only
+        self.generator = OcclusionAwareGenerator(**generator)
+        widths = (512, 512, 512, 256, 128, 64)             # raft.py:105-113, coarsest first
+        self.total_iter = self.num_iter = int(math.log(2 ** 5, 2)) + 1
+        self.basic_res_index = int(math.log(self.h // (size // 32), 2))
+        if self.prior_only:
+            return
+        self.kp = Hourglass(**driving_encoder)
+        self.kp_img = Hourglass(**source_encoder)
+        self.kp_head = nn.Conv2d(self.kp.out_filters, dim, kernel_size=1, padding=0)
+        self.kp_img_head = nn.Conv2d(self.kp_img.out_filters, dim, kernel_size=1, padding=0)
+        self.pos_embedding = nn.Parameter(torch.zeros(1, num_kp, self.h, self.w))
+        nn.init.trunc_normal_(self.pos_embedding, std=.02)
+        self.corr_enc = BasicMotionEncoder()
+        self.refine = RefineFlow()
+        self.to_context = nn.ModuleList(nn.Conv2d(widths[i], 192, 1, padding=0) for i in range(self.num_iter))
+
+    # ------------------------------------------------------------------ raft.py:155-173
+    def _forward_prior_only(self, feature, dense_motion, img_full):
+        grid, occ = dense_motion["deformation"], dense_motion["occlusion"]
+        warps, occs = [], []
+        g = grid
+        for f in feature:
+            if grid.shape[2] != f.shape[2]:
+                g = _resize(grid.permute(0, 3, 1, 2), f.shape[2:]).permute(0, 2, 3, 1)
+                o = _resize(occ, f.shape[2:])
+            else:
+                g, o = grid, occ
+            warps.append(sampling.grid_sample(f, g))
+            occs.append(torch.sigmoid(o))
+        warp_img = sampling.grid_sample(img_full, g)
+        out = self.generator.decode(warps, warp_img, occs)
+        occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in occs], dim=3)
+        return out, warp_img, occlusion
+
+    def structure_features(self, kp_s, kp_d, img):
+        """raft.py:177-182: Gaussian key-point maps (+ positional embedding) -> q_d, k_s."""
+        h, w = img.shape[2:]
+        g_s = torch.ops.mrfa.kp2gaussian(kp_s, self.pos_embedding, h, w, 0.1)
+        g_d = torch.ops.mrfa.kp2gaussian(kp_d, self.pos_embedding, h, w, 0.1)
+        k_s = self.kp_img_head(self.kp_img(torch.cat([g_s, img], dim=1)))
+        q_d = self.kp_head(self.kp(g_d))
+        return q_d, k_s
+
+    def forward(self, kp_s, kp_d, dense_motion, img, img_full):
+        feature = self.generator.encode(img_full)
+        if img is None:
+            raise RuntimeError("RaftFlow.forward needs `img` (the reference's self.down is commented out, raft.py:102)")
+        if self.prior_only:
+            return self._forward_prior_only(feature, dense_motion, img_full)
+        B = img.shape[0]
+        dev = img.device
+        h, w, base = self.h, self.w, self.basic_res_index
+
+        # structure correlation volume + pyramid at the basic resolution (raft.py:177-186, :208)
+        q_d, k_s = self.structure_features(kp_s, kp_d, img)
+        pyramid = CorrPyramid(q_d, k_s, self.scale)
+
+        prior = dense_motion["deformation"]
+        prior_occ = dense_motion["occlusion"]
+        init_flow = torch.ops.mrfa.prior_to_flow(prior, float(self.h - 1))                    # raft.py:189-190
+        flow = F.interpolate(init_flow, scale_factor=1.0 / 8.0, mode="bilinear", align_corners=True) / 8.0
+        occlusion = F.interpolate(prior_occ, scale_factor=1.0 / 8.0, mode="bilinear", align_corners=True)
+        prior_nchw = prior.permute(0, 3, 1, 2)
+        ident_basic = sampling.coords_grid(B, h, w, dev)
+
+        out_warp_f, out_occlusion, out_warp_f_c, out_occlusion_c = [], [], [], []
+        d_f_pre = d_occ_pre = None
+        for i in range(self.total_iter):
+            R = self.size // 32 * 2 ** i
+            # ---- correlation features at this level (raft.py:217-243) ----
+            if i < base:
+                k = 2 ** (base - i)
+                coords = (flow + sampling.coords_grid(B, R, R, dev)) * k
+                corr = pyramid.block(base - i)(coords)
+            elif i == base:
+                corr = pyramid.block(0)(flow + ident_basic)
+            else:
+                flow_sample = _resize(flow, (self.h, self.h)) * 0.5 ** (i - base)
+                corr = _resize(pyramid.block(0)(flow_sample + ident_basic), (R, R))
+            m_f = self.corr_enc(flow, corr)
+
+            # ---- warps of feature[i]: refined (at flow) and coarse (prior grid) in one pass ----
+            if i != base:
+                prior_grid = _resize(prior_nchw, (R, R)).permute(0, 2, 3, 1).contiguous()
+                occ_res = _resize(prior_occ, (R, R))
+            else:
+                prior_grid, occ_res = prior, prior_occ
+            warp_f, warp_c = torch.ops.mrfa.dual_warp(feature[i], flow, prior_grid)       # raft.py:247, :271
+            warp_f = F.relu(self.to_context[i](warp_f))
+
+            d_flow, _ = self.refine(m_f, warp_f)
+            flow_w = flow + d_flow[:, 0:2]
+            d_occ = d_flow[:, 2:]
+            occlusion = occlusion + d_occ
+
+            out_warp_f.append(sampling.warp_by_flow(feature[i], flow_w))                     # raft.py:260
+            out_occlusion.append(torch.sigmoid(occlusion))
+            out_warp_f_c.append(warp_c)
+            out_occlusion_c.append(torch.sigmoid(occ_res))
+
+            # ---- carry flow / occlusion to the next resolution (raft.py:276-295) ----
+            if i < self.num_iter - 1:
+                R2 = 2 * R
+                scale = 2 ** (base - i) / 2.0
+                d_f = _resize(d_flow[:, 0:2], (R2, R2)) * 2
+                flow = d_f + _resize(init_flow, (R2, R2)) / scale
+                d_o = _resize(d_occ, (R2, R2))
+                occlusion = d_o + _resize(prior_occ, (R2, R2))
+                if i == 0:
+                    d_f_pre, d_occ_pre = d_f, d_o
+                else:
+                    up_f = _resize(d_f_pre, (R2, R2)) * 2
+                    up_o = _resize(d_occ_pre, (R2, R2))
+                    flow = flow + up_f
+                    occlusion = occlusion + up_o
+                    d_f_pre, d_occ_pre = d_f + up_f, d_o + up_o
+
+        warp_img = sampling.warp_by_flow(img_full, flow)                                   # raft.py:302
+        out = self.generator.decode(out_warp_f, warp_img, out_occlusion, out_warp_f_c, out_occlusion_c)
+        vis = out_occlusion + [torch.sigmoid(prior_occ)]
+        occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in vis], dim=3)
+        return out, warp_img, occlusion

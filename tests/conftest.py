@@ -14,6 +14,13 @@ warnings.filterwarnings("ignore", message=".*indexing argument.*")
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+try:  # parity tests compare against fp32 CPU results: keep cuDNN / cuBLAS in true fp32
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+except Exception:  # pragma: no cover
+    pass
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -1,0 +1,406 @@
+"""GPU parity tests: every kernel of libmrfa_b200 (through the C ABI / torch custom ops)
+against the CPU oracle and the golden vectors of the unmodified reference.
+
+Tolerances (BASELINE.json north_star): bit-exact for index / coordinate-grid construction,
+1e-5 abs for fp32 warps and lookups, 2e-2 relative for the bf16 correlation.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import np_ops as O                      # noqa: E402
+from oracle import torch_path as TP                 # noqa: E402
+
+DEV = "cuda"
+
+
+def mb():
+    import mrfa_b200
+    return mrfa_b200
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def close(a, b, atol=1e-5, rtol=0.0):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a.astype(np.float64), b.astype(np.float64), atol=atol, rtol=rtol)
+
+
+def rel_close(a, b, rel=2e-2):
+    """|a-b| <= rel * (|b| + rms(b)): relative tolerance with an rms floor for near-zero entries."""
+    a = a.detach().float().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().float().cpu().numpy().astype(np.float64) if torch.is_tensor(b) else np.asarray(b, np.float64)
+    rms = np.sqrt((b ** 2).mean())
+    bad = np.abs(a - b) > rel * (np.abs(b) + rms)
+    assert not bad.any(), f"{bad.sum()} / {bad.size} outside {rel} rel; max abs err {np.abs(a - b).max():.4g}, rms {rms:.4g}"
+
+
+# ------------------------------------------------------------------ no CPU fallback
+def test_cpu_tensors_are_rejected():
+    m = mb()
+    with pytest.raises(Exception):
+        m.bilinear_sampler(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 2, 2))
+    with pytest.raises(Exception):
+        m.coords_grid(1, 2, 2, "cpu")
+
+
+# ------------------------------------------------------------------ grids: bit-exact
+def test_grids_bit_exact(golden):
+    m, g = mb(), golden("grids")
+    for (h, w) in ((2, 3), (16, 16), (64, 64), (5, 7), (128, 128)):
+        out = m.make_coordinate_grid((h, w), "torch.cuda.FloatTensor").cpu().numpy()
+        assert np.array_equal(out, g[f"mcg_{h}x{w}"])
+    for (b, h, w) in ((1, 2, 3), (2, 8, 8), (1, 64, 64)):
+        assert np.array_equal(m.coords_grid(b, h, w, DEV).cpu().numpy(), g[f"cg_{b}_{h}x{w}"])
+    assert np.array_equal(m.coords_grid(3, 256, 256, DEV).cpu().numpy(), O.coords_grid(3, 256, 256))
+    assert np.array_equal(m.make_coordinate_grid((256, 192), "torch.cuda.FloatTensor").cpu().numpy(),
+                          O.make_coordinate_grid(256, 192))
+
+
+def test_kp2gaussian(golden):
+    m, g = mb(), golden("grids")
+    kp = cu(g["kp"])
+    close(m.kp2gaussian(kp, (16, 16), 0.1), g["kp2g_16_0.1"], 1e-6)
+    close(m.kp2gaussian(kp, (16, 16), 0.01), g["kp2g_16_0.01"], 1e-6)
+    close(m.kp2gaussian(kp, (12, 20), 0.01), g["kp2g_12x20_0.01"], 1e-6)
+    pos = torch.randn(1, 10, 16, 16, device=DEV) * 0.02
+    out = torch.ops.mrfa.kp2gaussian(kp, pos, 16, 16, 0.1)
+    close(out, g["kp2g_16_0.1"] + pos.cpu().numpy(), 1e-6)
+
+
+# ------------------------------------------------------------------ warps
+def test_samplers_golden(golden):
+    m, s = mb(), golden("samplers")
+    img = cu(s["img"])
+    close(m.bilinear_sampler(img, cu(s["pix_coords"])), s["bilinear_sampler"])
+    _, mask = m.bilinear_sampler(img, cu(s["pix_coords"]), mask=True)
+    assert np.array_equal(mask.cpu().numpy(), s["bilinear_sampler_mask"])
+    close(m.grid_sample(img, cu(s["norm_grid"])), s["grid_sample_acF"])
+    close(m.grid_sample(img, cu(s["norm_grid"]), align_corners=True), s["grid_sample_acT"])
+    close(m.grid_sample(img, cu(s["norm_grid"]) * 1.7, padding_mode="reflection"), s["grid_sample_reflect_acF"])
+    close(m.batch_bilinear_sampler(cu(s["bimg"]), cu(s["bco"]), h=2, w=2, mini_batch=1), s["batch_bilinear_mb1"])
+    out = m.batch_bilinear_sampler(cu(s["bimg"]), cu(s["bco"]), h=2, w=2, mini_batch=2)
+    assert tuple(out.shape) == (8, 1, 3, 3)
+    close(out, s["batch_bilinear_mb2"])
+    close(m.deform_input(cu(s["feat"]), cu(s["prior"])), s["coarse_warp"])
+
+
+@pytest.mark.parametrize("C,R", [(512, 8), (512, 16), (256, 64), (64, 128), (3, 256), (5, 37)])
+def test_feature_warp_shapes(C, R):
+    """The six feature-warp shapes of RaftFlow (reduced batch) + a ragged one, all conventions."""
+    m = mb()
+    torch.manual_seed(C * R)
+    B = 2
+    feat = torch.randn(B, C, R, R)
+    flow = torch.randn(B, 2, R, R) * 2.5               # some taps leave the image
+    ident = TP.coords_grid(B, R, R)
+    ref = TP.bilinear_sampler(feat, (flow + ident).permute(0, 2, 3, 1))
+    close(m.warp_by_flow(feat.to(DEV), flow.to(DEV)), ref)
+    close(m.bilinear_sampler(feat.to(DEV), (flow + ident).permute(0, 2, 3, 1).to(DEV)), ref)
+    grid = TP.make_coordinate_grid((R, R))[None].repeat(B, 1, 1, 1) + torch.randn(B, R, R, 2) * 0.1
+    close(m.grid_sample(feat.to(DEV), grid.to(DEV)), F.grid_sample(feat, grid, align_corners=False))
+    close(m.grid_sample(feat.to(DEV), grid.to(DEV), align_corners=True), F.grid_sample(feat, grid, align_corners=True))
+    a, b = torch.ops.mrfa.dual_warp(feat.to(DEV), flow.to(DEV), grid.to(DEV))
+    close(a, ref)
+    close(b, F.grid_sample(feat, grid, align_corners=False))
+
+
+def test_warp_edge_cases():
+    m = mb()
+    feat = torch.randn(1, 2, 4, 4, device=DEV)
+    # everything out of the image -> zeros; NaN / inf coordinates -> zeros, no fault
+    far = torch.full((1, 3, 3, 2), 1e6, device=DEV)
+    assert m.bilinear_sampler(feat, far).abs().max().item() == 0
+    bad = torch.tensor([float("nan"), float("inf")], device=DEV).view(1, 1, 1, 2)
+    assert torch.isfinite(m.bilinear_sampler(feat, bad)).all()
+    # exact pixel centres reproduce the input
+    ident = m.coords_grid(1, 4, 4, DEV).permute(0, 2, 3, 1)
+    close(m.bilinear_sampler(feat, ident), feat, 1e-6)
+    # empty batch
+    assert m.bilinear_sampler(feat[:0], ident[:0]).shape == (0, 2, 4, 4)
+
+
+@pytest.mark.parametrize("mode", ["pixel", "acF", "acT", "reflect"])
+def test_warp_backward(mode):
+    m = mb()
+    torch.manual_seed(3)
+    B, C, H, W, Ho, Wo = 2, 6, 9, 11, 7, 5
+    feat = torch.randn(B, C, H, W, dtype=torch.float64)
+    if mode == "pixel":
+        grid = torch.rand(B, Ho, Wo, 2, dtype=torch.float64) * torch.tensor([W + 2.0, H + 2.0], dtype=torch.float64) - 1.5
+    else:
+        grid = torch.rand(B, Ho, Wo, 2, dtype=torch.float64) * 2.6 - 1.3
+    go = torch.randn(B, C, Ho, Wo, dtype=torch.float64)
+    f64, g64 = feat.clone().requires_grad_(), grid.clone().requires_grad_()
+    if mode == "pixel":
+        gn = torch.stack([2 * g64[..., 0] / (W - 1) - 1, 2 * g64[..., 1] / (H - 1) - 1], -1)
+        ref = F.grid_sample(f64, gn, align_corners=True)
+    elif mode == "reflect":
+        ref = F.grid_sample(f64, g64, padding_mode="reflection", align_corners=False)
+    else:
+        ref = F.grid_sample(f64, g64, align_corners=(mode == "acT"))
+    ref.backward(go)
+    f32 = feat.float().to(DEV).requires_grad_()
+    g32 = grid.float().to(DEV).requires_grad_()
+    if mode == "pixel":
+        out = m.bilinear_sampler(f32, g32)
+    elif mode == "reflect":
+        out = m.grid_sample(f32, g32, padding_mode="reflection")
+    else:
+        out = m.grid_sample(f32, g32, align_corners=(mode == "acT"))
+    out.backward(go.float().to(DEV))
+    close(out, ref, 1e-5)
+    close(f32.grad, f64.grad, 2e-5)
+    close(g32.grad, g64.grad, 5e-4, 1e-4)
+
+
+def test_dual_warp_backward():
+    torch.manual_seed(4)
+    B, C, R = 2, 5, 12
+    feat = torch.randn(B, C, R, R, dtype=torch.float64)
+    flow = torch.randn(B, 2, R, R, dtype=torch.float64) * 1.5
+    grid = (TP.make_coordinate_grid((R, R))[None].double() + torch.randn(B, R, R, 2, dtype=torch.float64) * 0.1)
+    ga, gb = torch.randn(B, C, R, R, dtype=torch.float64), torch.randn(B, C, R, R, dtype=torch.float64)
+    f64, fl64, g64 = feat.clone().requires_grad_(), flow.clone().requires_grad_(), grid.clone().requires_grad_()
+    co = (fl64 + TP.coords_grid(B, R, R).double()).permute(0, 2, 3, 1)
+    gn = torch.stack([2 * co[..., 0] / (R - 1) - 1, 2 * co[..., 1] / (R - 1) - 1], -1)
+    (F.grid_sample(f64, gn, align_corners=True) * ga).sum().add((F.grid_sample(f64, g64, align_corners=False) * gb).sum()).backward()
+    f32, fl32, g32 = (t.float().to(DEV).requires_grad_() for t in (feat, flow, grid))
+    a, b = torch.ops.mrfa.dual_warp(f32, fl32, g32)
+    ((a * ga.float().to(DEV)).sum() + (b * gb.float().to(DEV)).sum()).backward()
+    close(f32.grad, f64.grad, 5e-5)
+    close(fl32.grad, fl64.grad, 5e-4, 1e-4)
+    close(g32.grad, g64.grad, 2e-3, 1e-4)
+
+
+# ------------------------------------------------------------------ correlation
+def test_corr_pack_and_volume_small(golden):
+    m, c = mb(), golden("corr")
+    q, k = cu(c["q_d"]), cu(c["k_s"])
+    B, C, h, w = q.shape
+    a_op, b_op = m.ops.corr_pack_debug(q, k)
+    qa = c["q_d"].reshape(B, C, -1).transpose(0, 2, 1)
+    assert np.array_equal(a_op[:, :h * w].float().cpu().numpy(), O.round_bf16(qa))
+    assert np.array_equal(b_op.float().cpu().numpy(), O.round_bf16(c["k_s"].reshape(B, C, -1).transpose(0, 2, 1)))
+    off = 0
+    for lvl in range(4):
+        kk = 2 ** lvl
+        pooled = O.avg_pool2d(c["q_d"], kk) if kk > 1 else c["q_d"]
+        n = pooled.shape[-1] * pooled.shape[-2]
+        exp = O.round_bf16(pooled.reshape(B, C, n).transpose(0, 2, 1))
+        got = a_op[:, off:off + n].float().cpu().numpy()
+        assert np.abs(got - exp).max() <= 2 ** -7 * np.abs(exp).max()        # within one bf16 ulp of the mean
+        assert m.ops.corr_row_offset(h, w, lvl) == off
+        off += n
+    assert off == m.ops.corr_rows_total(h, w)
+
+    pyr = m.CorrPyramid(q, k, C ** -0.5)
+    vol = pyr.volume0.float().cpu().numpy()
+    rel_close(vol[:, :h * w], c["volume"])                                     # vs the reference's fp32 einsum
+    # against the exact product of the bf16 operands: only the output rounding remains
+    exact = O.corr_volume(c["q_d"], c["k_s"], C ** -0.5, bf16_inputs=True)
+    rel_close(vol[:, :h * w], exact, 2 ** -7)
+    # pooled driving levels and the source-pooled level 1
+    ref = c["volume"]
+    for lvl in (1, 2):
+        rows = O.corr_pyramid_rows(ref, h, w, 2 ** lvl)
+        o = m.ops.corr_row_offset(h, w, lvl)
+        rel_close(vol[:, o:o + rows.shape[1]], rows)
+    l1 = O.avg_pool2d(ref.reshape(B, h * w, 1, h, w), 2).reshape(B, h * w, -1)
+    rel_close(pyr.volume1[:, :h * w].float().cpu().numpy(), l1)
+
+
+@pytest.mark.parametrize("h,C,B", [(8, 64, 3), (32, 128, 2), (64, 256, 2)])
+def test_corr_volume_sizes(h, C, B):
+    m = mb()
+    torch.manual_seed(h + C)
+    q = torch.randn(B, C, h, h, device=DEV)
+    k = torch.randn(B, C, h, h, device=DEV)
+    pyr = m.CorrPyramid(q, k, C ** -0.5)
+    N = h * h
+    qd = q.flatten(2).transpose(1, 2).double()
+    kd = k.flatten(2).transpose(1, 2).double()
+    ref = torch.einsum("bic,bjc->bij", qd, kd) * C ** -0.5
+    rel_close(pyr.volume0[:, :N], ref)
+    rows, off = [], 0
+    for lvl in range(4):
+        kk = 2 ** lvl
+        qp = F.avg_pool2d(q.double(), kk) if kk > 1 else q.double()
+        r = torch.einsum("bic,bjc->bij", qp.flatten(2).transpose(1, 2), kd) * C ** -0.5
+        rel_close(pyr.volume0[:, off:off + r.shape[1]], r)
+        l1 = F.avg_pool2d(r.view(B, -1, h, h), 2).flatten(2)
+        rel_close(pyr.volume1[:, off:off + r.shape[1]], l1)
+        off += r.shape[1]
+    assert off == pyr.rows_total
+
+
+def test_corr_volume_512_tile_geometry():
+    """w = 128 (the 512x512 configuration): 256-wide tiles, one source row pair per tile."""
+    m = mb()
+    torch.manual_seed(9)
+    B, C, h = 1, 64, 128
+    q = torch.randn(B, C, h, h, device=DEV)
+    k = torch.randn(B, C, h, h, device=DEV)
+    pyr = m.CorrPyramid(q, k, C ** -0.5)
+    N = h * h
+    idx = torch.randint(0, N, (64,), device=DEV)
+    qd = q.flatten(2).transpose(1, 2)[:, idx].double()
+    kd = k.flatten(2).transpose(1, 2).double()
+    ref = torch.einsum("bic,bjc->bij", qd, kd) * C ** -0.5
+    rel_close(pyr.volume0[:, idx], ref)
+    rel_close(pyr.volume1[:, idx], F.avg_pool2d(ref.view(B, -1, h, h), 2).flatten(2))
+
+
+def test_corr_lookup_golden(golden):
+    m, c = mb(), golden("corr")
+    B, h = 2, 16
+    vol = c["volume"]
+    for k in (1, 2, 4):
+        rows = O.corr_pyramid_rows(vol, h, h, k)
+        l0 = cu(rows.reshape(-1, 1, h, h))
+        blk = m.CorrBlock(l0)
+        close(blk.corr_pyramid[1], c[f"level1_k{k}"], 1e-6)
+        close(blk(cu(c[f"coords_k{k}"])), c[f"lookup_k{k}"])
+
+
+def test_corr_lookup_from_bf16_pyramid(golden):
+    m, c = mb(), golden("corr")
+    q, k = cu(c["q_d"]), cu(c["k_s"])
+    B, C, h, w = q.shape
+    pyr = m.CorrPyramid(q, k, C ** -0.5)
+    for lvl, kk in ((0, 1), (1, 2), (2, 4)):
+        coords = cu(c[f"coords_k{kk}"])
+        got = pyr.block(lvl)(coords)
+        # same lookup evaluated by the oracle on the very bf16 maps the kernel read
+        off = m.ops.corr_row_offset(h, w, lvl)
+        Q = (h // kk) * (w // kk)
+        l0 = pyr.volume0[:, off:off + Q].float().reshape(B * Q, 1, h, w).cpu().numpy()
+        l1 = pyr.volume1[:, off:off + Q].float().reshape(B * Q, 1, h // 2, w // 2).cpu().numpy()
+        close(got, O.corr_lookup([l0, l1], c[f"coords_k{kk}"]))
+        rel_close(got, c[f"lookup_k{kk}"])                                    # and 2e-2 of the fp32 reference
+
+
+def test_corr_lookup_edge_cases():
+    m = mb()
+    torch.manual_seed(5)
+    B, h1, H = 1, 3, 10                      # ragged query count (9 < 32), odd map size
+    corr = torch.randn(B * h1 * h1, 1, H, H)
+    coords = torch.rand(B, 2, h1, h1) * (H + 6) - 3
+    coords[0, :, 0, 0] = torch.tensor([-50.0, 4.0])         # window entirely outside
+    coords[0, :, 0, 1] = torch.tensor([0.0, 0.0])           # corner
+    coords[0, :, 0, 2] = torch.tensor([H - 1.0, H - 1.0])
+    ref = TP.corr_lookup(corr, coords)
+    close(m.CorrBlock(corr.to(DEV))(coords.to(DEV)), ref)
+
+
+def test_corr_lookup_backward():
+    m = mb()
+    torch.manual_seed(6)
+    B, h1, H = 2, 4, 12
+    corr = torch.randn(B * h1 * h1, 1, H, H, dtype=torch.float64)
+    coords = torch.rand(B, 2, h1, h1, dtype=torch.float64) * (H + 2) - 1
+    go = torch.randn(B, 98, h1, h1, dtype=torch.float64)
+    c64, x64 = corr.clone().requires_grad_(), coords.clone().requires_grad_()
+
+    def ref_lookup(level0, co):
+        n, r = 7, 3
+        d = torch.linspace(-r, r, n, dtype=co.dtype)
+        delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, n, n, 2)
+        centre = co.permute(0, 2, 3, 1).reshape(-1, 1, 1, 2)
+        outs, lvl_map = [], level0
+        for lvl in range(2):
+            if lvl:
+                lvl_map = F.avg_pool2d(lvl_map, 2, stride=2)
+            outs.append(TP.bilinear_sampler(lvl_map, centre / 2 ** lvl + delta).view(co.shape[0], h1, h1, n * n))
+        return torch.cat(outs, -1).permute(0, 3, 1, 2)
+
+    ref_lookup(c64, x64).backward(go)
+    c32, x32 = corr.float().to(DEV).requires_grad_(), coords.float().to(DEV).requires_grad_()
+    out = m.CorrBlock(c32)(x32)
+    out.backward(go.float().to(DEV))
+    close(c32.grad, c64.grad, 5e-5)
+    close(x32.grad, x64.grad, 5e-4, 1e-4)
+
+
+# ------------------------------------------------------------------ prior dense motion
+def _prior_inputs():
+    from mrfa_b200 import synthetic as syn
+    src, _ = syn.frame_pairs(2, 64, seed=1)
+    kp_s, kp_d = syn.keypoints(2, 10, seed=1)
+    return src, kp_s, kp_d, syn.bg_affine(2, seed=1)
+
+
+def _to(d):
+    return {k: v.to(DEV) for k, v in d.items()}
+
+
+def _cfg():
+    import os
+    import yaml
+    return yaml.safe_load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vox1.yaml")))
+
+
+def test_dense_motion_prior_kernels(golden):
+    from mrfa_b200 import synthetic as syn
+    m, d = mb(), golden("prior_motion")
+    _, kp_s, kp_d, bg = _prior_inputs()
+    cfg = _cfg()
+    net = m.DenseMotionNetwork(**dict(cfg["dense_motion"], block_expansion=16, max_features=64, num_blocks=3)).to(DEV)
+    small = cu(d["source_small"])
+    close(net.create_heatmap_representations(small, _to(kp_d), _to(kp_s)), d["heatmap"], 1e-6)
+    close(net.create_sparse_motions(small, _to(kp_d), _to(kp_s), bg_param=bg.to(DEV)), d["sparse_motions_jac_bg"])
+    close(net.create_sparse_motions(small, {"kp": kp_d["kp"].to(DEV)}, {"kp": kp_s["kp"].to(DEV)}), d["sparse_motions_plain"], 1e-6)
+    close(net.create_deformed_source_image(small, cu(d["sparse_motions_jac_bg"])), d["deformed"])
+    # fused path writes the same numbers into the hourglass input layout
+    motions, hg = torch.ops.mrfa.dense_motion_prior(kp_d["kp"].to(DEV), kp_s["kp"].to(DEV), kp_d["jacobian"].to(DEV),
+                                                    kp_s["jacobian"].to(DEV), bg.to(DEV), small, 0.01)
+    hg = hg.view(2, 11, 4, 16, 16)
+    close(hg[:, :, 1:], d["deformed"])
+    close(hg[:, :, :1], d["heatmap"], 1e-6)
+
+
+def test_tps_kernels(golden):
+    m, d = mb(), golden("prior_motion")
+    from mrfa_b200 import synthetic as syn
+    bg = syn.bg_affine(2, seed=1).to(DEV)
+    kp_d, kp_s = cu(d["tps_kp_d"]), cu(d["tps_kp_s"])
+    tps = m.TPS(mode="kp", bs=2, kp_1=kp_d.view(2, -1, 5, 2), kp_2=kp_s.view(2, -1, 5, 2))
+    # the fp64 in-kernel solve must agree with the fp64 oracle solve to fp32 resolution ...
+    th, cp, cw = O.tps_params(d["tps_kp_d"].reshape(2, -1, 5, 2), d["tps_kp_s"].reshape(2, -1, 5, 2))
+    close(tps.theta, th, 1e-5, 1e-5)
+    close(tps.control_params, cw, 1e-5, 1e-5)
+    # ... and with the reference (fp32 LU inverse) to that inverse's own round-off
+    close(tps.theta, d["tps_theta"], 2e-3, 2e-3)
+    cfg = _cfg()
+    net = m.TPSDenseMotionNetwork(**dict(cfg["tpsm_dense_motion"], block_expansion=16, max_features=64, num_blocks=3)).to(DEV)
+    small = cu(d["source_small"])
+    got = net.create_transformations(small, {"kp": kp_d}, {"kp": kp_s}, bg)
+    close(got, O.tps_transformations(d["tps_kp_d"], d["tps_kp_s"], 16, 16, bg.cpu().numpy()), 2e-5)
+    close(got, d["tps_transformations_bg"], 5e-3)
+    close(tps.transform_frame(small), O.tps_transformations(d["tps_kp_d"], d["tps_kp_s"], 16, 16)[:, 1:], 2e-5)
+
+
+def test_dense_motion_networks_forward(golden):
+    from mrfa_b200 import synthetic as syn
+    m, d = mb(), golden("prior_motion")
+    src, kp_s, kp_d, bg = _prior_inputs()
+    cfg = _cfg()
+    with torch.no_grad():
+        net = syn.fill_state_dict_(m.DenseMotionNetwork(**dict(cfg["dense_motion"], block_expansion=16, max_features=64,
+                                                               num_blocks=3))).to(DEV).eval()
+        out = net(src.to(DEV), _to(kp_d), _to(kp_s), bg_param=bg.to(DEV))
+        for k in ("sparse_deformed", "logit_mask", "mask", "deformation", "occlusion"):
+            close(out[k], d["fwd_" + k], 1e-4)
+        out = net(src.to(DEV), {"kp": kp_d["kp"].to(DEV)}, {"kp": kp_s["kp"].to(DEV)})
+        close(out["deformation"], d["fwd_plain_deformation"], 1e-4)
+        tnet = syn.fill_state_dict_(m.TPSDenseMotionNetwork(**dict(cfg["tpsm_dense_motion"], block_expansion=16,
+                                                                   max_features=64, num_blocks=3))).to(DEV).eval()
+        out = tnet(src.to(DEV), {"kp": cu(d["tps_kp_d"])}, {"kp": cu(d["tps_kp_s"])}, bg_param=bg.to(DEV))
+        for k in ("deformed_source", "contribution_maps", "deformation", "occlusion"):
+            close(out[k], d["tps_fwd_" + k], 5e-3)

@@ -1,0 +1,91 @@
+"""End-to-end parity of the drop-in RaftFlow / DenseMotionNetwork on the GPU against the golden
+output of the unmodified reference and against the CPU oracle (same weights, same inputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+from mrfa_b200 import synthetic as syn               # noqa: E402
+from oracle import torch_path as TP                   # noqa: E402
+
+DEV = "cuda"
+
+
+def _cfg():
+    return yaml.safe_load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vox1.yaml")))
+
+
+def _rf_cfg(size=64):
+    rfc = dict(_cfg()["raft_flow"], size=size)
+    rfc["driving_encoder"] = dict(rfc["driving_encoder"], block_expansion=8, max_features=32, num_blocks=3)
+    rfc["source_encoder"] = dict(rfc["source_encoder"], block_expansion=8, max_features=32, num_blocks=3)
+    return rfc
+
+
+def _rel(a, b, rel):
+    a = a.detach().float().cpu().numpy().astype(np.float64)
+    b = np.asarray(b.detach().float().cpu().numpy() if torch.is_tensor(b) else b, np.float64)
+    rms = np.sqrt((b ** 2).mean())
+    err = np.abs(a - b)
+    assert (err <= rel * (np.abs(b) + rms)).all(), f"max abs err {err.max():.4g} (rms {rms:.4g})"
+    return err.max()
+
+
+def _inputs(golden):
+    d = golden("prior_motion")
+    src, _ = syn.frame_pairs(2, 64, seed=1)
+    kp_s, kp_d = syn.keypoints(2, 10, seed=1)
+    dense = {"deformation": torch.from_numpy(d["fwd_deformation"]), "occlusion": torch.from_numpy(d["fwd_occlusion"])}
+    return src, kp_s, kp_d, dense, torch.from_numpy(d["source_small"])
+
+
+def test_raft_flow_vs_reference_golden(golden):
+    import mrfa_b200
+    r = golden("raft_flow")
+    src, kp_s, kp_d, dense, small = _inputs(golden)
+    with torch.no_grad():
+        net = syn.fill_state_dict_(mrfa_b200.RaftFlow(**_rf_cfg())).to(DEV).eval()
+        assert sorted(net.state_dict().keys()) == list(r["state_dict_keys"])
+        dd = {k: v.to(DEV) for k, v in dense.items()}
+        out, warp_img, occ = net(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), dd, img=small.to(DEV), img_full=src.to(DEV))
+        # bf16 correlation -> 2e-2 relative on the predicted frames (north_star tolerance)
+        _rel(out, r["out"], 2e-2)
+        _rel(warp_img, r["warp_img"], 2e-2)
+        _rel(occ, r["occlusion"], 2e-2)
+        netp = syn.fill_state_dict_(mrfa_b200.RaftFlow(**dict(_rf_cfg(), prior_only=True))).to(DEV).eval()
+        out, warp_img, occ = netp(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), dd, img=small.to(DEV), img_full=src.to(DEV))
+        # no correlation on this path: fp32 warps only
+        np.testing.assert_allclose(out.cpu().numpy(), r["prior_only_out"], atol=1e-4)
+        np.testing.assert_allclose(warp_img.cpu().numpy(), r["prior_only_warp_img"], atol=1e-5)
+        np.testing.assert_allclose(occ.cpu().numpy(), r["prior_only_occlusion"], atol=1e-4)
+
+
+def test_full_chain_vs_oracle_128(golden):
+    """DenseMotionNetwork -> RaftFlow at 128x128 (h=w=32), celebvhq-style bg path on, B=2."""
+    import mrfa_b200
+    cfg = _cfg()
+    dmc = dict(cfg["dense_motion"], block_expansion=16, max_features=64, num_blocks=3)
+    src, _ = syn.frame_pairs(2, 128, seed=3)
+    kp_s, kp_d = syn.keypoints(2, 10, seed=3)
+    bg = syn.bg_affine(2, seed=3)
+    with torch.no_grad():
+        o_dm = syn.fill_state_dict_(TP.DenseMotionOracle(**dmc)).eval()
+        o_rf = syn.fill_state_dict_(TP.RaftFlowOracle(**_rf_cfg(128))).eval()
+        small = o_dm.down(src)
+        dense = o_dm(src, kp_d, kp_s, bg_param=bg)
+        ref_out, ref_warp, ref_occ = o_rf(kp_s["kp"], kp_d["kp"], dense, img=small, img_full=src)
+
+        dm = syn.fill_state_dict_(mrfa_b200.DenseMotionNetwork(**dmc)).to(DEV).eval()
+        rf = syn.fill_state_dict_(mrfa_b200.RaftFlow(**_rf_cfg(128))).to(DEV).eval()
+        c = lambda d: {k: v.to(DEV) for k, v in d.items()}
+        got_dense = dm(src.to(DEV), c(kp_d), c(kp_s), bg_param=bg.to(DEV))
+        np.testing.assert_allclose(got_dense["deformation"].cpu().numpy(), dense["deformation"].numpy(), atol=1e-4)
+        np.testing.assert_allclose(got_dense["occlusion"].cpu().numpy(), dense["occlusion"].numpy(), atol=1e-4)
+        out, warp_img, occ = rf(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), got_dense, img=dm.down(src.to(DEV)), img_full=src.to(DEV))
+        _rel(out, ref_out, 2e-2)
+        _rel(warp_img, ref_warp, 2e-2)
+        _rel(occ, ref_occ, 2e-2)
