@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the MRFA refinement forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
+
+A step = one refinement forward (AntiAlias down -> DenseMotionNetwork -> RaftFlow, vox1.yaml
+architecture, random-init weights, eval / no_grad) over one batch of synthetic frame pairs with
+synthetic key-points (the key-point detector is upstream of the hot path).
+N=1 workload: BASELINE.json configs[1] (batch 64, 256x256, one B200).  N>1: one process per GPU
+(torchrun), the batch of pairs is sharded by rank with no data-path collective ("weak" scaling:
+64 pairs per GPU); NCCL only all-reduces the reconstruction-L1 / timing statistics.
+
+Prints ONE JSON line (rank 0).  `value` is timed with the inputs resident in HBM; `e2e` times
+the same call with pinned HOST inputs (H2D inside) and the predicted frames read back (D2H).
+`--impl reference` times the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frame-pairs/sec (refinement forward, 256x256)"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--config", default="vox1", choices=["vox1", "celebvhq"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=1, help="pairs per step of the CPU reference arm")
+    return ap.parse_args()
+
+
+def load_cfg(name):
+    import yaml
+    return yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", name + ".yaml")))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            out = {"source": "measured"}
+            out["hbm_gbs"] = float(d.get("hbm_gbs") or FALLBACK_PEAKS["hbm_gbs"])
+            out["bf16_tflops"] = float(d.get("bf16_tflops") or FALLBACK_PEAKS["bf16_tflops"])
+            out["bf16_tflops_sustained"] = float(d.get("bf16_tflops_sustained") or out["bf16_tflops"])
+            return out
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], 0, set()
+        for f in self.rows:
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+def build_cpu_oracle(cfg, size):
+    import torch
+    from oracle import torch_path as TP
+    torch.manual_seed(0)
+    dm = TP.DenseMotionOracle(**cfg["dense_motion"]).eval()
+    rf = TP.RaftFlowOracle(**dict(cfg["raft_flow"], size=size)).eval()
+    return dm, rf
+
+
+def cpu_forward(dm, rf, src, kp_s, kp_d, bg):
+    dense = dm(src, kp_d, kp_s, bg_param=bg)
+    return rf(kp_s["kp"], kp_d["kp"], dense, img=dm.down(src), img_full=src)[0]
+
+
+def time_cpu_oracle(cfg, size, batch, steps, warmup):
+    """The reference's CPU path (oracle port, stock torch CPU ops = the reference's arithmetic)."""
+    import torch
+    from mrfa_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dm, rf = build_cpu_oracle(cfg, size)
+    src, _ = syn.frame_pairs(batch, size, seed=0)
+    kp_s, kp_d = syn.keypoints(batch, cfg["raft_flow"]["num_kp"], seed=0)
+    bg = syn.bg_affine(batch) if cfg["train_params"]["bg_start"] == 0 else None
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            cpu_forward(dm, rf, src, kp_s, kp_d, bg)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "best_pairs_s": batch / min(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = load_cfg(args.config)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    r = time_cpu_oracle(cfg, args.size, args.ref_batch, steps, warmup)
+    sample = f"{args.ref_batch} pair(s) per step, {steps} timed steps after {warmup} warm-up, torch CPU, {r['cores']} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args, args.ref_batch, 1),
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, n):
+    return {"workload": f"{args.config}.yaml refinement forward (DenseMotionNetwork + RaftFlow), {args.size}x{args.size}, "
+                        f"batch {batch} pairs per GPU, random-init weights, synthetic key-points",
+            "pairs_per_gpu": batch, "global_pairs": batch * n, "size": args.size, "parallelism": f"dp{n} (batch-sharded, no data-path collective)",
+            "l2": "inputs and intermediates (>3 GB per step) exceed the 126 MB L2; no explicit flush",
+            "convs": "cuDNN, TF32 allowed (PyTorch default)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mrfa_b200
+    from mrfa_b200 import ops
+    from mrfa_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = load_cfg(args.config)
+    B, S, K = args.batch, args.size, cfg["raft_flow"]["num_kp"]
+    use_bg = cfg["train_params"]["bg_start"] == 0
+
+    torch.manual_seed(0)
+    dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).to(dev).eval()
+    rf = mrfa_b200.RaftFlow(**dict(cfg["raft_flow"], size=S)).to(dev).eval()
+
+    # synthetic inputs: generated on the host (pinned), seeded per rank so ranks hold different pairs
+    src_h, drv_h = syn.frame_pairs(B, S, seed=rank)
+    kp_s_h, kp_d_h = syn.keypoints(B, K, seed=rank)
+    host = {"src": src_h, "drv": drv_h, "kp_s": kp_s_h["kp"], "kp_d": kp_d_h["kp"], "jac_s": kp_s_h["jacobian"],
+            "jac_d": kp_d_h["jacobian"]}
+    if use_bg:
+        host["bg"] = syn.bg_affine(B, seed=rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    out_h = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+
+    def forward(d):
+        kp_s = {"kp": d["kp_s"], "jacobian": d["jac_s"]}
+        kp_d = {"kp": d["kp_d"], "jacobian": d["jac_d"]}
+        dense = dm(d["src"], kp_d, kp_s, bg_param=d.get("bg"))
+        out, _, _ = rf(kp_s["kp"], kp_d["kp"], dense, img=dm.down(d["src"]), img_full=d["src"])
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host.items() if k != "drv")
+    d2h_bytes = out_h.numel() * out_h.element_size()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = forward(resident)
+        sync_all()
+
+        # ---- device-resident timing (value) + per-kernel roofline accounting ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ops.KernelTimer() as timer:
+            sync_all()
+            e0.record()
+            for _ in range(args.steps):
+                out = forward(resident)
+            e1.record()
+            sync_all()
+        dev_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        kernels = timer.summary()
+        l1 = (out - resident["drv"]).abs().sum().double()
+
+        # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the predicted frames ----
+        for _ in range(2):
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "drv"}
+            out_h.copy_(forward(d), non_blocking=True)
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "drv"}
+            out_h.copy_(forward(d), non_blocking=True)
+        e3.record()
+        sync_all()
+        e2e_ms = e2.elapsed_time(e3)
+
+    stats = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    sums = torch.tensor([float(l1), float(out.numel())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)       # max over ranks
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)        # reconstruction-L1 statistics
+    dev_ms, e2e_ms = float(stats[0]), float(stats[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    pairs = B * world * args.steps
+    step_ms = dev_ms / args.steps
+    klist = []
+    for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"]):
+        sec = k["total_ms"] / 1e3
+        e = {"kernel": name, "launches": k["launches"], "total_ms": round(k["total_ms"], 4),
+             "share_of_step": round(k["total_ms"] / dev_ms, 4), "avg_ms": round(k["total_ms"] / max(1, k["calls"]), 5)}
+        if sec > 0:
+            e["hbm_gbs"] = round(k["bytes"] / sec / 1e9, 1)
+            e["hbm_frac"] = round(k["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4)
+            if k["flops"]:
+                e["tflops"] = round(k["flops"] / sec / 1e12, 1)
+                e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
+        klist.append(e)
+    ours_ms = sum(k["total_ms"] for k in kernels.values())
+    top = klist[0] if klist else None
+    roofline = None
+    if top:
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top["kernel"])
+        if top["kernel"] == "corr_volume":
+            roofline = {"kernel": "corr_volume", "bound": "tensor", "achieved": top["tflops"],
+                        "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tensor_frac"],
+                        "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
+                        "note": "output-write-bound: also see hbm_frac in kernels[]"}
+        else:
+            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["hbm_gbs"], "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic, "peak_source": pk["source"]}
+
+    line = {"metric": METRIC, "value": pairs / (dev_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 warps/lookups + bf16 tensor-core correlation", "data": "synthetic",
+            "config": workload_config(args, B, world), "clocks": clocks,
+            "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": sum(k["launches"] for k in kernels.values()),
+            "roofline": roofline, "kernels": klist,
+            "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
+            "recon_l1_mean": float(sums[0] / sums[1]), "peaks": pk}
+    if not args.no_cpu_baseline:
+        r = time_cpu_oracle(cfg, S, 1, 3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                                "sample": f"1 pair per step, 3 timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step), "
+                                          f"oracle torch-CPU port of the reference path, {r['cores']} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

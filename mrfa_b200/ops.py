@@ -39,6 +39,55 @@ def _grid_strides(grid: Tensor) -> GridStrides:
     return GridStrides(s[0], s[1], s[2], s[3])
 
 
+class KernelTimer:
+    """Per-kernel CUDA-event timing on the launching stream (bench.py roofline accounting).
+
+    While installed (``with KernelTimer() as t:``) every C-ABI launch is bracketed by two events
+    recorded on the current stream and tagged with its algorithmic bytes / flops."""
+
+    def __init__(self):
+        self.records = {}
+
+    def __enter__(self):
+        global _TIMER
+        self._prev, _TIMER = _TIMER, self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = self._prev
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _, _, _ in recs]
+            out[name] = {"launches": sum(r[4] for r in recs), "calls": len(recs), "total_ms": sum(ms),
+                         "bytes": sum(r[2] for r in recs), "flops": sum(r[3] for r in recs)}
+        return out
+
+
+_TIMER = None
+
+
+class _timed:
+    __slots__ = ("name", "nbytes", "flops", "launches", "start")
+
+    def __init__(self, name, nbytes=0, flops=0, launches=1):
+        self.name, self.nbytes, self.flops, self.launches = name, nbytes, flops, launches
+
+    def __enter__(self):
+        if _TIMER is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if _TIMER is not None and exc[0] is None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _TIMER.records.setdefault(self.name, []).append((self.start, end, self.nbytes, self.flops, self.launches))
+
+
 _SM_COUNT = {}
 
 
@@ -65,10 +114,13 @@ def grid_sample(inp: Tensor, grid: Tensor, coord_mode: int, padding_mode: int, a
     if Nin * in_batch_div != N:
         raise RuntimeError(f"mrfa_b200: grid batch {N} != input batch {Nin} * {in_batch_div}")
     out = torch.empty((N, C, Ho, Wo), device=inp.device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(inp.device):
-        check(lib.mrfa_grid_sample_fwd(_p(inp), _p(grid), _grid_strides(grid), _p(out), N, C, H, W, Ho, Wo,
-                                       in_batch_div, coord_mode, padding_mode, int(add_identity), _stream()),
-              "mrfa_grid_sample_fwd")
+        with _timed("grid_sample_fwd", 4 * (N * C * Ho * Wo + Nin * C * H * W + 2 * N * Ho * Wo)):
+            check(lib.mrfa_grid_sample_fwd(_p(inp), _p(grid), _grid_strides(grid), _p(out), N, C, H, W, Ho, Wo,
+                                           in_batch_div, coord_mode, padding_mode, int(add_identity), _stream()),
+                  "mrfa_grid_sample_fwd")
     return out
 
 
@@ -87,10 +139,11 @@ def grid_sample_bwd(grad_out: Tensor, inp: Tensor, grid: Tensor, coord_mode: int
     g_in = torch.zeros_like(inp) if need_input else inp.new_empty(0)
     g_grid = torch.empty((N, Ho, Wo, 2), device=inp.device, dtype=torch.float32) if need_grid else inp.new_empty(0)
     with torch.cuda.device(inp.device):
-        check(lib.mrfa_grid_sample_bwd(_p(grad_out), _p(inp), _p(grid), _grid_strides(grid),
-                                       _p(g_in) if need_input else None, _p(g_grid) if need_grid else None,
-                                       N, C, H, W, Ho, Wo, in_batch_div, coord_mode, padding_mode, int(add_identity),
-                                       _stream()), "mrfa_grid_sample_bwd")
+        with _timed("grid_sample_bwd", 4 * (N * C * Ho * Wo + 3 * inp.numel() + 4 * N * Ho * Wo)):
+            check(lib.mrfa_grid_sample_bwd(_p(grad_out), _p(inp), _p(grid), _grid_strides(grid),
+                                           _p(g_in) if need_input else None, _p(g_grid) if need_grid else None,
+                                           N, C, H, W, Ho, Wo, in_batch_div, coord_mode, padding_mode, int(add_identity),
+                                           _stream()), "mrfa_grid_sample_bwd")
     return g_in, g_grid
 
 
@@ -124,8 +177,9 @@ def dual_warp(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Te
         raise RuntimeError("mrfa_b200: dual_warp expects flow (N,2,H,W) and prior_grid (N,H,W,2) at the feature size")
     out_r, out_c = torch.empty_like(inp), torch.empty_like(inp)
     with torch.cuda.device(inp.device):
-        check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, _stream()),
-              "mrfa_dual_warp_fwd")
+        with _timed("dual_warp_fwd", 4 * (3 * inp.numel() + 4 * N * H * W)):
+            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, _stream()),
+                  "mrfa_dual_warp_fwd")
     return out_r, out_c
 
 
@@ -166,7 +220,8 @@ def coords_grid_cuda(batch: int, ht: int, wd: int, device) -> Tensor:
         raise RuntimeError("mrfa_b200: coords_grid needs a CUDA device (there is no CPU fallback)")
     out = torch.empty((batch, 2, ht, wd), device=device, dtype=torch.float32)
     with torch.cuda.device(device):
-        check(lib.mrfa_coords_grid(_p(out), batch, ht, wd, _stream()), "mrfa_coords_grid")
+        with _timed("coords_grid", 4 * out.numel()):
+            check(lib.mrfa_coords_grid(_p(out), batch, ht, wd, _stream()), "mrfa_coords_grid")
     return out
 
 
@@ -176,7 +231,8 @@ def make_coordinate_grid_cuda(h: int, w: int, device) -> Tensor:
         raise RuntimeError("mrfa_b200: make_coordinate_grid needs a CUDA device (there is no CPU fallback)")
     out = torch.empty((h, w, 2), device=device, dtype=torch.float32)
     with torch.cuda.device(device):
-        check(lib.mrfa_make_coordinate_grid(_p(out), h, w, _stream()), "mrfa_make_coordinate_grid")
+        with _timed("make_coordinate_grid", 4 * out.numel()):
+            check(lib.mrfa_make_coordinate_grid(_p(out), h, w, _stream()), "mrfa_make_coordinate_grid")
     return out
 
 
@@ -190,7 +246,8 @@ def kp2gaussian(kp: Tensor, add: Optional[Tensor], h: int, w: int, variance: flo
         period = add.numel() // (h * w)
     out = torch.empty(tuple(kp.shape[:-1]) + (h, w), device=kp.device, dtype=torch.float32)
     with torch.cuda.device(kp.device):
-        check(lib.mrfa_kp2gaussian(_p(kp), _p(add), period, _p(out), P, h, w, variance, _stream()), "mrfa_kp2gaussian")
+        with _timed("kp2gaussian", 4 * (out.numel() + kp.numel())):
+            check(lib.mrfa_kp2gaussian(_p(kp), _p(add), period, _p(out), P, h, w, variance, _stream()), "mrfa_kp2gaussian")
     return out
 
 
@@ -229,7 +286,8 @@ def prior_to_flow(deformation: Tensor, hm1: float) -> Tensor:
     B, h, w, _ = deformation.shape
     out = torch.empty((B, 2, h, w), device=deformation.device, dtype=torch.float32)
     with torch.cuda.device(deformation.device):
-        check(lib.mrfa_prior_to_flow(_p(deformation), _p(out), B, h, w, hm1, _stream()), "mrfa_prior_to_flow")
+        with _timed("prior_to_flow", 8 * out.numel()):
+            check(lib.mrfa_prior_to_flow(_p(deformation), _p(out), B, h, w, hm1, _stream()), "mrfa_prior_to_flow")
     return out
 
 
@@ -265,9 +323,10 @@ def dense_motion_prior(kp_d: Tensor, kp_s: Tensor, jac_d: Optional[Tensor], jac_
     motions = torch.empty((B, K + 1, h, w, 2), device=source.device, dtype=torch.float32)
     hg_input = torch.empty((B, (K + 1) * (C + 1), h, w), device=source.device, dtype=torch.float32)
     with torch.cuda.device(source.device):
-        check(lib.mrfa_dense_motion_prior(_p(kp_d), _p(kp_s), _p(jac_d), _p(jac_s), _p(bg_param), _p(source),
-                                          _p(motions), _p(hg_input), B, K, C, h, w, variance, _stream()),
-              "mrfa_dense_motion_prior")
+        with _timed("dense_motion_prior", 4 * (motions.numel() + hg_input.numel() + source.numel())):
+            check(lib.mrfa_dense_motion_prior(_p(kp_d), _p(kp_s), _p(jac_d), _p(jac_s), _p(bg_param), _p(source),
+                                              _p(motions), _p(hg_input), B, K, C, h, w, variance, _stream()),
+                  "mrfa_dense_motion_prior")
     return motions, hg_input
 
 
@@ -287,7 +346,8 @@ def tps_solve(kp_1: Tensor, kp_2: Tensor) -> Tuple[Tensor, Tensor]:
     theta = torch.empty((B, G, 2, 3), device=kp_1.device, dtype=torch.float32)
     params = torch.empty((B, G, n, 2), device=kp_1.device, dtype=torch.float32)
     with torch.cuda.device(kp_1.device):
-        check(lib.mrfa_tps_solve(_p(kp_1), _p(kp_2), _p(theta), _p(params), B * G, _stream()), "mrfa_tps_solve")
+        with _timed("tps_solve", 4 * (2 * kp_1.numel() + theta.numel() + params.numel())):
+            check(lib.mrfa_tps_solve(_p(kp_1), _p(kp_2), _p(theta), _p(params), B * G, _stream()), "mrfa_tps_solve")
     return theta, params
 
 
@@ -308,9 +368,10 @@ def tps_motion_prior(kp_d: Tensor, kp_s: Tensor, theta: Tensor, control_params: 
     motions = torch.empty((B, G + 1, h, w, 2), device=source.device, dtype=torch.float32)
     hg_input = torch.empty((B, G * 5 + 1 + (G + 1) * C, h, w), device=source.device, dtype=torch.float32)
     with torch.cuda.device(source.device):
-        check(lib.mrfa_tps_motion_prior(_p(kp_d), _p(kp_s), _p(theta), _p(control_params), _p(bg_param), _p(source),
-                                        _p(motions), _p(hg_input), B, G, C, h, w, variance, _stream()),
-              "mrfa_tps_motion_prior")
+        with _timed("tps_motion_prior", 4 * (motions.numel() + hg_input.numel() + source.numel()), launches=2):
+            check(lib.mrfa_tps_motion_prior(_p(kp_d), _p(kp_s), _p(theta), _p(control_params), _p(bg_param), _p(source),
+                                            _p(motions), _p(hg_input), B, G, C, h, w, variance, _stream()),
+                  "mrfa_tps_motion_prior")
     return motions, hg_input
 
 
@@ -345,9 +406,13 @@ def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor
     vol1 = torch.empty((B, rows, (h * w) // 4), device=dev, dtype=torch.bfloat16)
     with torch.cuda.device(dev):
         st = _stream()
-        check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, st), "mrfa_corr_pack")
-        check(lib.mrfa_corr_volume(_p(a_op), _p(b_op), _p(vol0), _p(vol1), B, C, h, w, scale, sm_count(dev), st),
-              "mrfa_corr_volume")
+        with _timed("corr_pack", 8 * q_d.numel() + 2 * (a_op.numel() + b_op.numel())):
+            check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, st), "mrfa_corr_pack")
+        # algorithmic FLOPs: the basic-resolution contraction only; bytes: operands + pyramid
+        with _timed("corr_volume", 2 * (a_op.numel() + b_op.numel() + vol0.numel() + vol1.numel()),
+                    2 * B * (h * w) ** 2 * C):
+            check(lib.mrfa_corr_volume(_p(a_op), _p(b_op), _p(vol0), _p(vol1), B, C, h, w, scale, sm_count(dev), st),
+                  "mrfa_corr_volume")
     return vol0, vol1
 
 
@@ -377,7 +442,8 @@ def avg_pool2x2(x: Tensor) -> Tensor:
     P = x.numel() // (H * W)
     out = torch.empty(tuple(x.shape[:-2]) + (H // 2, W // 2), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
-        check(lib.mrfa_avg_pool2x2(_p(x), _p(out), P, H, W, _stream()), "mrfa_avg_pool2x2")
+        with _timed("avg_pool2x2", 4 * (x.numel() + out.numel())):
+            check(lib.mrfa_avg_pool2x2(_p(x), _p(out), P, H, W, _stream()), "mrfa_avg_pool2x2")
     return out
 
 
@@ -414,9 +480,10 @@ def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, 
     n = 2 * radius + 1
     out = torch.empty((B, 2 * n * n, h1, w1), device=coords.device, dtype=torch.float32)
     with torch.cuda.device(coords.device):
-        check(lib.mrfa_corr_lookup_fwd(_p(level0), _p(level1), int(level0.dtype == torch.bfloat16), _p(coords), _p(out),
-                                       B, h1 * w1, H, W, map_batch_stride, row_offset, radius, _stream()),
-              "mrfa_corr_lookup_fwd")
+        with _timed("corr_lookup_fwd", B * h1 * w1 * (2 * (2 * radius + 2) ** 2 * level0.element_size() + 8 + 4 * 2 * n * n)):
+            check(lib.mrfa_corr_lookup_fwd(_p(level0), _p(level1), int(level0.dtype == torch.bfloat16), _p(coords), _p(out),
+                                           B, h1 * w1, H, W, map_batch_stride, row_offset, radius, _stream()),
+                  "mrfa_corr_lookup_fwd")
     return out
 
 
@@ -437,10 +504,11 @@ def corr_lookup_bwd(grad_out: Tensor, level0: Tensor, level1: Tensor, coords: Te
     g1 = torch.zeros(level1.shape, device=dev, dtype=torch.float32) if need_levels else coords.new_empty(0)
     gc = torch.empty_like(coords) if need_coords else coords.new_empty(0)
     with torch.cuda.device(dev):
-        check(lib.mrfa_corr_lookup_bwd(_p(grad_out), _p(level0), _p(level1), int(level0.dtype == torch.bfloat16),
-                                       _p(coords), _p(g0) if need_levels else None, _p(g1) if need_levels else None,
-                                       _p(gc) if need_coords else None, B, h1 * w1, H, W, map_batch_stride,
-                                       row_offset, radius, _stream()), "mrfa_corr_lookup_bwd")
+        with _timed("corr_lookup_bwd", B * h1 * w1 * (4 * (2 * radius + 2) ** 2 * 4 + 16 + 4 * 2 * (2 * radius + 1) ** 2)):
+            check(lib.mrfa_corr_lookup_bwd(_p(grad_out), _p(level0), _p(level1), int(level0.dtype == torch.bfloat16),
+                                           _p(coords), _p(g0) if need_levels else None, _p(g1) if need_levels else None,
+                                           _p(gc) if need_coords else None, B, h1 * w1, H, W, map_batch_stride,
+                                           row_offset, radius, _stream()), "mrfa_corr_lookup_bwd")
     return g0, g1, gc
 
 

@@ -216,28 +216,32 @@ def test_corr_pack_and_volume_small(golden):
     rel_close(pyr.volume1[:, :h * w].float().cpu().numpy(), l1)
 
 
-@pytest.mark.parametrize("h,C,B", [(8, 64, 3), (32, 128, 2), (64, 256, 2)])
-def test_corr_volume_sizes(h, C, B):
+@pytest.mark.parametrize("h,w,C,B", [(16, 8, 64, 3), (32, 32, 128, 2), (64, 64, 256, 2), (8, 64, 512, 1)])
+def test_corr_volume_sizes(h, w, C, B):
     m = mb()
     torch.manual_seed(h + C)
-    q = torch.randn(B, C, h, h, device=DEV)
-    k = torch.randn(B, C, h, h, device=DEV)
+    q = torch.randn(B, C, h, w, device=DEV)
+    k = torch.randn(B, C, h, w, device=DEV)
     pyr = m.CorrPyramid(q, k, C ** -0.5)
-    N = h * h
-    qd = q.flatten(2).transpose(1, 2).double()
     kd = k.flatten(2).transpose(1, 2).double()
-    ref = torch.einsum("bic,bjc->bij", qd, kd) * C ** -0.5
-    rel_close(pyr.volume0[:, :N], ref)
-    rows, off = [], 0
+    off = 0
     for lvl in range(4):
         kk = 2 ** lvl
         qp = F.avg_pool2d(q.double(), kk) if kk > 1 else q.double()
         r = torch.einsum("bic,bjc->bij", qp.flatten(2).transpose(1, 2), kd) * C ** -0.5
         rel_close(pyr.volume0[:, off:off + r.shape[1]], r)
-        l1 = F.avg_pool2d(r.view(B, -1, h, h), 2).flatten(2)
+        l1 = F.avg_pool2d(r.view(B, -1, h, w), 2).flatten(2)
         rel_close(pyr.volume1[:, off:off + r.shape[1]], l1)
         off += r.shape[1]
     assert off == pyr.rows_total
+
+
+def test_corr_shape_errors():
+    m = mb()
+    with pytest.raises(RuntimeError):                     # h*w not a multiple of the 128-wide tile
+        m.CorrPyramid(torch.randn(1, 64, 8, 8, device=DEV), torch.randn(1, 64, 8, 8, device=DEV), 1.0)
+    with pytest.raises(RuntimeError):                     # C not a multiple of 64
+        m.CorrPyramid(torch.randn(1, 32, 16, 16, device=DEV), torch.randn(1, 32, 16, 16, device=DEV), 1.0)
 
 
 def test_corr_volume_512_tile_geometry():
