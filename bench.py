@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--config", default="vox1", choices=["vox1", "celebvhq"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=1, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--nchw", action="store_true", help="keep the networks in NCHW memory (default: channels_last)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="pairs per step of the CPU reference arm (0 = auto)")
     return ap.parse_args()
 
 
@@ -144,17 +145,25 @@ def time_cpu_oracle(cfg, size, batch, steps, warmup):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port -- the
+    Python reference cannot travel to the GPU box), all host threads, on a bounded sample of
+    the workload: each step processes `ref_batch` pairs, sized from a one-pair probe so that the
+    whole --steps/--warmup run stays within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = load_cfg(args.config)
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    r = time_cpu_oracle(cfg, args.size, args.ref_batch, steps, warmup)
-    sample = f"{args.ref_batch} pair(s) per step, {steps} timed steps after {warmup} warm-up, torch CPU, {r['cores']} threads"
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    probe = time_cpu_oracle(cfg, args.size, 1, 1, 1)
+    t1 = probe["ms_per_step"] / 1e3
+    ref_batch = args.ref_batch or int(max(1, min(8, 180.0 / ((steps + warmup) * t1))))
+    r = time_cpu_oracle(cfg, args.size, ref_batch, steps, warmup)
+    sample = (f"{ref_batch} pair(s) per step (bounded sample of the {args.batch}-pair batch), {steps} timed steps after "
+              f"{warmup} warm-up, oracle torch-CPU port of the reference path, {r['cores']} threads")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(args, args.ref_batch, 1),
+            "config": workload_config(args, args.batch, max(1, args.gpus)),
             "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -166,7 +175,7 @@ def workload_config(args, batch, n):
                         f"batch {batch} pairs per GPU, random-init weights, synthetic key-points",
             "pairs_per_gpu": batch, "global_pairs": batch * n, "size": args.size, "parallelism": f"dp{n} (batch-sharded, no data-path collective)",
             "l2": "inputs and intermediates (>3 GB per step) exceed the 126 MB L2; no explicit flush",
-            "convs": "cuDNN, TF32 allowed (PyTorch default)"}
+            "convs": "cuDNN, TF32 allowed (PyTorch default), " + ("NCHW" if args.nchw else "channels_last (NHWC) memory")}
 
 
 def run_ours(args):
@@ -192,6 +201,9 @@ def run_ours(args):
     torch.manual_seed(0)
     dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).to(dev).eval()
     rf = mrfa_b200.RaftFlow(**dict(cfg["raft_flow"], size=S)).to(dev).eval()
+    if not args.nchw:
+        dm.channels_last_()
+        rf.channels_last_()
 
     # synthetic inputs: generated on the host (pinned), seeded per rank so ranks hold different pairs
     src_h, drv_h = syn.frame_pairs(B, S, seed=rank)

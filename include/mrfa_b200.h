@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 1
+#define MRFA_B200_ABI_VERSION 2
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -60,24 +60,29 @@ typedef struct {
  * in (N/in_batch_div, C, H, W); out (N, C, Ho, Wo).  If add_identity != 0 the pixel index
  * (x, y) is added to the grid value first (fuses `flow + coords_grid`, raft.py:247,260,302).
  * in_batch_div > 1 reads one input for several grids (fuses the `.repeat` of
- * dense_motion.py:80-81 / :238-239).                                                        */
+ * dense_motion.py:80-81 / :238-239).
+ * channels_last != 0: `in` and `out` are NHWC in memory (torch.channels_last; the layout the
+ * sm_100 tensor-core convolutions produce), C % 4 == 0, 16-byte aligned: a tap is C contiguous
+ * floats and every access is a 16-byte vector.  channels_last == 0: NCHW.                    */
 int mrfa_grid_sample_fwd(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out,
                          int N, int C, int H, int W, int Ho, int Wo, int in_batch_div,
-                         int coord_mode, int padding_mode, int add_identity, mrfa_stream_t stream);
+                         int coord_mode, int padding_mode, int add_identity, int channels_last,
+                         mrfa_stream_t stream);
 
 /* Backward of the above.  grad_in must be ZERO-FILLED by the caller (scatter-add target);
  * grad_grid is written densely as (N,Ho,Wo,2).  Either may be NULL to skip it.               */
 int mrfa_grid_sample_bwd(const float* grad_out, const float* in, const float* grid, mrfa_grid_strides_t gs,
                          float* grad_in, float* grad_grid,
                          int N, int C, int H, int W, int Ho, int Wo, int in_batch_div,
-                         int coord_mode, int padding_mode, int add_identity, mrfa_stream_t stream);
+                         int coord_mode, int padding_mode, int add_identity, int channels_last,
+                         mrfa_stream_t stream);
 
 /* Two warps of the same feature map in one pass: refined (pixel flow + identity, raft.py:247)
  * and coarse/prior (normalised grid, align_corners=False, raft.py:271).  flow (B,2,Ho,Wo)
  * planar; prior_grid (B,Ho,Wo,2).  Reads `in` once from HBM.                                */
 int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid,
                        float* out_refined, float* out_coarse,
-                       int N, int C, int H, int W, mrfa_stream_t stream);
+                       int N, int C, int H, int W, int channels_last, mrfa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Coordinate grids and key-point heat-maps
@@ -145,9 +150,10 @@ int64_t mrfa_corr_row_offset(int h, int w, int pool_log2);
 /* fp32 NCHW features -> bf16 K-major GEMM operands (fuses the rearranges raft.py:183-184, the
  * fp32->bf16 cast and the driving-side average pooling raft.py:219).
  *   q_d, k_s (B,C,h,w) fp32;  a_op (B, rows_total, C) bf16;  b_op (B, h*w, C) bf16.
- * C % 64 == 0, h and w multiples of 8.                                                       */
+ * C % 64 == 0, h and w multiples of 8.  channels_last != 0: q_d / k_s are NHWC in memory (then
+ * the rearrange is the identity and the kernel is a vectorised cast + pool).                 */
 int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op,
-                   int B, int C, int h, int w, mrfa_stream_t stream);
+                   int B, int C, int h, int w, int channels_last, mrfa_stream_t stream);
 
 /* volume0[b,i,j]  = scale * sum_c a_op[b,i,c] * b_op[b,j,c]            (B, rows_total, h*w)  bf16
  * volume1[b,i,j'] = mean over the 2x2 source block j' of the above      (B, rows_total, hw/4) bf16
@@ -173,11 +179,13 @@ int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_
  *   reference `corr` (B*Q,1,H,W) has map_batch_stride = Q, row_offset = 0; a pyramid volume
  *   from mrfa_corr_volume has map_batch_stride = rows_total, row_offset = pooled-level offset.
  *   level1 is the 2x2-pooled map (H/2 x W/2) with the same indexing.
- *   elem_bf16: 0 -> fp32 maps, 1 -> bf16 maps.   out (B, 2*(2r+1)^2, Q) fp32.  radius <= 4.  */
+ *   elem_bf16: 0 -> fp32 maps, 1 -> bf16 maps.   out (B, 2*(2r+1)^2, Q) fp32, or (B, Q, 2*(2r+1)^2)
+ *   in memory when out_channels_last != 0 (feeds the 1x1 convc1 without a layout change).
+ *   radius <= 4.                                                                              */
 int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16,
                          const float* coords, float* out,
                          int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
-                         int radius, mrfa_stream_t stream);
+                         int radius, int out_channels_last, mrfa_stream_t stream);
 
 /* Backward: grad_level0/1 (fp32, same indexing as the maps, ZERO-FILLED by the caller, may be
  * NULL) receive the scatter-add; grad_coords (B,2,Q) is written.                             */

@@ -1,7 +1,7 @@
 """ctypes binding of libmrfa_b200.so (C ABI declared in include/mrfa_b200.h).
 
 There is deliberately no fallback: if the library is missing this module raises, and every
-wrapper raises on non-CUDA tensors.  Build with ``python -m mrfa_b200.build``.
+wrapper raises on non-CUDA tensors.  Build with ``python mrfa_b200/build.py``.
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
 
@@ -25,10 +25,10 @@ class GridStrides(ctypes.Structure):
 SIGNATURES = {
     "mrfa_abi_version": (c_int, []),
     "mrfa_error_string": (c_char_p, [c_int]),
-    "mrfa_grid_sample_fwd": (c_int, [c_void_p, c_void_p, GridStrides, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "mrfa_grid_sample_fwd": (c_int, [c_void_p, c_void_p, GridStrides, c_void_p] + [c_int] * 11 + [c_void_p]),
     "mrfa_grid_sample_bwd": (c_int, [c_void_p, c_void_p, c_void_p, GridStrides, c_void_p, c_void_p]
-                             + [c_int] * 10 + [c_void_p]),
-    "mrfa_dual_warp_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+                             + [c_int] * 11 + [c_void_p]),
+    "mrfa_dual_warp_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "mrfa_coords_grid": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mrfa_make_coordinate_grid": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mrfa_kp2gaussian": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
@@ -38,11 +38,11 @@ SIGNATURES = {
     "mrfa_prior_to_flow": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "mrfa_corr_rows_total": (c_int64, [c_int, c_int]),
     "mrfa_corr_row_offset": (c_int64, [c_int, c_int, c_int]),
-    "mrfa_corr_pack": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
+    "mrfa_corr_pack": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_corr_volume": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "mrfa_avg_pool2x2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 4
-                             + [c_int64, c_int64, c_int, c_void_p]),
+                             + [c_int64, c_int64, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4
                              + [c_int64, c_int64, c_int, c_void_p]),
 }
@@ -52,7 +52,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: the CUDA kernels are the product and there is no fallback. "
-            "Build them with `python -m mrfa_b200.build` (needs nvcc, no GPU required).")
+            "Build them with `python mrfa_b200/build.py` (needs nvcc, no GPU required).")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header / library drift

@@ -3,7 +3,7 @@
 nvcc cross-compiles without a GPU; the library has no torch / CUTLASS dependency and links the
 CUDA runtime statically, so the in-tree .so travels to the GPU box as-is.
 
-    python -m mrfa_b200.build [--force] [-v]
+    python mrfa_b200/build.py [--force] [-v]
 """
 from __future__ import annotations
 

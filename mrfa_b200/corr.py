@@ -67,11 +67,11 @@ class CorrBlock:
         self._offset = ops.corr_row_offset(pyr.h, pyr.w, pool_log2)
         return self
 
-    def __call__(self, coords):
+    def __call__(self, coords, channels_last: bool = False):
         B, _, h1, w1 = coords.shape
         stride = self._stride if self._stride is not None else h1 * w1
         if self._stride is None and self.corr_pyramid[0].shape[0] != B * h1 * w1:
             raise RuntimeError("mrfa_b200: corr has %d maps but coords address %d queries"
                                % (self.corr_pyramid[0].shape[0], B * h1 * w1))
         return torch.ops.mrfa.corr_lookup(self.corr_pyramid[0], self.corr_pyramid[1], coords, self._H, self._W,
-                                          stride, self._offset, self.radius)
+                                          stride, self._offset, self.radius, channels_last)

@@ -15,6 +15,7 @@
 // Roofline: the output (rows_total x hw x 1.25 bf16) makes the kernel HBM-write-bound once the
 // operands sit in L2; algorithmic FLOPs = 2 * hw * hw * C per pair.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mrfa {
@@ -82,6 +83,48 @@ corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, _
       const int64_t row = off + (int64_t)(y0 / k + py) * wl + x0 / k + px;
       dst[row * C + c0 + lane] = __float2bfloat16_rn(acc / (float)(k * k));
     }
+  }
+}
+
+// channels-last inputs: (B,h,w,C) in memory is already "(h w) c" row-major, so the pack is a
+// vectorised cast (float4 -> 4 x bf16) plus the pooled driving rows; one thread per (row, 4 ch).
+__global__ void __launch_bounds__(256)
+corr_pack_nhwc_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, __nv_bfloat16* __restrict__ a_op,
+                      __nv_bfloat16* __restrict__ b_op, int B, int C, int h, int w, int64_t rows_total) {
+  const int hw = h * w, cq = C / 4;
+  const int64_t per_b = (rows_total + hw) * cq;
+  const int64_t total = (int64_t)B * per_b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const int64_t r_ = (i - (int64_t)b * per_b) / cq;
+    const int c = (int)(i % cq) * 4;
+    float4 acc;
+    __nv_bfloat16* dst;
+    if (r_ >= rows_total) {                                   // source operand: plain cast
+      const int64_t r = r_ - rows_total;
+      acc = __ldg(reinterpret_cast<const float4*>(k_s + ((int64_t)b * hw + r) * C + c));
+      dst = b_op + ((int64_t)b * hw + r) * C + c;
+    } else {
+      int lvl = 0;
+      int64_t off = 0, r = r_;
+      while (r >= (hw >> (2 * lvl))) { r -= hw >> (2 * lvl); off += hw >> (2 * lvl); ++lvl; }
+      const int k = 1 << lvl, wl = w >> lvl;
+      const int py = (int)(r / wl), px = (int)(r - (int64_t)py * wl);
+      const float* src = q_d + (int64_t)b * hw * C + c;
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)(py * k + dy) * w + px * k + dx) * C));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      const float inv = 1.f / (float)(k * k);
+      if (lvl) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+      dst = a_op + ((int64_t)b * rows_total + r_) * C + c;
+    }
+    const uint2 packed = make_uint2(
+        (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.y)) << 16),
+        (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.z)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.w)) << 16));
+    *reinterpret_cast<uint2*>(dst) = packed;
   }
 }
 
@@ -432,6 +475,338 @@ corr_volume_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+
+// ============================================================================================
+// v2: 256-row units (two M=128 accumulators share every B tile), A ring released per K block,
+//     epilogue staged through swizzled shared memory and written by TMA bulk tensor stores.
+//     Used for w in {64, 128}: the production shapes (256x256 and 512x512 frames).
+// ============================================================================================
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr uint32_t kStageWarpBytes = 4096 + 4096 + 2048;   // two 32x64 bf16 boxes + one 32x32 box
+
+template <int kW, int kBlockN_, int kMTiles> struct Gemm2Cfg {
+  static_assert(kW == 64 || kW == 128, "TMA-store epilogue is specialised for w = 64 / 128");
+  static_assert(kBlockN_ % (2 * kW) == 0 && kBlockN_ <= 256, "a tile holds whole source row pairs");
+  static constexpr int kBlockN = kBlockN_;
+  static constexpr int kGroups = kBlockN / (2 * kW);                     // source row pairs per tile
+  static constexpr int kUnitRows = kBlockM * kMTiles;
+  static constexpr uint32_t kBStageBytes = kBlockN * kBlockK * 2;
+  static constexpr uint32_t kAKBytes = kUnitRows * kBlockK * 2;          // one K block of the A unit
+  static constexpr int kTmemCols = 2 * kMTiles * kBlockN;               // double-buffered accumulators
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
+  static constexpr int kSteps = kW / 64;                                  // 64-column pairs per tile
+};
+
+struct Gemm2Params {
+  int B, kblocks, m_blocks, n_tiles, n_split, b_stages;
+  float scale;
+  int store_mode;            // 0 = TMA bulk tensor stores, 1 = coalesced LSU stores from the staged boxes
+  int N;                     // hw
+  int64_t rows_total;
+  __nv_bfloat16 *vol0, *vol1;
+  int debug;   // MRFA_CORR_DEBUG bit mask (timing decomposition only; breaks results): 1 = no TMA stores,
+               // 2 = epilogue skips TMEM loads / math / staging, 4 = no wait on staging reuse
+};
+
+template <int kW, int kBlockN_, int kMTiles, int kCluster>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1,
+                       const Gemm2Params prm) {
+  using Cfg = Gemm2Cfg<kW, kBlockN_, kMTiles>;
+  constexpr int kBlockN = Cfg::kBlockN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                                 // [kblocks][kUnitRows x 128 B]
+  uint8_t* smem_b = smem_a + (size_t)prm.kblocks * Cfg::kAKBytes;         // [b_stages][kBStageBytes]
+  uint8_t* smem_st = smem_b + (size_t)prm.b_stages * Cfg::kBStageBytes;   // [4 warps][kStageWarpBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + 4 * kStageWarpBytes);
+  uint64_t* a_full = bars;               // [8] per K block
+  uint64_t* a_empty = bars + 8;          // [8]
+  uint64_t* b_full = bars + 16;          // [8] per stage
+  uint64_t* b_empty = bars + 24;         // [8]
+  uint64_t* t_full = bars + 32;          // [2]
+  uint64_t* t_empty = bars + 34;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  // kCluster == 2: the CTA pair works on adjacent 128-row blocks of the same pair and N tiles in
+  // lock step; each CTA loads half of every B tile and multicasts it into both shared memories,
+  // so B crosses the L2 -> SM fabric once per 256 rows.
+  const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
+  const int64_t cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;
+  constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v1) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], kCluster);   // released by the MMA warp of every CTA that received the tile
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast can land
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_unit = prm.n_tiles / prm.n_split;
+  // a unit = (pair, block of kCluster * kUnitRows rows, N split); prm.m_blocks counts those blocks
+  const int64_t units = (int64_t)prm.B * prm.m_blocks * prm.n_split;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int64_t u = cid; u < units; u += ncl, ++it) {
+        const int split = (int)(u % prm.n_split);
+        const int m_blk = (int)((u / prm.n_split) % prm.m_blocks) * kCluster + (int)crank;
+        const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+        const uint32_t aphase = it & 1u;
+        for (int kb = 0; kb < prm.kblocks; ++kb) {        // K block kb was released by the previous unit's last tile
+          mbar_wait(&a_empty[kb], aphase ^ 1u);
+          mbar_expect_tx(&a_full[kb], Cfg::kAKBytes);
+          tma_load_3d(smem_a + (size_t)kb * Cfg::kAKBytes, &map_a, &a_full[kb], kb * kBlockK, m_blk * Cfg::kUnitRows, b);
+        }
+        for (int t = 0; t < tiles_per_unit; ++t) {
+          const int nt = split * tiles_per_unit + t;
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_expect_tx(&b_full[stage], Cfg::kBStageBytes);
+            if (kCluster == 1) {
+              tma_load_3d(smem_b + (size_t)stage * Cfg::kBStageBytes, &map_b, &b_full[stage], kb * kBlockK, nt * kBlockN, b);
+            } else {
+              constexpr int kSlice = kBlockN / kCluster;          // B rows this CTA fetches for the cluster
+              tma_load_3d_mcast(smem_b + (size_t)stage * Cfg::kBStageBytes + (size_t)crank * kSlice * kBlockK * 2, &map_b,
+                                &b_full[stage], kb * kBlockK, nt * kBlockN + (int)crank * kSlice, b, kMask);
+            }
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0, it = 0, tcount = 0;
+      for (int64_t u = cid; u < units; u += ncl, ++it) {
+        const uint32_t aphase = it & 1u;
+        for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+          const uint32_t acc = tcount & 1u;
+          mbar_wait(&t_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+          tcgen05_fence_after();
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            if (t == 0) mbar_wait(&a_full[kb], aphase);
+            mbar_wait(&b_full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * Cfg::kBStageBytes);
+#pragma unroll
+            for (int half = 0; half < kMTiles; ++half) {
+              const uint32_t a_addr = smem_u32(smem_a + (size_t)kb * Cfg::kAKBytes + (size_t)half * kATileBytes);
+              const uint32_t tmem_d = tmem_base + (acc * kMTiles + half) * kBlockN;
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                tcgen05_mma_bf16(tmem_d, umma_desc_sw128(a_addr + k * kUmmaK * 2), umma_desc_sw128(b_addr + k * kUmmaK * 2),
+                                 idesc, (uint32_t)((kb | k) != 0));
+            }
+            if (kCluster == 1) tcgen05_commit(&b_empty[stage]);
+            else tcgen05_commit_mcast(&b_empty[stage], kMask);          // frees the stage in every CTA of the cluster
+            if (t == tiles_per_unit - 1) tcgen05_commit(&a_empty[kb]);   // last use of this A K block
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+          tcgen05_commit(&t_full[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> swizzled smem -> TMA store =================
+    const int ew = warp - 4;
+    const float scale = prm.scale, scale4 = prm.scale * 0.25f;
+    const uint32_t st_base = smem_u32(smem_st + (size_t)ew * kStageWarpBytes);
+    const uint32_t box0 = st_base, box1 = st_base + 4096, boxl = st_base + 8192;
+    const uint32_t row128 = (uint32_t)lane * 128, row64 = (uint32_t)lane * 64;
+    const uint32_t sw128 = (uint32_t)(lane & 7), sw64 = (uint32_t)((lane >> 1) & 3);
+    uint32_t tcount = 0;
+    for (int64_t u = cid; u < units; u += ncl) {
+      const int split = (int)(u % prm.n_split);
+      const int m_blk = (int)((u / prm.n_split) % prm.m_blocks) * kCluster + (int)crank;
+      const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+      for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+        const int nt = split * tiles_per_unit + t;
+        const uint32_t acc = tcount & 1u;
+        mbar_wait(&t_full[acc], (tcount >> 1) & 1u);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < kMTiles; ++half) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * kMTiles + half) * kBlockN;
+          const int row0 = m_blk * Cfg::kUnitRows + half * kBlockM + ew * 32;
+#pragma unroll 1
+          for (int gs = 0; gs < Cfg::kGroups * Cfg::kSteps; ++gs) {
+            const int g = gs / Cfg::kSteps, s = gs - g * Cfg::kSteps;
+            // the staging boxes are free once the previous bulk stores have read them
+            if (prm.store_mode == 0 && lane == 0 && !(prm.debug & 4)) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              if (prm.debug & 2) break;
+              const int c0 = g * 2 * kW + s * 64 + sub * 32;  // source row p   : tile cols [c0, c0+32)
+              const int c1 = c0 + kW;                         // source row p+1 : tile cols [c1, c1+32)
+              uint32_t v0[32], v1[32];
+              tmem_ld_32x32(taddr + c0, v0);
+              tmem_ld_32x32(taddr + c1, v1);
+              tmem_ld_wait();
+              uint32_t p0[16], p1[16], pl[8];
+              float pooled[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
+                const float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
+                p0[j] = pack_bf16(a0 * scale, a1 * scale);
+                p1[j] = pack_bf16(b0 * scale, b1 * scale);
+                pooled[j] = ((a0 + a1) + (b0 + b1)) * scale4;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
+              // 16-byte chunk j of a 128-byte row lands at chunk (j ^ (row & 7))  [SWIZZLE_128B]
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t ch = (uint32_t)(sub * 4 + j) ^ sw128;
+                st_shared_v4(box0 + row128 + ch * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+                st_shared_v4(box1 + row128 + ch * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+              }
+              // 64-byte rows: chunk j lands at chunk (j ^ ((row >> 1) & 3))            [SWIZZLE_64B]
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t ch = (uint32_t)(sub * 2 + j) ^ sw64;
+                st_shared_v4(boxl + row64 + ch * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+              }
+            }
+            if (half == kMTiles - 1 && gs == Cfg::kGroups * Cfg::kSteps - 1) {
+              // every TMEM read of this accumulator stage is done: hand it back to the MMA warp
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&t_empty[acc]);
+            }
+            if (prm.store_mode == 0) {
+              // ---- (a) TMA bulk tensor stores of the three staged boxes ----
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0 && !(prm.debug & 1)) {
+                const int col = nt * kBlockN + g * 2 * kW + s * 64;
+                const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+                tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes, col, row0, b);
+                tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + kW, row0, b);
+                tma_store_3d(&map_v1, smem_st + (size_t)ew * kStageWarpBytes + 8192, colp, row0, b);
+                tma_store_commit();
+              }
+            } else {
+              // ---- (b) read the staged boxes back row-contiguously and store through the LSU:
+              //      every warp instruction writes 4 (or 8) whole rows = full 128-byte lines ----
+              __syncwarp();
+              if (!(prm.debug & 1)) {
+                const int col = nt * kBlockN + g * 2 * kW + s * 64;
+                const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+                const int64_t rbase = (int64_t)b * prm.rows_total + row0;
+                const int rows_ok = (int)min((int64_t)32, prm.rows_total - row0);     // may be <= 0
+                {
+                  const int ch = lane & 7, rsub = lane >> 3;                           // 8 chunks x 4 rows / instr
+#pragma unroll
+                  for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + rsub;
+                    const uint32_t off = (uint32_t)r * 128 + (uint32_t)((ch ^ (r & 7)) * 16);
+                    uint4 x0, x1;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0.x), "=r"(x0.y), "=r"(x0.z), "=r"(x0.w) : "r"(box0 + off));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x1.x), "=r"(x1.y), "=r"(x1.z), "=r"(x1.w) : "r"(box1 + off));
+                    if (r < rows_ok) {
+                      __nv_bfloat16* o = prm.vol0 + (rbase + r) * prm.N + col + ch * 8;
+                      st_global_v4(o, x0.x, x0.y, x0.z, x0.w);
+                      st_global_v4(o + kW, x1.x, x1.y, x1.z, x1.w);
+                    }
+                  }
+                }
+                {
+                  const int ch = lane & 3, rsub = lane >> 2;                           // 4 chunks x 8 rows / instr
+#pragma unroll
+                  for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + rsub;
+                    const uint32_t off = (uint32_t)r * 64 + (uint32_t)((ch ^ ((r >> 1) & 3)) * 16);
+                    uint4 x;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(boxl + off));
+                    if (r < rows_ok) st_global_v4(prm.vol1 + (rbase + r) * (prm.N / 4) + colp + ch * 8, x.x, x.y, x.z, x.w);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA leaves while its peer can still multicast into it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -449,17 +824,92 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_operand_map(CUtensorMap* map, const void* base, int C, int64_t rows, int B, int box_rows) {
+static int make_bf16_map(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int B, int box_cols,
+                         int box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MRFA_E_DRIVER;
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : MRFA_E_DRIVER;
+}
+
+static int make_operand_map(CUtensorMap* map, const void* base, int C, int64_t rows, int B, int box_rows) {
+  return make_bf16_map(map, base, C, rows, B, kBlockK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int kW, int kBlockN_, int kMTiles, int kCluster>
+static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, void* v1, int B, int C, int h, int w,
+                                  float scale, int num_sms, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<kW, kBlockN_, kMTiles>;
+  Gemm2Params prm;
+  prm.B = B;
+  prm.kblocks = C / kBlockK;
+  const int N = h * w;
+  const int64_t rows_total = mrfa_corr_rows_total(h, w);
+  prm.m_blocks = (int)cdiv64(rows_total, Cfg::kUnitRows * kCluster);
+  prm.n_tiles = N / Cfg::kBlockN;
+  prm.scale = scale;
+  const uint32_t fixed = (uint32_t)prm.kblocks * Cfg::kAKBytes + 4 * kStageWarpBytes + 2048;
+  const uint32_t budget = 227 * 1024;
+  if (fixed + 2 * Cfg::kBStageBytes > budget) return MRFA_E_SHAPE;
+  int stages = (int)((budget - fixed) / Cfg::kBStageBytes);
+  prm.b_stages = stages > 8 ? 8 : stages;
+  const uint32_t smem_bytes = fixed + prm.b_stages * Cfg::kBStageBytes;
+  int n_split = 1;
+  while ((int64_t)B * prm.m_blocks * n_split < 2ll * num_sms && n_split * 2 <= prm.n_tiles &&
+         prm.n_tiles % (n_split * 2) == 0)
+    n_split *= 2;
+  {
+    const char* e = getenv("MRFA_CORR_NSPLIT");
+    if (e && atoi(e) > 0 && prm.n_tiles % atoi(e) == 0) n_split = atoi(e);
+  }
+  prm.n_split = n_split;
+  {
+    const char* e = getenv("MRFA_CORR_DEBUG");
+    prm.debug = e ? atoi(e) : 0;
+    const char* m = getenv("MRFA_CORR_STORE");
+    prm.store_mode = m ? atoi(m) : 1;
+  }
+  prm.N = N;
+  prm.rows_total = rows_total;
+  prm.vol0 = static_cast<__nv_bfloat16*>(v0);
+  prm.vol1 = static_cast<__nv_bfloat16*>(v1);
+
+  CUtensorMap map_a, map_b, map_v0, map_v1;
+  int rc = make_operand_map(&map_a, a_op, C, rows_total, B, Cfg::kUnitRows);
+  if (rc) return rc;
+  rc = make_operand_map(&map_b, b_op, C, N, B, Cfg::kBlockN / kCluster);
+  if (rc) return rc;
+  rc = make_bf16_map(&map_v0, v0, N, rows_total, B, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_bf16_map(&map_v1, v1, N / 4, rows_total, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+
+  auto kern = corr_volume_tma_kernel<kW, kBlockN_, kMTiles, kCluster>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t units = (int64_t)B * prm.m_blocks * n_split;
+  int64_t clusters = num_sms / kCluster;
+  if (units < clusters) clusters = units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * kCluster));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_v0, map_v1, prm);
+  return (int)e;
 }
 
 template <int kW>
@@ -517,11 +967,21 @@ extern "C" int64_t mrfa_corr_row_offset(int h, int w, int pool_log2) {
 }
 
 extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op, int B, int C, int h, int w,
-                              mrfa_stream_t stream) {
+                              int channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(q_d && k_s && a_op && b_op && B >= 0 && C > 0 && h > 0 && w > 0);
   MRFA_CHECK_SHAPE(C % kPackCh == 0 && h % 8 == 0 && w % 8 == 0 && B <= 65535);
   MRFA_CHECK_SHAPE(w <= 32 || w % 32 == 0);
   if (B == 0) return 0;
+  if (channels_last) {
+    if (((reinterpret_cast<uintptr_t>(q_d) | reinterpret_cast<uintptr_t>(k_s)) & 15) != 0) return MRFA_E_ALIGN;
+    const int64_t total = (int64_t)B * (mrfa_corr_rows_total(h, w) + (int64_t)h * w) * (C / 4);
+    int64_t blocks = cdiv64(total, 256);
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    corr_pack_nhwc_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), B, C, h, w,
+        mrfa_corr_rows_total(h, w));
+    return MRFA_LAUNCH_RESULT();
+  }
   const int tile_w = w < 32 ? w : 32;
   dim3 grid((unsigned)((h / kPackRows) * (w / tile_w)), (unsigned)(2 * C / kPackCh), (unsigned)B);
   const size_t smem = (size_t)kPackCh * (kPackRows * tile_w + 1) * sizeof(float);
@@ -529,6 +989,23 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
       q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), C, h, w, tile_w,
       mrfa_corr_rows_total(h, w));
   return MRFA_LAUNCH_RESULT();
+}
+
+// MRFA_CORR_EPILOGUE=direct selects the v1 register-store epilogue (A/B measurements only)
+static bool use_direct_epilogue() {
+  static const bool v = []() {
+    const char* e = getenv("MRFA_CORR_EPILOGUE");
+    return e != nullptr && e[0] == 'd';
+  }();
+  return v;
+}
+
+static int corr_variant() {      // MRFA_CORR_VARIANT=1: 256-row units x 128-wide tiles (A/B measurements only)
+  static const int v = []() {
+    const char* e = getenv("MRFA_CORR_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume0, void* volume1, int B, int C, int h,
@@ -546,8 +1023,20 @@ extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume
     case 8: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<8>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 16: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<16>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 32: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<32>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-    case 64: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<64>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-    case 128: MRFA_CHECK_SHAPE(N % 256 == 0); return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 64:
+      MRFA_CHECK_SHAPE(N % 128 == 0);
+      if (use_direct_epilogue()) return launch_corr_volume<64>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      // 128-row units, 256-wide tiles (two source row pairs): every B tile (32 KiB per K block) feeds
+      // 128x256 outputs and ~96 KiB of B stay in flight; deeper K falls back to 128-wide tiles
+      if (corr_variant() == 1) return launch_corr_volume_tma<64, 128, 2, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 2 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      return launch_corr_volume_tma<64, 128, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+    case 128:
+      MRFA_CHECK_SHAPE(N % 256 == 0);
+      if (use_direct_epilogue()) return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 2) return launch_corr_volume_tma<128, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      return launch_corr_volume_tma<128, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     default: return MRFA_E_SHAPE;
   }
 }

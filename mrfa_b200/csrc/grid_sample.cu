@@ -184,6 +184,170 @@ grid_sample_bwd_kernel(const float* __restrict__ grad_out, const float* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// channels-last (NHWC) variants: the memory layout cuDNN's tensor-core convolutions produce on
+// sm_100.  A tap is C contiguous floats, so 16 lanes x float4 read one tap of one pixel as 256
+// contiguous bytes (C = 64) and the store is a full line -- no scalar gathers at all.
+// Thread group = 16 lanes per output pixel (2 pixels per warp); lane j walks channel quads
+// j, j+16, ...  (C % 4 == 0).
+// ---------------------------------------------------------------------------------------------
+constexpr int kNhwcGroup = 16;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 blend4(float4 a, float4 b, float4 c, float4 d, const Taps& t) {
+  float4 r;
+  r.x = fmaf(d.x, t.w_se, fmaf(c.x, t.w_sw, fmaf(b.x, t.w_ne, a.x * t.w_nw)));
+  r.y = fmaf(d.y, t.w_se, fmaf(c.y, t.w_sw, fmaf(b.y, t.w_ne, a.y * t.w_nw)));
+  r.z = fmaf(d.z, t.w_se, fmaf(c.z, t.w_sw, fmaf(b.z, t.w_ne, a.z * t.w_nw)));
+  r.w = fmaf(d.w, t.w_se, fmaf(c.w, t.w_sw, fmaf(b.w, t.w_ne, a.w * t.w_nw)));
+  return r;
+}
+
+template <int MODE, int PAD, bool ADD_ID>
+__global__ void __launch_bounds__(kThreads)
+grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
+                            float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div) {
+  const int HoWo = Ho * Wo;
+  const int64_t gp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kNhwcGroup;
+  const int j = threadIdx.x % kNhwcGroup;
+  if (gp >= (int64_t)N * HoWo) return;
+  const int n = (int)(gp / HoWo);
+  const int p = (int)(gp - (int64_t)n * HoWo);
+  const int y = p / Wo, x = p - y * Wo;
+  float ix, iy, mx, my;
+  load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
+  const Taps t = make_taps(ix, iy, H, W);
+  const float* src = in + (int64_t)(n / in_batch_div) * H * W * C;
+  float* dst = out + gp * C;
+  const float* p_nw = src + (int64_t)t.o_nw * C;
+  const float* p_ne = src + (int64_t)t.o_ne * C;
+  const float* p_sw = src + (int64_t)t.o_sw * C;
+  const float* p_se = src + (int64_t)t.o_se * C;
+  for (int c = j * 4; c < C; c += kNhwcGroup * 4 * 2) {
+    // two channel quads per iteration: 8 independent 16-byte loads in flight
+    const int c2 = c + kNhwcGroup * 4;
+    const float4 a0 = ldg4(p_nw + c), b0 = ldg4(p_ne + c), d0 = ldg4(p_sw + c), e0 = ldg4(p_se + c);
+    if (c2 < C) {
+      const float4 a1 = ldg4(p_nw + c2), b1 = ldg4(p_ne + c2), d1 = ldg4(p_sw + c2), e1 = ldg4(p_se + c2);
+      stcs4(dst + c, blend4(a0, b0, d0, e0, t));
+      stcs4(dst + c2, blend4(a1, b1, d1, e1, t));
+    } else {
+      stcs4(dst + c, blend4(a0, b0, d0, e0, t));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
+                          float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W) {
+  const int HW = H * W;
+  const int64_t gp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kNhwcGroup;
+  const int j = threadIdx.x % kNhwcGroup;
+  if (gp >= (int64_t)N * HW) return;
+  const int n = (int)(gp / HW);
+  const int p = (int)(gp - (int64_t)n * HW);
+  const int y = p / W, x = p - y * W;
+  const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
+  const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
+  const Taps tr = make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W);
+  const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
+  const Taps tc = make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W);
+  const float* src = in + (int64_t)n * HW * C;
+  float* dr = out_r + gp * C;
+  float* dc = out_c + gp * C;
+  for (int c = j * 4; c < C; c += kNhwcGroup * 4) {
+    const float4 a0 = ldg4(src + (int64_t)tr.o_nw * C + c), a1 = ldg4(src + (int64_t)tr.o_ne * C + c);
+    const float4 a2 = ldg4(src + (int64_t)tr.o_sw * C + c), a3 = ldg4(src + (int64_t)tr.o_se * C + c);
+    const float4 b0 = ldg4(src + (int64_t)tc.o_nw * C + c), b1 = ldg4(src + (int64_t)tc.o_ne * C + c);
+    const float4 b2 = ldg4(src + (int64_t)tc.o_sw * C + c), b3 = ldg4(src + (int64_t)tc.o_se * C + c);
+    stcs4(dr + c, blend4(a0, a1, a2, a3, tr));
+    stcs4(dc + c, blend4(b0, b1, b2, b3, tc));
+  }
+}
+
+// NHWC backward: one thread group (16 lanes) per output pixel; the grad_input scatter is a
+// vector red.global.add.v4.f32 per tap and channel quad; the coordinate gradient is reduced over
+// the channel axis with shuffles inside the 16-lane group.
+template <int MODE, int PAD, bool ADD_ID>
+__global__ void __launch_bounds__(kThreads)
+grid_sample_bwd_nhwc_kernel(const float* __restrict__ grad_out, const float* __restrict__ in,
+                            const float* __restrict__ grid, mrfa_grid_strides_t gs, float* __restrict__ grad_in,
+                            float* __restrict__ grad_grid, int N, int C, int H, int W, int Ho, int Wo,
+                            int in_batch_div) {
+  const int HoWo = Ho * Wo;
+  const int64_t gp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kNhwcGroup;
+  const int j = threadIdx.x % kNhwcGroup;
+  const bool live = gp < (int64_t)N * HoWo;
+  float gix = 0.f, giy = 0.f, mx = 0.f, my = 0.f;
+  if (live) {
+    const int n = (int)(gp / HoWo);
+    const int p = (int)(gp - (int64_t)n * HoWo);
+    const int y = p / Wo, x = p - y * Wo;
+    float ix, iy;
+    load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
+    const Taps t = make_taps(ix, iy, H, W);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float ax = ix - fx, ay = iy - fy, bx = (fx + 1.f) - ix, by = (fy + 1.f) - iy;
+    const bool fin = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+    const int x0 = fin ? (int)fx : -2, y0 = fin ? (int)fy : -2;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
+    const int64_t ibase = (int64_t)(n / in_batch_div) * H * W * C;
+    const float* go = grad_out + gp * C;
+    for (int c = j * 4; c < C; c += kNhwcGroup * 4) {
+      const float4 g = ldg4(go + c);
+      if (grad_in != nullptr) {
+        float* gi = grad_in + ibase + c;
+        if (t.w_nw != 0.f) atomicAdd(reinterpret_cast<float4*>(gi + (int64_t)t.o_nw * C), make_float4(g.x * t.w_nw, g.y * t.w_nw, g.z * t.w_nw, g.w * t.w_nw));
+        if (t.w_ne != 0.f) atomicAdd(reinterpret_cast<float4*>(gi + (int64_t)t.o_ne * C), make_float4(g.x * t.w_ne, g.y * t.w_ne, g.z * t.w_ne, g.w * t.w_ne));
+        if (t.w_sw != 0.f) atomicAdd(reinterpret_cast<float4*>(gi + (int64_t)t.o_sw * C), make_float4(g.x * t.w_sw, g.y * t.w_sw, g.z * t.w_sw, g.w * t.w_sw));
+        if (t.w_se != 0.f) atomicAdd(reinterpret_cast<float4*>(gi + (int64_t)t.o_se * C), make_float4(g.x * t.w_se, g.y * t.w_se, g.z * t.w_se, g.w * t.w_se));
+      }
+      if (grad_grid != nullptr) {
+        const float* s = in + ibase + c;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 nw = (vx0 & vy0) ? ldg4(s + (int64_t)t.o_nw * C) : z;
+        const float4 ne = (vx1 & vy0) ? ldg4(s + (int64_t)t.o_ne * C) : z;
+        const float4 sw = (vx0 & vy1) ? ldg4(s + (int64_t)t.o_sw * C) : z;
+        const float4 se = (vx1 & vy1) ? ldg4(s + (int64_t)t.o_se * C) : z;
+        gix += g.x * ((ne.x - nw.x) * by + (se.x - sw.x) * ay) + g.y * ((ne.y - nw.y) * by + (se.y - sw.y) * ay) +
+               g.z * ((ne.z - nw.z) * by + (se.z - sw.z) * ay) + g.w * ((ne.w - nw.w) * by + (se.w - sw.w) * ay);
+        giy += g.x * ((sw.x - nw.x) * bx + (se.x - ne.x) * ax) + g.y * ((sw.y - nw.y) * bx + (se.y - ne.y) * ax) +
+               g.z * ((sw.z - nw.z) * bx + (se.z - ne.z) * ax) + g.w * ((sw.w - nw.w) * bx + (se.w - ne.w) * ax);
+      }
+    }
+  }
+  if (grad_grid == nullptr) return;
+#pragma unroll
+  for (int o = kNhwcGroup / 2; o > 0; o >>= 1) {
+    gix += __shfl_xor_sync(0xffffffffu, gix, o);
+    giy += __shfl_xor_sync(0xffffffffu, giy, o);
+  }
+  if (live && j == 0) reinterpret_cast<float2*>(grad_grid)[gp] = make_float2(gix * mx, giy * my);
+}
+
+template <int MODE, int PAD>
+static int launch_fwd_nhwc(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C, int H,
+                           int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
+  dim3 g((unsigned)cdiv64((int64_t)N * Ho * Wo * kNhwcGroup, kThreads));
+  if (add_id) grid_sample_fwd_nhwc_kernel<MODE, PAD, true><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);
+  else grid_sample_fwd_nhwc_kernel<MODE, PAD, false><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);
+  return MRFA_LAUNCH_RESULT();
+}
+
+template <int MODE, int PAD>
+static int launch_bwd_nhwc(const float* go, const float* in, const float* grid, mrfa_grid_strides_t gs, float* gi,
+                           float* gg, int N, int C, int H, int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
+  dim3 g((unsigned)cdiv64((int64_t)N * Ho * Wo * kNhwcGroup, kThreads));
+  if (add_id)
+    grid_sample_bwd_nhwc_kernel<MODE, PAD, true><<<g, kThreads, 0, st>>>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div);
+  else
+    grid_sample_bwd_nhwc_kernel<MODE, PAD, false><<<g, kThreads, 0, st>>>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div);
+  return MRFA_LAUNCH_RESULT();
+}
+
 template <int MODE, int PAD>
 static int launch_fwd(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C, int H,
                       int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
@@ -223,34 +387,55 @@ using namespace mrfa;
 
 extern "C" int mrfa_grid_sample_fwd(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N,
                                     int C, int H, int W, int Ho, int Wo, int in_batch_div, int coord_mode,
-                                    int padding_mode, int add_identity, mrfa_stream_t stream) {
+                                    int padding_mode, int add_identity, int channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(in && grid && out);
   MRFA_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && in_batch_div >= 1);
   MRFA_CHECK_ARG(N % in_batch_div == 0);
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31) && (int64_t)Ho * Wo < (1ll << 31));
   if (N == 0) return 0;
+  if (channels_last) {
+    MRFA_CHECK_SHAPE(C % 4 == 0);
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return MRFA_E_ALIGN;
+    DISPATCH_MODE_PAD(launch_fwd_nhwc, in, grid, gs, out, N, C, H, W, Ho, Wo, in_batch_div, add_identity, as_stream(stream));
+  }
   DISPATCH_MODE_PAD(launch_fwd, in, grid, gs, out, N, C, H, W, Ho, Wo, in_batch_div, add_identity, as_stream(stream));
 }
 
 extern "C" int mrfa_grid_sample_bwd(const float* grad_out, const float* in, const float* grid,
                                     mrfa_grid_strides_t gs, float* grad_in, float* grad_grid, int N, int C, int H,
                                     int W, int Ho, int Wo, int in_batch_div, int coord_mode, int padding_mode,
-                                    int add_identity, mrfa_stream_t stream) {
+                                    int add_identity, int channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(grad_out && in && grid && (grad_in || grad_grid));
   MRFA_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && in_batch_div >= 1);
   MRFA_CHECK_ARG(N % in_batch_div == 0);
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31) && (int64_t)Ho * Wo < (1ll << 31));
   if (N == 0) return 0;
+  if (channels_last) {
+    MRFA_CHECK_SHAPE(C % 4 == 0);
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_in)) & 15) != 0)
+      return MRFA_E_ALIGN;
+    DISPATCH_MODE_PAD(launch_bwd_nhwc, grad_out, in, grid, gs, grad_in, grad_grid, N, C, H, W, Ho, Wo, in_batch_div,
+                      add_identity, as_stream(stream));
+  }
   DISPATCH_MODE_PAD(launch_bwd, grad_out, in, grid, gs, grad_in, grad_grid, N, C, H, W, Ho, Wo, in_batch_div,
                     add_identity, as_stream(stream));
 }
 
 extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid, float* out_refined,
-                                  float* out_coarse, int N, int C, int H, int W, mrfa_stream_t stream) {
+                                  float* out_coarse, int N, int C, int H, int W, int channels_last,
+                                  mrfa_stream_t stream) {
   MRFA_CHECK_ARG(in && flow && prior_grid && out_refined && out_coarse);
   MRFA_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0);
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31));
   if (N == 0) return 0;
+  if (channels_last) {
+    MRFA_CHECK_SHAPE(C % 4 == 0);
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_refined) | reinterpret_cast<uintptr_t>(out_coarse)) & 15) != 0)
+      return MRFA_E_ALIGN;
+    dim3 gn((unsigned)cdiv64((int64_t)N * H * W * kNhwcGroup, kThreads));
+    dual_warp_fwd_nhwc_kernel<<<gn, kThreads, 0, as_stream(stream)>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W);
+    return MRFA_LAUNCH_RESULT();
+  }
   dim3 g((unsigned)cdiv64((int64_t)N * H * W, kWarpPix), (unsigned)cdiv64(C, kCPT * (kThreads / kWarpPix)));
   dual_warp_fwd_kernel<<<g, kThreads, 0, as_stream(stream)>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W);
   return MRFA_LAUNCH_RESULT();

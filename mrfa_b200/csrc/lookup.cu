@@ -45,7 +45,8 @@ __device__ __forceinline__ QueryGeom query_geom(float cx, float cy, int lvl, int
 template <typename T, int R>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level1, const float* __restrict__ coords,
-                       float* __restrict__ out, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset) {
+                       float* __restrict__ out, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
+                       int out_channels_last) {
   constexpr int n = 2 * R + 1, F = n + 1, FF = F * F;
   constexpr int kStride = 2 * FF + 1;                 // odd -> conflict-free lane-per-query reads
   __shared__ float foot[kQPB * kStride];
@@ -81,6 +82,27 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   }
   __syncthreads();
 
+  if (out_channels_last) {
+    // ---- phase 2 (NHWC output): warp per query, lanes along the 2*(2r+1)^2 contiguous channels
+    for (int qi = warp; qi < kQPB; qi += kLookupThreads / 32) {
+      const int q = q0 + qi;
+      if (q >= Q) break;
+      const float* fq = foot + qi * kStride;
+      float* dst = out + ((int64_t)b * Q + q) * (2 * n * n);
+      for (int k = lane; k < 2 * n * n; k += 32) {
+        const int lvl = k / (n * n), kk = k - lvl * n * n;
+        const int a = kk / n, bb = kk - a * n;
+        const float fx = frac[qi][2 * lvl], fy = frac[qi][2 * lvl + 1];
+        const float* c = fq + lvl * FF + bb * F + a;
+        float acc = c[0] * ((1.f - fx) * (1.f - fy));
+        acc = fmaf(c[1], fx * (1.f - fy), acc);
+        acc = fmaf(c[F], (1.f - fx) * fy, acc);
+        acc = fmaf(c[F + 1], fx * fy, acc);
+        __stcs(dst + k, acc);
+      }
+    }
+    return;
+  }
   // ---- phase 2: lane = query, warps stride over the output channels ----------------------
   const int q = q0 + lane;
   if (q >= Q) return;
@@ -212,15 +234,15 @@ using namespace mrfa;
 
 template <typename T>
 static int launch_lookup_fwd(const void* l0, const void* l1, const float* coords, float* out, int B, int Q, int H,
-                             int W, int64_t mbs, int64_t ro, int radius, cudaStream_t st) {
+                             int W, int64_t mbs, int64_t ro, int radius, int ocl, cudaStream_t st) {
   dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
   const T* a = static_cast<const T*>(l0);
   const T* b = static_cast<const T*>(l1);
   switch (radius) {
-    case 1: corr_lookup_fwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
-    case 2: corr_lookup_fwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
-    case 3: corr_lookup_fwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
-    case 4: corr_lookup_fwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro); break;
+    case 1: corr_lookup_fwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 2: corr_lookup_fwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 3: corr_lookup_fwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 4: corr_lookup_fwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
     default: return MRFA_E_SHAPE;
   }
   return MRFA_LAUNCH_RESULT();
@@ -245,14 +267,14 @@ static int launch_lookup_bwd(const float* go, const void* l0, const void* l1, co
 
 extern "C" int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16, const float* coords,
                                     float* out, int B, int Q, int H, int W, int64_t map_batch_stride,
-                                    int64_t row_offset, int radius, mrfa_stream_t stream) {
+                                    int64_t row_offset, int radius, int out_channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(level0 && level1 && coords && out);
   MRFA_CHECK_ARG(B >= 0 && Q > 0 && H >= 2 && W >= 2 && map_batch_stride >= 0 && row_offset >= 0);
   MRFA_CHECK_SHAPE(radius >= 1 && radius <= kMaxR && B <= 65535);
   if (B == 0) return 0;
   if (elem_bf16)
-    return launch_lookup_fwd<__nv_bfloat16>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
-  return launch_lookup_fwd<float>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+    return launch_lookup_fwd<__nv_bfloat16>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, as_stream(stream));
+  return launch_lookup_fwd<float>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, as_stream(stream));
 }
 
 extern "C" int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* level1, int elem_bf16,

@@ -34,6 +34,32 @@ def _req(t: Tensor, name: str, dtype=torch.float32) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _is_channels_last(t: Tensor) -> bool:
+    """NHWC in memory (and not simultaneously NCHW-contiguous), with a vectorisable channel count."""
+    return (t.dim() == 4 and t.shape[1] % 4 == 0 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _req_image(t: Tensor, name: str):
+    """float32 CUDA image in either NCHW or NHWC memory; returns (tensor, channels_last flag)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"mrfa_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"mrfa_b200: `{name}` must be float32, got {t.dtype}")
+    if _is_channels_last(t):
+        return t, True
+    return (t if t.is_contiguous() else t.contiguous()), False
+
+
+def _like_layout(t: Tensor, channels_last: bool) -> Tensor:
+    return t.contiguous(memory_format=torch.channels_last) if channels_last else t.contiguous()
+
+
+def _empty_image(shape, device, channels_last: bool) -> Tensor:
+    return torch.empty(shape, device=device, dtype=torch.float32,
+                       memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+
+
 def _grid_strides(grid: Tensor) -> GridStrides:
     s = grid.stride()
     return GridStrides(s[0], s[1], s[2], s[3])
@@ -106,34 +132,35 @@ def sm_count(device) -> int:
 @torch.library.custom_op("mrfa::grid_sample", mutates_args=(), device_types="cuda")
 def grid_sample(inp: Tensor, grid: Tensor, coord_mode: int, padding_mode: int, add_identity: bool,
                 in_batch_div: int) -> Tensor:
-    inp = _req(inp, "input")
+    inp, cl = _req_image(inp, "input")
     if not grid.is_cuda or grid.dtype != torch.float32 or grid.dim() != 4 or grid.shape[-1] != 2:
         raise RuntimeError("mrfa_b200: grid must be a CUDA float32 tensor of logical shape (N,Ho,Wo,2)")
     N, Ho, Wo, _ = grid.shape
     Nin, C, H, W = inp.shape
     if Nin * in_batch_div != N:
         raise RuntimeError(f"mrfa_b200: grid batch {N} != input batch {Nin} * {in_batch_div}")
-    out = torch.empty((N, C, Ho, Wo), device=inp.device, dtype=torch.float32)
+    out = _empty_image((N, C, Ho, Wo), inp.device, cl)
     if out.numel() == 0:
         return out
     with torch.cuda.device(inp.device):
         with _timed("grid_sample_fwd", 4 * (N * C * Ho * Wo + Nin * C * H * W + 2 * N * Ho * Wo)):
             check(lib.mrfa_grid_sample_fwd(_p(inp), _p(grid), _grid_strides(grid), _p(out), N, C, H, W, Ho, Wo,
-                                           in_batch_div, coord_mode, padding_mode, int(add_identity), _stream()),
+                                           in_batch_div, coord_mode, padding_mode, int(add_identity), int(cl), _stream()),
                   "mrfa_grid_sample_fwd")
     return out
 
 
 @grid_sample.register_fake
 def _(inp, grid, coord_mode, padding_mode, add_identity, in_batch_div):
-    return inp.new_empty((grid.shape[0], inp.shape[1], grid.shape[1], grid.shape[2]))
+    out = inp.new_empty((grid.shape[0], inp.shape[1], grid.shape[1], grid.shape[2]))
+    return out.contiguous(memory_format=torch.channels_last) if _is_channels_last(inp) else out
 
 
 @torch.library.custom_op("mrfa::grid_sample_bwd", mutates_args=(), device_types="cuda")
 def grid_sample_bwd(grad_out: Tensor, inp: Tensor, grid: Tensor, coord_mode: int, padding_mode: int,
                     add_identity: bool, in_batch_div: int, need_input: bool, need_grid: bool) -> Tuple[Tensor, Tensor]:
-    grad_out = _req(grad_out, "grad_out")
-    inp = _req(inp, "input")
+    inp, cl = _req_image(inp, "input")
+    grad_out = _like_layout(_req_image(grad_out, "grad_out")[0], cl)
     N, Ho, Wo, _ = grid.shape
     _, C, H, W = inp.shape
     g_in = torch.zeros_like(inp) if need_input else inp.new_empty(0)
@@ -143,7 +170,7 @@ def grid_sample_bwd(grad_out: Tensor, inp: Tensor, grid: Tensor, coord_mode: int
             check(lib.mrfa_grid_sample_bwd(_p(grad_out), _p(inp), _p(grid), _grid_strides(grid),
                                            _p(g_in) if need_input else None, _p(g_grid) if need_grid else None,
                                            N, C, H, W, Ho, Wo, in_batch_div, coord_mode, padding_mode, int(add_identity),
-                                           _stream()), "mrfa_grid_sample_bwd")
+                                           int(cl), _stream()), "mrfa_grid_sample_bwd")
     return g_in, g_grid
 
 
@@ -171,14 +198,14 @@ grid_sample.register_autograd(_gs_backward, setup_context=_gs_setup)
 
 @torch.library.custom_op("mrfa::dual_warp", mutates_args=(), device_types="cuda")
 def dual_warp(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Tensor]:
-    inp, flow, prior_grid = _req(inp, "input"), _req(flow, "flow"), _req(prior_grid, "prior_grid")
+    (inp, cl), flow, prior_grid = _req_image(inp, "input"), _req(flow, "flow"), _req(prior_grid, "prior_grid")
     N, C, H, W = inp.shape
     if tuple(flow.shape) != (N, 2, H, W) or tuple(prior_grid.shape) != (N, H, W, 2):
         raise RuntimeError("mrfa_b200: dual_warp expects flow (N,2,H,W) and prior_grid (N,H,W,2) at the feature size")
     out_r, out_c = torch.empty_like(inp), torch.empty_like(inp)
     with torch.cuda.device(inp.device):
         with _timed("dual_warp_fwd", 4 * (3 * inp.numel() + 4 * N * H * W)):
-            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, _stream()),
+            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, int(cl), _stream()),
                   "mrfa_dual_warp_fwd")
     return out_r, out_c
 
@@ -396,7 +423,9 @@ def corr_row_offset(h: int, w: int, pool_log2: int) -> int:
 @torch.library.custom_op("mrfa::corr_pyramid", mutates_args=(), device_types="cuda")
 def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
     """(B,C,h,w) x2 -> volume0 (B, rows_total, h*w) bf16, volume1 (B, rows_total, h*w/4) bf16."""
-    q_d, k_s = _req(q_d, "q_d"), _req(k_s, "k_s")
+    (q_d, cl), (k_s, cl2) = _req_image(q_d, "q_d"), _req_image(k_s, "k_s")
+    if cl != cl2:
+        k_s = _like_layout(k_s, cl)
     B, C, h, w = q_d.shape
     rows = corr_rows_total(h, w)
     dev = q_d.device
@@ -407,7 +436,7 @@ def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor
     with torch.cuda.device(dev):
         st = _stream()
         with _timed("corr_pack", 8 * q_d.numel() + 2 * (a_op.numel() + b_op.numel())):
-            check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, st), "mrfa_corr_pack")
+            check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, int(cl), st), "mrfa_corr_pack")
         # algorithmic FLOPs: the basic-resolution contraction only; bytes: operands + pyramid
         with _timed("corr_volume", 2 * (a_op.numel() + b_op.numel() + vol0.numel() + vol1.numel()),
                     2 * B * (h * w) ** 2 * C):
@@ -426,12 +455,14 @@ def _(q_d, k_s, scale):
 
 def corr_pack_debug(q_d: Tensor, k_s: Tensor) -> Tuple[Tensor, Tensor]:
     """Packed bf16 operands only (test / profiling helper)."""
-    q_d, k_s = _req(q_d, "q_d"), _req(k_s, "k_s")
+    (q_d, cl), (k_s, cl2) = _req_image(q_d, "q_d"), _req_image(k_s, "k_s")
+    if cl != cl2:
+        k_s = _like_layout(k_s, cl)
     B, C, h, w = q_d.shape
     a_op = torch.empty((B, corr_rows_total(h, w), C), device=q_d.device, dtype=torch.bfloat16)
     b_op = torch.empty((B, h * w, C), device=q_d.device, dtype=torch.bfloat16)
     with torch.cuda.device(q_d.device):
-        check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, _stream()), "mrfa_corr_pack")
+        check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, int(cl), _stream()), "mrfa_corr_pack")
     return a_op, b_op
 
 
@@ -469,7 +500,7 @@ avg_pool2x2.register_autograd(_ap_backward, setup_context=_ap_setup)
 
 @torch.library.custom_op("mrfa::corr_lookup", mutates_args=(), device_types="cuda")
 def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, map_batch_stride: int,
-                row_offset: int, radius: int) -> Tensor:
+                row_offset: int, radius: int, channels_last: bool) -> Tensor:
     """coords (B,2,h1,w1) -> (B, 2*(2r+1)^2, h1, w1).  level maps fp32 or bf16 (see the header)."""
     coords = _req(coords, "coords")
     if level0.dtype != level1.dtype or level0.dtype not in (torch.float32, torch.bfloat16):
@@ -478,19 +509,20 @@ def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, 
         raise RuntimeError("mrfa_b200: correlation levels must be contiguous CUDA tensors")
     B, _, h1, w1 = coords.shape
     n = 2 * radius + 1
-    out = torch.empty((B, 2 * n * n, h1, w1), device=coords.device, dtype=torch.float32)
+    out = _empty_image((B, 2 * n * n, h1, w1), coords.device, channels_last)
     with torch.cuda.device(coords.device):
         with _timed("corr_lookup_fwd", B * h1 * w1 * (2 * (2 * radius + 2) ** 2 * level0.element_size() + 8 + 4 * 2 * n * n)):
             check(lib.mrfa_corr_lookup_fwd(_p(level0), _p(level1), int(level0.dtype == torch.bfloat16), _p(coords), _p(out),
-                                           B, h1 * w1, H, W, map_batch_stride, row_offset, radius, _stream()),
-                  "mrfa_corr_lookup_fwd")
+                                           B, h1 * w1, H, W, map_batch_stride, row_offset, radius, int(channels_last),
+                                           _stream()), "mrfa_corr_lookup_fwd")
     return out
 
 
 @corr_lookup.register_fake
-def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius):
+def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius, channels_last):
     B, _, h1, w1 = coords.shape
-    return coords.new_empty((B, 2 * (2 * radius + 1) ** 2, h1, w1))
+    out = coords.new_empty((B, 2 * (2 * radius + 1) ** 2, h1, w1))
+    return out.contiguous(memory_format=torch.channels_last) if channels_last else out
 
 
 @torch.library.custom_op("mrfa::corr_lookup_bwd", mutates_args=(), device_types="cuda")
@@ -519,7 +551,7 @@ def _(grad_out, level0, level1, coords, H, W, map_batch_stride, row_offset, radi
 
 
 def _cl_setup(ctx, inputs, output):
-    level0, level1, coords, H, W, mbs, ro, radius = inputs
+    level0, level1, coords, H, W, mbs, ro, radius, _cl = inputs
     ctx.save_for_backward(level0, level1, coords)
     ctx.cfg = (H, W, mbs, ro, radius)
 
@@ -531,7 +563,7 @@ def _cl_backward(ctx, g):
     g0, g1, gc = torch.ops.mrfa.corr_lookup_bwd(g, level0, level1, coords, *ctx.cfg, need_levels, need_coords)
     return (g0.to(level0.dtype) if ctx.needs_input_grad[0] else None,
             g1.to(level1.dtype) if ctx.needs_input_grad[1] else None,
-            gc if need_coords else None, None, None, None, None, None)
+            gc if need_coords else None, None, None, None, None, None, None)
 
 
 corr_lookup.register_autograd(_cl_backward, setup_context=_cl_setup)

@@ -49,6 +49,11 @@ class DenseMotionNetwork(nn.Module):
         if self.scale_factor != 1:
             self.down = AntiAliasInterpolation2d(num_channels, self.scale_factor)
 
+    def channels_last_(self, enable: bool = True):
+        """Run the hourglass convolutions in NHWC memory (see RaftFlow.channels_last_)."""
+        self.to(memory_format=torch.channels_last if enable else torch.contiguous_format)
+        return self
+
     # --- the three reference helper methods, each backed by the fused kernel -------------------
     def _prior(self, source_image, kp_driving, kp_source, bg_param):
         jd, js = kp_driving.get("jacobian"), kp_source.get("jacobian")

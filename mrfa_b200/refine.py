@@ -81,6 +81,16 @@ class RaftFlow(nn.Module):
         self.refine = RefineFlow()
         self.to_context = nn.ModuleList(nn.Conv2d(widths[i], 192, 1, padding=0) for i in range(self.num_iter))
 
+    channels_last = False
+
+    def channels_last_(self, enable: bool = True):
+        """Run the decoder in NHWC memory (torch.channels_last): the layout the sm_100 tensor-core
+        convolutions produce natively and the one in which a bilinear tap is C contiguous floats,
+        so the warp / lookup kernels take their vectorised path.  Values are unchanged."""
+        self.to(memory_format=torch.channels_last if enable else torch.contiguous_format)
+        self.channels_last = enable
+        return self
+
     # ------------------------------------------------------------------ raft.py:155-173
     def _forward_prior_only(self, feature, dense_motion, img_full):
         grid, occ = dense_motion["deformation"], dense_motion["occlusion"]
@@ -109,6 +119,9 @@ class RaftFlow(nn.Module):
         return q_d, k_s
 
     def forward(self, kp_s, kp_d, dense_motion, img, img_full):
+        cl = self.channels_last
+        if cl:
+            img_full = img_full.contiguous(memory_format=torch.channels_last)
         feature = self.generator.encode(img_full)
         if img is None:
             raise RuntimeError("RaftFlow.forward needs `img` (the reference's self.down is commented out, raft.py:102)")
@@ -138,12 +151,12 @@ class RaftFlow(nn.Module):
             if i < base:
                 k = 2 ** (base - i)
                 coords = (flow + sampling.coords_grid(B, R, R, dev)) * k
-                corr = pyramid.block(base - i)(coords)
+                corr = pyramid.block(base - i)(coords, cl)
             elif i == base:
-                corr = pyramid.block(0)(flow + ident_basic)
+                corr = pyramid.block(0)(flow + ident_basic, cl)
             else:
                 flow_sample = _resize(flow, (self.h, self.h)) * 0.5 ** (i - base)
-                corr = _resize(pyramid.block(0)(flow_sample + ident_basic), (R, R))
+                corr = _resize(pyramid.block(0)(flow_sample + ident_basic, cl), (R, R))
             m_f = self.corr_enc(flow, corr)
 
             # ---- warps of feature[i]: refined (at flow) and coarse (prior grid) in one pass ----

@@ -1,0 +1,160 @@
+"""Isolated timing of every hot-path kernel at the bench shapes (B pairs, 256x256 / 512x512).
+
+CUDA events on the launching stream, 3 warm-ups, an L2 flush (256 MB write) between timed
+iterations, median of N.  Prints one JSON line per kernel: algorithmic GB/s (or TFLOP/s) and the
+fraction of the measured / fallback peak.   python scripts/bench_kernels.py [--batch 64] [--size 256]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mrfa_b200                                   # noqa: E402
+from mrfa_b200 import _lib, ops                    # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--size", type=int, default=256)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--only", default="")
+ap.add_argument("--C", type=int, default=256)
+ap.add_argument("--stock", action="store_true", help="also time the stock PyTorch op on the same shapes")
+a = ap.parse_args()
+
+dev = torch.device("cuda:0")
+peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pp):
+    d = json.load(open(pp))
+    peaks = {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "bf16_tflops": float(d.get("bf16_tflops", 1590.0)), "source": "measured"}
+flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+
+def timeit(fn, iters=a.iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def report(name, ms, nbytes=0, flops=0, **extra):
+    r = {"kernel": name, "ms": round(ms, 4)}
+    if nbytes:
+        r["GBps"] = round(nbytes / ms / 1e6, 1)
+        r["hbm_frac"] = round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 3)
+    if flops:
+        r["TFLOPs"] = round(flops / ms / 1e9, 1)
+        r["tensor_frac"] = round(flops / ms / 1e9 / peaks["bf16_tflops"], 3)
+    r.update(extra)
+    print(json.dumps(r), flush=True)
+
+
+B, S = a.batch, a.size
+h = w = S // 4
+N, C = h * w, a.C
+want = lambda n: (not a.only) or any(t in n or n in t for t in a.only.split(","))
+
+with torch.no_grad():
+    if want("membw"):
+        big = torch.empty(1 << 30, device=dev, dtype=torch.float32)          # 4 GiB
+        ms = timeit(lambda: big.zero_(), 5)
+        report("memset_4GiB(write only)", ms, big.numel() * 4)
+        half = big[: 1 << 29]
+        ms = timeit(lambda: big[1 << 29:].copy_(half), 5)
+        report("copy_2GiB(read+write)", ms, big.numel() * 4)
+        ms = timeit(lambda: half.sum(), 5)
+        report("sum_2GiB(read only)", ms, half.numel() * 4)
+        del big, half
+    if want("corr"):
+        q = torch.randn(B, C, h, w, device=dev)
+        k = torch.randn(B, C, h, w, device=dev)
+        rows = ops.corr_rows_total(h, w)
+        a_op = torch.empty((B, rows, C), device=dev, dtype=torch.bfloat16)
+        b_op = torch.empty((B, N, C), device=dev, dtype=torch.bfloat16)
+        v0 = torch.empty((B, rows, N), device=dev, dtype=torch.bfloat16)
+        v1 = torch.empty((B, rows, N // 4), device=dev, dtype=torch.bfloat16)
+        st = lambda: ops._stream()
+        pack = lambda: ops.check(ops.lib.mrfa_corr_pack(ops._p(q), ops._p(k), ops._p(a_op), ops._p(b_op), B, C, h, w, 0, st()))
+        qcl, kcl = q.contiguous(memory_format=torch.channels_last), k.contiguous(memory_format=torch.channels_last)
+        pack_cl = lambda: ops.check(ops.lib.mrfa_corr_pack(ops._p(qcl), ops._p(kcl), ops._p(a_op), ops._p(b_op), B, C, h, w, 1, st()))
+        ms = timeit(pack_cl)
+        report("corr_pack[nhwc]", ms, 8 * q.numel() + 2 * (a_op.numel() + b_op.numel()))
+        gemm = lambda: ops.check(ops.lib.mrfa_corr_volume(ops._p(a_op), ops._p(b_op), ops._p(v0), ops._p(v1), B, C, h, w,
+                                                          C ** -0.5, ops.sm_count(dev), st()))
+        pack()
+        ms = timeit(pack)
+        report("corr_pack", ms, 8 * q.numel() + 2 * (a_op.numel() + b_op.numel()))
+        ms = timeit(gemm)
+        report("corr_volume", ms, 2 * (a_op.numel() + b_op.numel() + v0.numel() + v1.numel()), 2 * B * N * N * C,
+               epilogue=os.environ.get("MRFA_CORR_EPILOGUE", "tma"), debug=os.environ.get("MRFA_CORR_DEBUG", "0"),
+               us_per_pair=round(1e3 * ms / B, 2))
+        if a.only == "corr_volume":
+            sys.exit(0)
+        if a.stock:
+            qf, kf = q.flatten(2).transpose(1, 2), k.flatten(2).transpose(1, 2)
+            nb = min(B, 16)
+            ms = timeit(lambda: torch.einsum("bic,bjc->bij", qf[:nb], kf[:nb]) * C ** -0.5)
+            report("stock_einsum_fp32(+scale)", ms * B / nb, 0, 2 * B * N * N * C, note=f"timed on {nb} pairs, scaled")
+        # lookups at the six levels
+        for i, R in enumerate([S // 32 * 2 ** j for j in range(6)]):
+            Rq = min(R, h)
+            lvl = max(3 - i, 0)
+            coords = (torch.rand(B, 2, Rq, Rq, device=dev) * (h + 4) - 2)
+            off = ops.corr_row_offset(h, w, lvl)
+            for cl in (False, True):
+                fn = lambda: torch.ops.mrfa.corr_lookup(v0, v1, coords, h, w, rows, off, 3, cl)
+                ms = timeit(fn)
+                report(f"corr_lookup_fwd[Q={Rq}x{Rq} {'nhwc' if cl else 'nchw'}]", ms, B * Rq * Rq * (2 * 64 * 2 + 8 + 98 * 4))
+        del v0, v1, a_op, b_op
+
+    if want("warp"):
+        chans = (512, 512, 512, 256, 128, 64)
+        for i, R in enumerate([S // 32 * 2 ** j for j in range(6)]):
+            Cc = chans[i]
+            feat = torch.randn(B, Cc, R, R, device=dev)
+            flow = torch.randn(B, 2, R, R, device=dev) * 2.0
+            prior = (mrfa_b200.make_coordinate_grid((R, R), "torch.cuda.FloatTensor")[None] +
+                     torch.randn(B, R, R, 2, device=dev) * 0.05).contiguous()
+            elems = B * Cc * R * R
+            for fmt in ("nchw", "nhwc"):
+                f_ = feat if fmt == "nchw" else feat.contiguous(memory_format=torch.channels_last)
+                try:
+                    ms = timeit(lambda: mrfa_b200.warp_by_flow(f_, flow))
+                    report(f"grid_sample_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R))
+                    ms = timeit(lambda: torch.ops.mrfa.dual_warp(f_, flow, prior))
+                    report(f"dual_warp_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (3 * elems + 4 * B * R * R))
+                except Exception as e:  # layout not supported yet
+                    print(json.dumps({"kernel": f"warp[{fmt} C={Cc} R={R}]", "error": str(e)[:120]}))
+            if a.stock:
+                ident = mrfa_b200.coords_grid(B, R, R, dev)
+                g = (flow + ident).permute(0, 2, 3, 1)
+                gn = torch.stack([2 * g[..., 0] / (R - 1) - 1, 2 * g[..., 1] / (R - 1) - 1], -1)
+                ms = timeit(lambda: F.grid_sample(feat, gn, align_corners=True))
+                report(f"stock_grid_sample[C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R))
+            del feat
+
+    if want("prior"):
+        src = torch.rand(B, 3, h, w, device=dev)
+        kp_s = torch.rand(B, 10, 2, device=dev) * 1.6 - 0.8
+        kp_d = kp_s + torch.randn(B, 10, 2, device=dev) * 0.1
+        jac = torch.eye(2, device=dev).view(1, 1, 2, 2) + 0.1 * torch.randn(B, 10, 2, 2, device=dev)
+        ms = timeit(lambda: torch.ops.mrfa.dense_motion_prior(kp_d, kp_s, jac, jac, None, src, 0.01))
+        report("dense_motion_prior", ms, 4 * B * h * w * (11 * 2 + 11 * 4 + 3))
+        pos = torch.randn(1, 10, h, w, device=dev)
+        ms = timeit(lambda: torch.ops.mrfa.kp2gaussian(kp_s, pos, h, w, 0.1))
+        report("kp2gaussian(+pos)", ms, 4 * B * 10 * h * w)

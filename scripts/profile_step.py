@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--nchw", action="store_true")
 a = ap.parse_args()
 
 cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "vox1.yaml")))
@@ -26,6 +27,9 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).to(dev).eval()
 rf = mrfa_b200.RaftFlow(**dict(cfg["raft_flow"], size=a.size)).to(dev).eval()
+if not a.nchw:
+    dm.channels_last_()
+    rf.channels_last_()
 src, _ = syn.frame_pairs(a.batch, a.size)
 kp_s, kp_d = syn.keypoints(a.batch, 10)
 src = src.to(dev)

@@ -408,3 +408,70 @@ def test_dense_motion_networks_forward(golden):
         out = tnet(src.to(DEV), {"kp": cu(d["tps_kp_d"])}, {"kp": cu(d["tps_kp_s"])}, bg_param=bg.to(DEV))
         for k in ("deformed_source", "contribution_maps", "deformation", "occlusion"):
             close(out[k], d["tps_fwd_" + k], 5e-3)
+
+
+# ------------------------------------------------------------------ channels-last (NHWC) paths
+@pytest.mark.parametrize("C,R", [(512, 8), (256, 64), (64, 128), (4, 19)])
+def test_feature_warp_channels_last(C, R):
+    m = mb()
+    torch.manual_seed(C + R)
+    B = 2
+    feat = torch.randn(B, C, R, R)
+    flow = torch.randn(B, 2, R, R) * 2.5
+    ident = TP.coords_grid(B, R, R)
+    ref = TP.bilinear_sampler(feat, (flow + ident).permute(0, 2, 3, 1))
+    fcl = feat.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = m.warp_by_flow(fcl, flow.to(DEV))
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    close(out, ref)
+    grid = TP.make_coordinate_grid((R, R))[None].repeat(B, 1, 1, 1) + torch.randn(B, R, R, 2) * 0.1
+    close(m.grid_sample(fcl, grid.to(DEV)), F.grid_sample(feat, grid, align_corners=False))
+    close(m.grid_sample(fcl, grid.to(DEV), align_corners=True), F.grid_sample(feat, grid, align_corners=True))
+    close(m.grid_sample(fcl, grid.to(DEV) * 1.6, padding_mode="reflection"),
+          F.grid_sample(feat, grid * 1.6, padding_mode="reflection", align_corners=False))
+    a, b = torch.ops.mrfa.dual_warp(fcl, flow.to(DEV), grid.to(DEV))
+    assert a.is_contiguous(memory_format=torch.channels_last)
+    close(a, ref)
+    close(b, F.grid_sample(feat, grid, align_corners=False))
+
+
+@pytest.mark.parametrize("mode", ["pixel", "acF"])
+def test_warp_backward_channels_last(mode):
+    m = mb()
+    torch.manual_seed(7)
+    B, C, H, W, Ho, Wo = 2, 8, 9, 11, 7, 5
+    feat = torch.randn(B, C, H, W, dtype=torch.float64)
+    if mode == "pixel":
+        grid = torch.rand(B, Ho, Wo, 2, dtype=torch.float64) * torch.tensor([W + 2.0, H + 2.0], dtype=torch.float64) - 1.5
+    else:
+        grid = torch.rand(B, Ho, Wo, 2, dtype=torch.float64) * 2.6 - 1.3
+    go = torch.randn(B, C, Ho, Wo, dtype=torch.float64)
+    f64, g64 = feat.clone().requires_grad_(), grid.clone().requires_grad_()
+    if mode == "pixel":
+        gn = torch.stack([2 * g64[..., 0] / (W - 1) - 1, 2 * g64[..., 1] / (H - 1) - 1], -1)
+        F.grid_sample(f64, gn, align_corners=True).backward(go)
+    else:
+        F.grid_sample(f64, g64, align_corners=False).backward(go)
+    f32 = feat.float().to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_()
+    g32 = grid.float().to(DEV).requires_grad_()
+    out = m.bilinear_sampler(f32, g32) if mode == "pixel" else m.grid_sample(f32, g32)
+    out.backward(go.float().to(DEV))
+    close(f32.grad, f64.grad, 2e-5)
+    close(g32.grad, g64.grad, 5e-4, 1e-4)
+
+
+def test_corr_channels_last_inputs_and_lookup_output(golden):
+    m, c = mb(), golden("corr")
+    q, k = cu(c["q_d"]), cu(c["k_s"])
+    B, C, h, w = q.shape
+    ref = m.CorrPyramid(q, k, C ** -0.5)
+    pyr = m.CorrPyramid(q.contiguous(memory_format=torch.channels_last), k.contiguous(memory_format=torch.channels_last), C ** -0.5)
+    # level-0 rows are the same cast; pooled rows may differ by summation order (one bf16 ulp)
+    assert torch.equal(pyr.volume0[:, :h * w], ref.volume0[:, :h * w])
+    rel_close(pyr.volume0, ref.volume0.float(), 2 ** -6)
+    for lvl, kk in ((0, 1), (1, 2)):
+        coords = cu(c[f"coords_k{kk}"])
+        a = ref.block(lvl)(coords)
+        b = ref.block(lvl)(coords, True)
+        assert b.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(a, b.contiguous())

@@ -89,3 +89,22 @@ def test_full_chain_vs_oracle_128(golden):
         _rel(out, ref_out, 2e-2)
         _rel(warp_img, ref_warp, 2e-2)
         _rel(occ, ref_occ, 2e-2)
+
+
+def test_channels_last_matches_nchw(golden):
+    """NHWC execution of the drop-in modules gives the NCHW results (layout is not numerics)."""
+    import mrfa_b200
+    src, kp_s, kp_d, dense, small = _inputs(golden)
+    with torch.no_grad():
+        net = syn.fill_state_dict_(mrfa_b200.RaftFlow(**_rf_cfg())).to(DEV).eval()
+        dd = {k: v.to(DEV) for k, v in dense.items()}
+        args = (kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), dd)
+        out0, warp0, occ0 = net(*args, img=small.to(DEV), img_full=src.to(DEV))
+        net.channels_last_()
+        out1, warp1, occ1 = net(*args, img=small.to(DEV), img_full=src.to(DEV))
+        # cuDNN may pick different (still fp32) algorithms per layout: allow conv round-off only
+        np.testing.assert_allclose(out1.cpu().numpy(), out0.cpu().numpy(), atol=2e-4)
+        np.testing.assert_allclose(warp1.cpu().numpy(), warp0.cpu().numpy(), atol=2e-4)
+        np.testing.assert_allclose(occ1.cpu().numpy(), occ0.cpu().numpy(), atol=2e-4)
+        r = golden("raft_flow")
+        _rel(out1, r["out"], 2e-2)
