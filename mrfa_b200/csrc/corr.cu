@@ -88,38 +88,46 @@ corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, _
 
 // channels-last inputs: (B,h,w,C) in memory is already "(h w) c" row-major, so the pack is a
 // vectorised cast (float4 -> 4 x bf16) plus the pooled driving rows; one thread per (row, 4 ch).
+// grid (row chunks, B): blockIdx.y = pair; thread = (row, channel quad) with 32-bit indexing only
 __global__ void __launch_bounds__(256)
 corr_pack_nhwc_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, __nv_bfloat16* __restrict__ a_op,
-                      __nv_bfloat16* __restrict__ b_op, int B, int C, int h, int w, int64_t rows_total) {
+                      __nv_bfloat16* __restrict__ b_op, int C, int h, int w, int rows_total) {
   const int hw = h * w, cq = C / 4;
-  const int64_t per_b = (rows_total + hw) * cq;
-  const int64_t total = (int64_t)B * per_b;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / per_b);
-    const int64_t r_ = (i - (int64_t)b * per_b) / cq;
-    const int c = (int)(i % cq) * 4;
+  const int b = blockIdx.y;
+  const int rows_all = rows_total + hw;
+  const uint32_t total = (uint32_t)rows_all * (uint32_t)cq;
+  const float* qb = q_d + (int64_t)b * hw * C;
+  const float* kb = k_s + (int64_t)b * hw * C;
+  __nv_bfloat16* ab = a_op + (int64_t)b * rows_total * C;
+  __nv_bfloat16* bb = b_op + (int64_t)b * hw * C;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r_ = (int)(i / (uint32_t)cq);
+    const int c = (int)(i - (uint32_t)r_ * (uint32_t)cq) * 4;
     float4 acc;
     __nv_bfloat16* dst;
-    if (r_ >= rows_total) {                                   // source operand: plain cast
-      const int64_t r = r_ - rows_total;
-      acc = __ldg(reinterpret_cast<const float4*>(k_s + ((int64_t)b * hw + r) * C + c));
-      dst = b_op + ((int64_t)b * hw + r) * C + c;
-    } else {
-      int lvl = 0;
-      int64_t off = 0, r = r_;
-      while (r >= (hw >> (2 * lvl))) { r -= hw >> (2 * lvl); off += hw >> (2 * lvl); ++lvl; }
+    if (r_ < hw) {                                              // driving level 0: plain cast
+      acc = __ldg(reinterpret_cast<const float4*>(qb + (int64_t)r_ * C + c));
+      dst = ab + (int64_t)r_ * C + c;
+    } else if (r_ >= rows_total) {                              // source operand: plain cast
+      const int r = r_ - rows_total;
+      acc = __ldg(reinterpret_cast<const float4*>(kb + (int64_t)r * C + c));
+      dst = bb + (int64_t)r * C + c;
+    } else {                                                    // pooled driving rows
+      int lvl = 1, r = r_ - hw;
+      while (r >= (hw >> (2 * lvl))) { r -= hw >> (2 * lvl); ++lvl; }
       const int k = 1 << lvl, wl = w >> lvl;
-      const int py = (int)(r / wl), px = (int)(r - (int64_t)py * wl);
-      const float* src = q_d + (int64_t)b * hw * C + c;
+      const int py = r / wl, px = r - py * wl;
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int dy = 0; dy < k; ++dy)
+      for (int dy = 0; dy < k; ++dy) {
+        const float* row = qb + ((int64_t)(py * k + dy) * w + px * k) * C + c;
         for (int dx = 0; dx < k; ++dx) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)(py * k + dy) * w + px * k + dx) * C));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + (int64_t)dx * C));
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+      }
       const float inv = 1.f / (float)(k * k);
-      if (lvl) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
-      dst = a_op + ((int64_t)b * rows_total + r_) * C + c;
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      dst = ab + (int64_t)r_ * C + c;
     }
     const uint2 packed = make_uint2(
         (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.y)) << 16),
@@ -974,12 +982,13 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
   if (B == 0) return 0;
   if (channels_last) {
     if (((reinterpret_cast<uintptr_t>(q_d) | reinterpret_cast<uintptr_t>(k_s)) & 15) != 0) return MRFA_E_ALIGN;
-    const int64_t total = (int64_t)B * (mrfa_corr_rows_total(h, w) + (int64_t)h * w) * (C / 4);
+    const int64_t rows_total = mrfa_corr_rows_total(h, w);
+    const int64_t total = (rows_total + (int64_t)h * w) * (C / 4);
+    MRFA_CHECK_SHAPE(total < (1ll << 31));
     int64_t blocks = cdiv64(total, 256);
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    corr_pack_nhwc_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-        q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), B, C, h, w,
-        mrfa_corr_rows_total(h, w));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    corr_pack_nhwc_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, as_stream(stream)>>>(
+        q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), C, h, w, (int)rows_total);
     return MRFA_LAUNCH_RESULT();
   }
   const int tile_w = w < 32 ? w : 32;

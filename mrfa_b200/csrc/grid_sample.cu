@@ -205,65 +205,121 @@ __device__ __forceinline__ float4 blend4(float4 a, float4 b, float4 c, float4 d,
   return r;
 }
 
-template <int MODE, int PAD, bool ADD_ID>
+// Forward NHWC kernels are warp-cooperative: lane l evaluates the coordinates / taps of pixel
+// (warp base + l) ONCE, then the warp walks its 32 pixels, broadcasting each pixel's taps with
+// shuffles while all lanes stream that pixel's channels as float4 (LPP lanes per pixel, 32/LPP
+// pixels per step).  The IEEE coordinate arithmetic is thereby amortised over the channel axis
+// instead of being repeated by every lane of a pixel.
+struct TapsB {              // taps + input-plane base of one pixel, as shuffled between lanes
+  int o_nw, o_ne, o_sw, o_se, n_in;
+  float w_nw, w_ne, w_sw, w_se;
+};
+__device__ __forceinline__ TapsB shfl_taps(const TapsB& t, int src) {
+  TapsB r;
+  r.o_nw = __shfl_sync(0xffffffffu, t.o_nw, src); r.o_ne = __shfl_sync(0xffffffffu, t.o_ne, src);
+  r.o_sw = __shfl_sync(0xffffffffu, t.o_sw, src); r.o_se = __shfl_sync(0xffffffffu, t.o_se, src);
+  r.n_in = __shfl_sync(0xffffffffu, t.n_in, src);
+  r.w_nw = __shfl_sync(0xffffffffu, t.w_nw, src); r.w_ne = __shfl_sync(0xffffffffu, t.w_ne, src);
+  r.w_sw = __shfl_sync(0xffffffffu, t.w_sw, src); r.w_se = __shfl_sync(0xffffffffu, t.w_se, src);
+  return r;
+}
+__device__ __forceinline__ float4 blend4b(float4 a, float4 b, float4 c, float4 d, const TapsB& t) {
+  float4 r;
+  r.x = fmaf(d.x, t.w_se, fmaf(c.x, t.w_sw, fmaf(b.x, t.w_ne, a.x * t.w_nw)));
+  r.y = fmaf(d.y, t.w_se, fmaf(c.y, t.w_sw, fmaf(b.y, t.w_ne, a.y * t.w_nw)));
+  r.z = fmaf(d.z, t.w_se, fmaf(c.z, t.w_sw, fmaf(b.z, t.w_ne, a.z * t.w_nw)));
+  r.w = fmaf(d.w, t.w_se, fmaf(c.w, t.w_sw, fmaf(b.w, t.w_ne, a.w * t.w_nw)));
+  return r;
+}
+__device__ __forceinline__ TapsB to_tapsb(const Taps& t, int n_in) {
+  TapsB r;
+  r.o_nw = t.o_nw; r.o_ne = t.o_ne; r.o_sw = t.o_sw; r.o_se = t.o_se; r.n_in = n_in;
+  r.w_nw = t.w_nw; r.w_ne = t.w_ne; r.w_sw = t.w_sw; r.w_se = t.w_se;
+  return r;
+}
+
+// LPP = lanes per pixel (power of two, LPP * 4 <= C or LPP == 1)
+// PW = pixels per warp (32 for large problems; 4 keeps enough warps in flight for small ones)
+template <int MODE, int PAD, bool ADD_ID, int LPP, int PW>
 __global__ void __launch_bounds__(kThreads)
 grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
                             float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div) {
+  constexpr int PPS = (32 / LPP) < PW ? (32 / LPP) : PW;   // pixels per step
+  constexpr int LPPE = 32 / PPS;                            // lanes actually assigned to one pixel
   const int HoWo = Ho * Wo;
-  const int64_t gp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kNhwcGroup;
-  const int j = threadIdx.x % kNhwcGroup;
-  if (gp >= (int64_t)N * HoWo) return;
-  const int n = (int)(gp / HoWo);
-  const int p = (int)(gp - (int64_t)n * HoWo);
-  const int y = p / Wo, x = p - y * Wo;
-  float ix, iy, mx, my;
-  load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
-  const Taps t = make_taps(ix, iy, H, W);
-  const float* src = in + (int64_t)(n / in_batch_div) * H * W * C;
-  float* dst = out + gp * C;
-  const float* p_nw = src + (int64_t)t.o_nw * C;
-  const float* p_ne = src + (int64_t)t.o_ne * C;
-  const float* p_sw = src + (int64_t)t.o_sw * C;
-  const float* p_se = src + (int64_t)t.o_se * C;
-  for (int c = j * 4; c < C; c += kNhwcGroup * 4 * 2) {
-    // two channel quads per iteration: 8 independent 16-byte loads in flight
-    const int c2 = c + kNhwcGroup * 4;
-    const float4 a0 = ldg4(p_nw + c), b0 = ldg4(p_ne + c), d0 = ldg4(p_sw + c), e0 = ldg4(p_se + c);
-    if (c2 < C) {
-      const float4 a1 = ldg4(p_nw + c2), b1 = ldg4(p_ne + c2), d1 = ldg4(p_sw + c2), e1 = ldg4(p_se + c2);
-      stcs4(dst + c, blend4(a0, b0, d0, e0, t));
-      stcs4(dst + c2, blend4(a1, b1, d1, e1, t));
-    } else {
-      stcs4(dst + c, blend4(a0, b0, d0, e0, t));
+  const int lane = threadIdx.x % 32;
+  const int64_t total = (int64_t)N * HoWo;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * PW;
+  if (gp0 >= total) return;
+  TapsB mine;
+  {
+    const int64_t gp = min(gp0 + (lane % PW), total - 1);
+    const int n = (int)(gp / HoWo);
+    const int p = (int)(gp - (int64_t)n * HoWo);
+    const int y = p / Wo, x = p - y * Wo;
+    float ix, iy, mx, my;
+    load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
+    mine = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div);
+  }
+  const int sub = lane / LPPE, cl = (lane % LPPE) * 4;
+  const int64_t plane = (int64_t)H * W * C;
+#pragma unroll 4
+  for (int s = 0; s < PW; s += PPS) {
+    const TapsB t = shfl_taps(mine, s + sub);
+    const int64_t gp = gp0 + s + sub;
+    if (gp >= total) continue;
+    const float* src = in + (int64_t)t.n_in * plane;
+    float* dst = out + gp * C;
+    for (int c = cl; c < C; c += LPPE * 4) {
+      const float4 a = ldg4(src + (int64_t)t.o_nw * C + c), b = ldg4(src + (int64_t)t.o_ne * C + c);
+      const float4 d = ldg4(src + (int64_t)t.o_sw * C + c), e = ldg4(src + (int64_t)t.o_se * C + c);
+      stcs4(dst + c, blend4b(a, b, d, e, t));
     }
   }
 }
 
+template <int LPP, int PW>
 __global__ void __launch_bounds__(kThreads)
 dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
                           float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W) {
+  constexpr int PPS = (32 / LPP) < PW ? (32 / LPP) : PW;
+  constexpr int LPPE = 32 / PPS;
   const int HW = H * W;
-  const int64_t gp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kNhwcGroup;
-  const int j = threadIdx.x % kNhwcGroup;
-  if (gp >= (int64_t)N * HW) return;
-  const int n = (int)(gp / HW);
-  const int p = (int)(gp - (int64_t)n * HW);
-  const int y = p / W, x = p - y * W;
-  const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
-  const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
-  const Taps tr = make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W);
-  const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
-  const Taps tc = make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W);
-  const float* src = in + (int64_t)n * HW * C;
-  float* dr = out_r + gp * C;
-  float* dc = out_c + gp * C;
-  for (int c = j * 4; c < C; c += kNhwcGroup * 4) {
-    const float4 a0 = ldg4(src + (int64_t)tr.o_nw * C + c), a1 = ldg4(src + (int64_t)tr.o_ne * C + c);
-    const float4 a2 = ldg4(src + (int64_t)tr.o_sw * C + c), a3 = ldg4(src + (int64_t)tr.o_se * C + c);
-    const float4 b0 = ldg4(src + (int64_t)tc.o_nw * C + c), b1 = ldg4(src + (int64_t)tc.o_ne * C + c);
-    const float4 b2 = ldg4(src + (int64_t)tc.o_sw * C + c), b3 = ldg4(src + (int64_t)tc.o_se * C + c);
-    stcs4(dr + c, blend4(a0, a1, a2, a3, tr));
-    stcs4(dc + c, blend4(b0, b1, b2, b3, tc));
+  const int lane = threadIdx.x % 32;
+  const int64_t total = (int64_t)N * HW;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * PW;
+  if (gp0 >= total) return;
+  TapsB mr, mc;
+  {
+    const int64_t gp = min(gp0 + (lane % PW), total - 1);
+    const int n = (int)(gp / HW);
+    const int p = (int)(gp - (int64_t)n * HW);
+    const int y = p / W, x = p - y * W;
+    const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
+    const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
+    mr = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n);
+    const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
+    mc = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n);
+  }
+  const int sub = lane / LPPE, cl = (lane % LPPE) * 4;
+  const int64_t plane = (int64_t)HW * C;
+#pragma unroll 2
+  for (int s = 0; s < PW; s += PPS) {
+    const TapsB tr = shfl_taps(mr, s + sub);
+    const TapsB tc = shfl_taps(mc, s + sub);
+    const int64_t gp = gp0 + s + sub;
+    if (gp >= total) continue;
+    const float* src = in + (int64_t)tr.n_in * plane;
+    float* dr = out_r + gp * C;
+    float* dc = out_c + gp * C;
+    for (int c = cl; c < C; c += LPPE * 4) {
+      const float4 a0 = ldg4(src + (int64_t)tr.o_nw * C + c), a1 = ldg4(src + (int64_t)tr.o_ne * C + c);
+      const float4 a2 = ldg4(src + (int64_t)tr.o_sw * C + c), a3 = ldg4(src + (int64_t)tr.o_se * C + c);
+      const float4 b0 = ldg4(src + (int64_t)tc.o_nw * C + c), b1 = ldg4(src + (int64_t)tc.o_ne * C + c);
+      const float4 b2 = ldg4(src + (int64_t)tc.o_sw * C + c), b3 = ldg4(src + (int64_t)tc.o_se * C + c);
+      stcs4(dr + c, blend4b(a0, a1, a2, a3, tr));
+      stcs4(dc + c, blend4b(b0, b1, b2, b3, tc));
+    }
   }
 }
 
@@ -328,13 +384,37 @@ grid_sample_bwd_nhwc_kernel(const float* __restrict__ grad_out, const float* __r
   if (live && j == 0) reinterpret_cast<float2*>(grad_grid)[gp] = make_float2(gix * mx, giy * my);
 }
 
+static inline int lanes_per_pixel(int C) {
+  int lpp = 1;
+  while (lpp < 32 && lpp * 2 * 4 <= C) lpp *= 2;
+  return lpp;
+}
+
+constexpr int64_t kSmallPixels = 100000;     // below this, 4 pixels per warp keep the SMs busy
+
+template <int MODE, int PAD, bool ADD_ID>
+static int launch_fwd_nhwc_lpp(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C,
+                               int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
+  const int64_t pixels = (int64_t)N * Ho * Wo;
+  const bool small = pixels < kSmallPixels;
+  dim3 g((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
+#define MRFA_GS_CASE(L)                                                                                            \
+  case L:                                                                                                          \
+    if (small) grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 4><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); \
+    else grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 32><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);    \
+    break;
+  switch (lanes_per_pixel(C)) {
+    MRFA_GS_CASE(1) MRFA_GS_CASE(2) MRFA_GS_CASE(4) MRFA_GS_CASE(8) MRFA_GS_CASE(16) MRFA_GS_CASE(32)
+  }
+#undef MRFA_GS_CASE
+  return MRFA_LAUNCH_RESULT();
+}
+
 template <int MODE, int PAD>
 static int launch_fwd_nhwc(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C, int H,
                            int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
-  dim3 g((unsigned)cdiv64((int64_t)N * Ho * Wo * kNhwcGroup, kThreads));
-  if (add_id) grid_sample_fwd_nhwc_kernel<MODE, PAD, true><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);
-  else grid_sample_fwd_nhwc_kernel<MODE, PAD, false><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);
-  return MRFA_LAUNCH_RESULT();
+  if (add_id) return launch_fwd_nhwc_lpp<MODE, PAD, true>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
+  return launch_fwd_nhwc_lpp<MODE, PAD, false>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
 }
 
 template <int MODE, int PAD>
@@ -432,8 +512,19 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
     MRFA_CHECK_SHAPE(C % 4 == 0);
     if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_refined) | reinterpret_cast<uintptr_t>(out_coarse)) & 15) != 0)
       return MRFA_E_ALIGN;
-    dim3 gn((unsigned)cdiv64((int64_t)N * H * W * kNhwcGroup, kThreads));
-    dual_warp_fwd_nhwc_kernel<<<gn, kThreads, 0, as_stream(stream)>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W);
+    const int64_t pixels = (int64_t)N * H * W;
+    const bool small = pixels < kSmallPixels;
+    dim3 gn((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
+    cudaStream_t st = as_stream(stream);
+#define MRFA_DW_CASE(L)                                                                                              \
+  case L:                                                                                                            \
+    if (small) dual_warp_fwd_nhwc_kernel<L, 4><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W); \
+    else dual_warp_fwd_nhwc_kernel<L, 32><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W);   \
+    break;
+    switch (lanes_per_pixel(C)) {
+      MRFA_DW_CASE(1) MRFA_DW_CASE(2) MRFA_DW_CASE(4) MRFA_DW_CASE(8) MRFA_DW_CASE(16) MRFA_DW_CASE(32)
+    }
+#undef MRFA_DW_CASE
     return MRFA_LAUNCH_RESULT();
   }
   dim3 g((unsigned)cdiv64((int64_t)N * H * W, kWarpPix), (unsigned)cdiv64(C, kCPT * (kThreads / kWarpPix)));
