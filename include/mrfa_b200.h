@@ -194,6 +194,23 @@ int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* 
                          int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
                          int radius, mrfa_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused elementwise passes between the warps and the cuDNN convolutions
+ * ------------------------------------------------------------------------------------- */
+/* y = act(x * scale[c] + shift[c] + residual); scale / shift / residual may be NULL.
+ * Replaces eval-mode BatchNorm2d + ReLU (util.py:126-127, :150-151), conv bias adds and the
+ * residual add of ResBlock2d (util.py:156).  x, residual, y: (N,C,H,W) NCHW (channels_last=0)
+ * or NHWC (channels_last=1, C % 4 == 0, 16-byte aligned); pixels = N*H*W; HW = H*W.
+ * act: 0 identity, 1 ReLU, 2 sigmoid.  y may alias x.                                        */
+int mrfa_channel_affine(const float* x, const float* scale, const float* shift, const float* residual,
+                        float* y, int64_t pixels, int C, int HW, int channels_last, int act,
+                        mrfa_stream_t stream);
+
+/* Decoder occlusion blending generator.py:47,57: y = a * occ + b * (1 - occ) (b NULL: y = a * occ),
+ * occ (N,1,H,W) broadcast over channels.  Same layouts as above.  y may alias a or b.        */
+int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float* y,
+                         int64_t pixels, int C, int HW, int channels_last, mrfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,8 +13,60 @@ import torch.nn.functional as F
 from torch import nn
 
 
+import os
+
+# Inference fast path (CUDA, eval mode, grad disabled): BatchNorm folded into the preceding
+# convolution, bias + ReLU fused into the cuDNN convolution (aten::cudnn_convolution_relu) and
+# the remaining per-channel passes done by one vectorised kernel (mrfa::channel_affine).  The
+# parameters themselves are never modified, so state_dicts stay reference-compatible; folded
+# tensors are cached per module and refreshed when any source tensor changes.
+FAST_INFERENCE = os.environ.get("MRFA_FAST_CONV", "1") != "0"
+
+
 def _conv(cin, cout, k, pad, groups=1):
     return nn.Conv2d(cin, cout, kernel_size=k, padding=pad, groups=groups)
+
+
+def fast_path(module: nn.Module, x: torch.Tensor) -> bool:
+    return FAST_INFERENCE and x.is_cuda and x.dtype == torch.float32 and not module.training and not torch.is_grad_enabled()
+
+
+class _Cache:
+    __slots__ = ("key", "val")
+
+    def __init__(self):
+        self.key, self.val = None, None
+
+    def get(self, tensors, build):
+        key = tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+        if key != self.key:
+            with torch.no_grad():
+                self.val = build()
+            self.key = key
+        return self.val
+
+
+def _bn_affine(bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm as y = x * scale + shift."""
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return scale, bn.bias - bn.running_mean * scale
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """conv followed by eval-mode BatchNorm == one conv with these weights / bias."""
+    scale, shift = _bn_affine(bn)
+    w = conv.weight * scale.view(-1, 1, 1, 1)
+    if conv.weight.dim() == 4 and conv.weight.is_contiguous(memory_format=torch.channels_last):
+        w = w.contiguous(memory_format=torch.channels_last)
+    b = shift if conv.bias is None else conv.bias * scale + shift
+    return w, b.contiguous()
+
+
+def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """relu(conv(x)); bias and ReLU ride in the cuDNN convolution epilogue on the fast path."""
+    if fast_path(conv, x):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
 
 
 class _ConvNormAct(nn.Module):
@@ -28,11 +80,17 @@ class _ConvNormAct(nn.Module):
         super().__init__()
         self.conv = _conv(in_features, out_features, kernel_size, padding, groups)
         self.norm = nn.BatchNorm2d(out_features, affine=True)
+        self._folded = _Cache()
 
     def forward(self, x):
         if self.pre_upsample:
             x = F.interpolate(x, scale_factor=2)
-        x = F.relu(self.norm(self.conv(x)))
+        if fast_path(self, x):
+            c, n = self.conv, self.norm
+            w, b = self._folded.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), lambda: _fold(c, n))
+            x = torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, c.groups)
+        else:
+            x = F.relu(self.norm(self.conv(x)))
         if self.post_pool:
             x = F.avg_pool2d(x, (2, 2))
         return x
@@ -60,8 +118,17 @@ class ResBlock2d(nn.Module):
         self.conv2 = _conv(in_features, in_features, kernel_size, padding)
         self.norm1 = nn.BatchNorm2d(in_features, affine=True)
         self.norm2 = nn.BatchNorm2d(in_features, affine=True)
+        self._pre, self._folded = _Cache(), _Cache()
 
     def forward(self, x):
+        if fast_path(self, x):
+            n1, n2, c1, c2 = self.norm1, self.norm2, self.conv1, self.conv2
+            s1, h1 = self._pre.get((n1.weight, n1.bias, n1.running_mean, n1.running_var), lambda: _bn_affine(n1))
+            w, b = self._folded.get((c1.weight, c1.bias, n2.weight, n2.bias, n2.running_mean, n2.running_var), lambda: _fold(c1, n2))
+            t = torch.ops.mrfa.channel_affine(x, s1, h1, None, 1)                       # norm1 + relu
+            t = torch.cudnn_convolution_relu(t, w, b, c1.stride, c1.padding, c1.dilation, c1.groups)   # conv1 + norm2 + relu
+            t = F.conv2d(t, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+            return torch.ops.mrfa.channel_affine(t, None, c2.bias, x, 0)                # + bias + residual
         y = self.conv1(F.relu(self.norm1(x)))
         y = self.conv2(F.relu(self.norm2(y)))
         return y + x
@@ -74,8 +141,15 @@ class ChannelBlock2d(nn.Module):
         super().__init__()
         self.conv1 = _conv(in_features, in_features // 2, kernel_size, padding)
         self.norm1 = nn.BatchNorm2d(in_features, affine=True)
+        self._pre = _Cache()
 
     def forward(self, x):
+        if fast_path(self, x):
+            n1, c1 = self.norm1, self.conv1
+            s1, h1 = self._pre.get((n1.weight, n1.bias, n1.running_mean, n1.running_var), lambda: _bn_affine(n1))
+            t = torch.ops.mrfa.channel_affine(x, s1, h1, None, 1)
+            t = F.conv2d(t, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
+            return torch.ops.mrfa.channel_affine(t, None, c1.bias, None, 0)
         return self.conv1(F.relu(self.norm1(x)))
 
 
@@ -176,6 +250,8 @@ class OcclusionAwareGenerator(nn.Module):
         return feats[::-1]          # coarsest first: R = S/32 ... S
 
     def decode(self, warp_f, warp_img, occlusion, warp_f_c=None, occlusion_c=None):
+        if fast_path(self, warp_img):
+            return self._decode_fast(warp_f, warp_img, occlusion, warp_f_c)
         use_coarse = warp_f_c is not None
         y = warp_f[0] * occlusion[0]
         if use_coarse:
@@ -190,6 +266,23 @@ class OcclusionAwareGenerator(nn.Module):
                 y = torch.cat([y, warp_f_c[i + 1]], dim=1)
         y = torch.sigmoid(self.final(y))
         return y * (1 - occlusion[-1]) + warp_img * occlusion[-1]
+
+    def _decode_fast(self, warp_f, warp_img, occlusion, warp_f_c):
+        """Same dataflow as decode(); the occlusion blends are single fused passes."""
+        blend = torch.ops.mrfa.occlusion_blend
+        use_coarse = warp_f_c is not None
+        y = blend(warp_f[0], None, occlusion[0])
+        if use_coarse:
+            y = torch.cat([y, warp_f_c[0]], dim=1)
+        for i in range(self.num_up_blocks):
+            if use_coarse:
+                y = self.channel_block[i](y)
+            y = self.up_blocks[i](self.resblock[i](y))
+            y = blend(warp_f[i + 1], y, occlusion[i + 1])
+            if use_coarse and i != self.num_up_blocks - 1:
+                y = torch.cat([y, warp_f_c[i + 1]], dim=1)
+        y = torch.sigmoid(self.final(y))
+        return blend(warp_img, y, occlusion[-1])
 
     def forward(self, x):
         return self.decode(self.encode(x))

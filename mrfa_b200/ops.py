@@ -567,3 +567,56 @@ def _cl_backward(ctx, g):
 
 
 corr_lookup.register_autograd(_cl_backward, setup_context=_cl_setup)
+
+
+# ------------------------------------------------------------------------------------------
+# fused elementwise passes (inference fast path of the conv blocks and the decoder blending)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("mrfa::channel_affine", mutates_args=(), device_types="cuda")
+def channel_affine(x: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], residual: Optional[Tensor],
+                   act: int) -> Tensor:
+    """act(x * scale[c] + shift[c] + residual); act 0 none / 1 relu / 2 sigmoid."""
+    x, cl = _req_image(x, "x")
+    if residual is not None:
+        residual = _like_layout(_req_image(residual, "residual")[0], cl)
+    scale = None if scale is None else _req(scale, "scale")
+    shift = None if shift is None else _req(shift, "shift")
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        with _timed("channel_affine", 4 * x.numel() * (2 + (residual is not None))):
+            check(lib.mrfa_channel_affine(_p(x), _p(scale), _p(shift), _p(residual), _p(y), N * H * W, C, H * W, int(cl),
+                                          act, _stream()), "mrfa_channel_affine")
+    return y
+
+
+@channel_affine.register_fake
+def _(x, scale, shift, residual, act):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("mrfa::occlusion_blend", mutates_args=(), device_types="cuda")
+def occlusion_blend(a: Tensor, b: Optional[Tensor], occ: Tensor) -> Tensor:
+    """a * occ + b * (1 - occ) (b None: a * occ); occ (N,1,H,W) broadcast over channels."""
+    a, cl = _req_image(a, "a")
+    if b is not None:
+        b = _like_layout(_req_image(b, "b")[0], cl)
+    occ = _req(occ, "occ")
+    N, C, H, W = a.shape
+    if tuple(occ.shape) != (N, 1, H, W):
+        raise RuntimeError("mrfa_b200: occlusion_blend expects occ of shape (N,1,H,W)")
+    y = torch.empty_like(a)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(a.device):
+        with _timed("occlusion_blend", 4 * (a.numel() * (2 + (b is not None)) + occ.numel())):
+            check(lib.mrfa_occlusion_blend(_p(a), _p(b), _p(occ), _p(y), N * H * W, C, H * W, int(cl), _stream()),
+                  "mrfa_occlusion_blend")
+    return y
+
+
+@occlusion_blend.register_fake
+def _(a, b, occ):
+    return torch.empty_like(a)

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import sampling
-from .blocks import Hourglass, OcclusionAwareGenerator
+from .blocks import Hourglass, OcclusionAwareGenerator, conv_relu
 from .corr import CorrPyramid
 
 
@@ -33,9 +33,9 @@ class BasicMotionEncoder(nn.Module):
         self.conv = nn.Conv2d(64 + 96, 128 - 2, 3, padding=1)
 
     def forward(self, delta_flow, corr):
-        c = F.relu(self.convc2(F.relu(self.convc1(corr))))
-        f = F.relu(self.convf2(F.relu(self.convf1(delta_flow))))
-        y = F.relu(self.conv(torch.cat([c, f], dim=1)))
+        c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
+        f = conv_relu(self.convf2, conv_relu(self.convf1, delta_flow))
+        y = conv_relu(self.conv, torch.cat([c, f], dim=1))
         return torch.cat([y, delta_flow], dim=1)
 
 
@@ -51,9 +51,9 @@ class RefineFlow(nn.Module):
         self.convo2 = nn.Conv2d(128, 1, 3, padding=1)
 
     def forward(self, m_f, warp_f):
-        inp = torch.cat([m_f, F.relu(self.convc1(warp_f))], dim=1)
-        flow = self.conv2(F.relu(self.conv1(inp)))
-        occ = self.convo2(F.relu(self.convo1(inp)))
+        inp = torch.cat([m_f, conv_relu(self.convc1, warp_f)], dim=1)
+        flow = self.conv2(conv_relu(self.conv1, inp))
+        occ = self.convo2(conv_relu(self.convo1, inp))
         return torch.cat([flow, occ], dim=1), inp
 
 
@@ -166,7 +166,7 @@ class RaftFlow(nn.Module):
             else:
                 prior_grid, occ_res = prior, prior_occ
             warp_f, warp_c = torch.ops.mrfa.dual_warp(feature[i], flow, prior_grid)       # raft.py:247, :271
-            warp_f = F.relu(self.to_context[i](warp_f))
+            warp_f = conv_relu(self.to_context[i], warp_f)
 
             d_flow, _ = self.refine(m_f, warp_f)
             flow_w = flow + d_flow[:, 0:2]
