@@ -5,7 +5,83 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
+
+
+class _GradHolder:
+    """fp32 gradient accumulators of one pyramid.  Every lookup's backward scatter-adds straight
+    into them (no per-lookup dense gradient tensors, no bf16 round trip); the pyramid's own
+    backward consumes them once all lookups are done."""
+
+    def __init__(self, vol0, vol1):
+        self.g0 = torch.zeros(vol0.shape, device=vol0.device, dtype=torch.float32)
+        self.g1 = torch.zeros(vol1.shape, device=vol1.device, dtype=torch.float32)
+
+
+class _CorrPyramidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_d, k_s, scale, holder_box):
+        vol0, vol1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, scale)
+        ctx.save_for_backward(q_d, k_s)
+        ctx.scale, ctx.holder_box = scale, holder_box
+        ctx.set_materialize_grads(False)
+        return vol0, vol1
+
+    @staticmethod
+    def backward(ctx, _g0, _g1):
+        # the volume gradients arrive through the holder (see _PyramidLookupFn), not through autograd
+        q_d, k_s = ctx.saved_tensors
+        holder = ctx.holder_box[0]
+        B, C, h, w = q_d.shape
+        N = h * w
+        if holder is None:
+            return torch.zeros_like(q_d), torch.zeros_like(k_s), None, None
+        # level-1 gradients: each pooled source cell feeds its 2x2 block with weight 1/4
+        g = holder.g0
+        g1 = holder.g1.view(B, -1, h // 2, w // 2)
+        g = g + (g1 * 0.25).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3).reshape(B, -1, N)
+        a_op, b_op = ops.corr_pack_debug(q_d.detach(), k_s.detach())
+        gb = (g * ctx.scale).to(torch.bfloat16)
+        d_a = torch.bmm(gb, b_op).float()                          # (B, rows_total, C)
+        d_b = torch.bmm(gb.transpose(1, 2), a_op).float()          # (B, N, C)
+        # driving operand rows: level 0 plus the average-pooled levels (pool backward = spread / k^2)
+        d_q = d_a[:, :N].transpose(1, 2).reshape(B, C, h, w)
+        off = N
+        for lvl in (1, 2, 3):
+            k = 1 << lvl
+            n_l = N >> (2 * lvl)
+            part = d_a[:, off:off + n_l].transpose(1, 2).reshape(B, C, h // k, w // k) / (k * k)
+            d_q = d_q + part.repeat_interleave(k, dim=2).repeat_interleave(k, dim=3)
+            off += n_l
+        d_k = d_b.transpose(1, 2).reshape(B, C, h, w)
+        ctx.holder_box[0] = None
+        return d_q.contiguous(), d_k.contiguous(), None, None
+
+
+class _PyramidLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, vol0, vol1, holder_box, H, W, stride, offset, radius, channels_last):
+        out = torch.ops.mrfa.corr_lookup(vol0, vol1, coords, H, W, stride, offset, radius, channels_last)
+        ctx.save_for_backward(coords, vol0, vol1)
+        ctx.cfg, ctx.holder_box = (H, W, stride, offset, radius), holder_box
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        coords, vol0, vol1 = ctx.saved_tensors
+        H, W, stride, offset, radius = ctx.cfg
+        holder = ctx.holder_box[0]
+        if holder is None:
+            holder = ctx.holder_box[0] = _GradHolder(vol0, vol1)
+        g = g.contiguous()
+        coords = coords.contiguous()
+        B, _, h1, w1 = coords.shape
+        gc = torch.empty_like(coords)
+        with torch.cuda.device(coords.device):
+            ops.check(ops.lib.mrfa_corr_lookup_bwd(ops._p(g), ops._p(vol0), ops._p(vol1), 1, ops._p(coords), ops._p(holder.g0),
+                                                   ops._p(holder.g1), ops._p(gc), B, h1 * w1, H, W, stride, offset, radius,
+                                                   ops._stream()), "mrfa_corr_lookup_bwd")
+        return gc, None, None, None, None, None, None, None, None, None
 
 
 class CorrPyramid:
@@ -20,7 +96,11 @@ class CorrPyramid:
 
     def __init__(self, q_d: torch.Tensor, k_s: torch.Tensor, scale: float):
         self.B, self.C, self.h, self.w = q_d.shape
-        self.volume0, self.volume1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, float(scale))
+        self._holder_box = [None]
+        if torch.is_grad_enabled() and (q_d.requires_grad or k_s.requires_grad):
+            self.volume0, self.volume1 = _CorrPyramidFn.apply(q_d, k_s, float(scale), self._holder_box)
+        else:
+            self.volume0, self.volume1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, float(scale))
         self.rows_total = self.volume0.shape[1]
 
     def block(self, pool_log2: int = 0, radius: int = 3) -> "CorrBlock":
@@ -56,6 +136,7 @@ class CorrBlock:
         self._H, self._W = corr.shape[-2:]
         self._stride = None          # maps per sample = queries per sample (set at call time)
         self._offset = 0
+        self._holder_box = None
 
     @classmethod
     def from_pyramid(cls, pyr: CorrPyramid, pool_log2: int, radius: int = 3) -> "CorrBlock":
@@ -65,6 +146,7 @@ class CorrBlock:
         self._H, self._W = pyr.h, pyr.w
         self._stride = pyr.rows_total
         self._offset = ops.corr_row_offset(pyr.h, pyr.w, pool_log2)
+        self._holder_box = pyr._holder_box
         return self
 
     def __call__(self, coords, channels_last: bool = False):
@@ -73,5 +155,9 @@ class CorrBlock:
         if self._stride is None and self.corr_pyramid[0].shape[0] != B * h1 * w1:
             raise RuntimeError("mrfa_b200: corr has %d maps but coords address %d queries"
                                % (self.corr_pyramid[0].shape[0], B * h1 * w1))
+        if self._holder_box is not None and torch.is_grad_enabled() and \
+                (coords.requires_grad or self.corr_pyramid[0].requires_grad):
+            return _PyramidLookupFn.apply(coords, self.corr_pyramid[0], self.corr_pyramid[1], self._holder_box, self._H,
+                                          self._W, stride, self._offset, self.radius, channels_last)
         return torch.ops.mrfa.corr_lookup(self.corr_pyramid[0], self.corr_pyramid[1], coords, self._H, self._W,
                                           stride, self._offset, self.radius, channels_last)
