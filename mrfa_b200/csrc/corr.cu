@@ -815,6 +815,7 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
 }
 
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -881,7 +882,7 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
     const char* e = getenv("MRFA_CORR_DEBUG");
     prm.debug = e ? atoi(e) : 0;
     const char* m = getenv("MRFA_CORR_STORE");
-    prm.store_mode = m ? atoi(m) : 1;
+    prm.store_mode = m ? atoi(m) : 0;
   }
   prm.N = N;
   prm.rows_total = rows_total;
@@ -1009,7 +1010,9 @@ static bool use_direct_epilogue() {
   return v;
 }
 
-static int corr_variant() {      // MRFA_CORR_VARIANT=1: 256-row units x 128-wide tiles (A/B measurements only)
+// MRFA_CORR_VARIANT (A/B measurements only): 1 = 256-row units x 128-wide tiles, 4 = 2-CTA cluster with
+// multicast B tiles; default 0 = 128-row units x 256-wide tiles, no cluster (all within 3 % on B200)
+static int corr_variant() {
   static const int v = []() {
     const char* e = getenv("MRFA_CORR_VARIANT");
     return e ? atoi(e) : 0;
@@ -1038,14 +1041,14 @@ extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume
       // 128-row units, 256-wide tiles (two source row pairs): every B tile (32 KiB per K block) feeds
       // 128x256 outputs and ~96 KiB of B stay in flight; deeper K falls back to 128-wide tiles
       if (corr_variant() == 1) return launch_corr_volume_tma<64, 128, 2, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-      if (corr_variant() == 2 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-      if (C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-      return launch_corr_volume_tma<64, 128, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 4 && C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      return launch_corr_volume_tma<64, 128, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 128:
       MRFA_CHECK_SHAPE(N % 256 == 0);
       if (use_direct_epilogue()) return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-      if (corr_variant() == 2) return launch_corr_volume_tma<128, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
-      return launch_corr_volume_tma<128, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 4) return launch_corr_volume_tma<128, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      return launch_corr_volume_tma<128, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     default: return MRFA_E_SHAPE;
   }
 }

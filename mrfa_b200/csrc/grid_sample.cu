@@ -6,6 +6,7 @@
 // parallelism), and lanes map to consecutive output pixels so both the taps (smooth motion
 // fields) and the stores are coalesced.  Roofline: HBM, algorithmic bytes per warp call =
 // (2*C*Ho*Wo + 2*Ho*Wo) * 4.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mrfa {
@@ -231,16 +232,17 @@ __device__ __forceinline__ float4 blend4b(float4 a, float4 b, float4 c, float4 d
   r.w = fmaf(d.w, t.w_se, fmaf(c.w, t.w_sw, fmaf(b.w, t.w_ne, a.w * t.w_nw)));
   return r;
 }
-__device__ __forceinline__ TapsB to_tapsb(const Taps& t, int n_in) {
+// offsets are pre-multiplied by C (element offsets inside one image, < 2^31 by the ABI check)
+__device__ __forceinline__ TapsB to_tapsb(const Taps& t, int n_in, int C) {
   TapsB r;
-  r.o_nw = t.o_nw; r.o_ne = t.o_ne; r.o_sw = t.o_sw; r.o_se = t.o_se; r.n_in = n_in;
+  r.o_nw = t.o_nw * C; r.o_ne = t.o_ne * C; r.o_sw = t.o_sw * C; r.o_se = t.o_se * C; r.n_in = n_in;
   r.w_nw = t.w_nw; r.w_ne = t.w_ne; r.w_sw = t.w_sw; r.w_se = t.w_se;
   return r;
 }
 
 // LPP = lanes per pixel (power of two, LPP * 4 <= C or LPP == 1)
 // PW = pixels per warp (32 for large problems; 4 keeps enough warps in flight for small ones)
-template <int MODE, int PAD, bool ADD_ID, int LPP, int PW>
+template <int MODE, int PAD, bool ADD_ID, int LPP, int PW, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
 grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
                             float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div) {
@@ -259,20 +261,20 @@ grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restric
     const int y = p / Wo, x = p - y * Wo;
     float ix, iy, mx, my;
     load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
-    mine = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div);
+    mine = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div, C);
   }
   const int sub = lane / LPPE, cl = (lane % LPPE) * 4;
   const int64_t plane = (int64_t)H * W * C;
-#pragma unroll 4
+#pragma unroll UNROLL
   for (int s = 0; s < PW; s += PPS) {
     const TapsB t = shfl_taps(mine, s + sub);
     const int64_t gp = gp0 + s + sub;
     if (gp >= total) continue;
-    const float* src = in + (int64_t)t.n_in * plane;
-    float* dst = out + gp * C;
-    for (int c = cl; c < C; c += LPPE * 4) {
-      const float4 a = ldg4(src + (int64_t)t.o_nw * C + c), b = ldg4(src + (int64_t)t.o_ne * C + c);
-      const float4 d = ldg4(src + (int64_t)t.o_sw * C + c), e = ldg4(src + (int64_t)t.o_se * C + c);
+    const float* src = in + (int64_t)t.n_in * plane + cl;
+    float* dst = out + gp * C + cl;
+    for (int c = 0; c < C - cl; c += LPPE * 4) {
+      const float4 a = ldg4(src + (t.o_nw + c)), b = ldg4(src + (t.o_ne + c));
+      const float4 d = ldg4(src + (t.o_sw + c)), e = ldg4(src + (t.o_se + c));
       stcs4(dst + c, blend4b(a, b, d, e, t));
     }
   }
@@ -297,9 +299,9 @@ dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict_
     const int y = p / W, x = p - y * W;
     const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
     const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
-    mr = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n);
+    mr = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n, C);
     const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
-    mc = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n);
+    mc = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n, C);
   }
   const int sub = lane / LPPE, cl = (lane % LPPE) * 4;
   const int64_t plane = (int64_t)HW * C;
@@ -309,16 +311,20 @@ dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict_
     const TapsB tc = shfl_taps(mc, s + sub);
     const int64_t gp = gp0 + s + sub;
     if (gp >= total) continue;
-    const float* src = in + (int64_t)tr.n_in * plane;
-    float* dr = out_r + gp * C;
-    float* dc = out_c + gp * C;
-    for (int c = cl; c < C; c += LPPE * 4) {
-      const float4 a0 = ldg4(src + (int64_t)tr.o_nw * C + c), a1 = ldg4(src + (int64_t)tr.o_ne * C + c);
-      const float4 a2 = ldg4(src + (int64_t)tr.o_sw * C + c), a3 = ldg4(src + (int64_t)tr.o_se * C + c);
-      const float4 b0 = ldg4(src + (int64_t)tc.o_nw * C + c), b1 = ldg4(src + (int64_t)tc.o_ne * C + c);
-      const float4 b2 = ldg4(src + (int64_t)tc.o_sw * C + c), b3 = ldg4(src + (int64_t)tc.o_se * C + c);
-      stcs4(dr + c, blend4b(a0, a1, a2, a3, tr));
-      stcs4(dc + c, blend4b(b0, b1, b2, b3, tc));
+    const float* src = in + (int64_t)tr.n_in * plane + cl;
+    float* dr = out_r + gp * C + cl;
+    float* dc = out_c + gp * C + cl;
+    for (int c = 0; c < C - cl; c += LPPE * 4) {
+      {
+        const float4 a0 = ldg4(src + (tr.o_nw + c)), a1 = ldg4(src + (tr.o_ne + c));
+        const float4 a2 = ldg4(src + (tr.o_sw + c)), a3 = ldg4(src + (tr.o_se + c));
+        stcs4(dr + c, blend4b(a0, a1, a2, a3, tr));
+      }
+      {
+        const float4 b0 = ldg4(src + (tc.o_nw + c)), b1 = ldg4(src + (tc.o_ne + c));
+        const float4 b2 = ldg4(src + (tc.o_sw + c)), b3 = ldg4(src + (tc.o_se + c));
+        stcs4(dc + c, blend4b(b0, b1, b2, b3, tc));
+      }
     }
   }
 }
@@ -397,11 +403,14 @@ static int launch_fwd_nhwc_lpp(const float* in, const float* grid, mrfa_grid_str
                                int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
   const int64_t pixels = (int64_t)N * Ho * Wo;
   const bool small = pixels < kSmallPixels;
+  static const int unroll = []() { const char* e = getenv("MRFA_WARP_UNROLL"); return e ? atoi(e) : 2; }();
   dim3 g((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
 #define MRFA_GS_CASE(L)                                                                                            \
   case L:                                                                                                          \
-    if (small) grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 4><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); \
-    else grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 32><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);    \
+    if (small) grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 4, 2><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); \
+    else if (unroll == 1) grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 32, 1><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); \
+    else if (unroll == 4) grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 32, 4><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); \
+    else grid_sample_fwd_nhwc_kernel<MODE, PAD, ADD_ID, L, 32, 2><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);    \
     break;
   switch (lanes_per_pixel(C)) {
     MRFA_GS_CASE(1) MRFA_GS_CASE(2) MRFA_GS_CASE(4) MRFA_GS_CASE(8) MRFA_GS_CASE(16) MRFA_GS_CASE(32)
@@ -474,7 +483,7 @@ extern "C" int mrfa_grid_sample_fwd(const float* in, const float* grid, mrfa_gri
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31) && (int64_t)Ho * Wo < (1ll << 31));
   if (N == 0) return 0;
   if (channels_last) {
-    MRFA_CHECK_SHAPE(C % 4 == 0);
+    MRFA_CHECK_SHAPE(C % 4 == 0 && (int64_t)H * W * C < (1ll << 31));
     if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return MRFA_E_ALIGN;
     DISPATCH_MODE_PAD(launch_fwd_nhwc, in, grid, gs, out, N, C, H, W, Ho, Wo, in_batch_div, add_identity, as_stream(stream));
   }
@@ -509,7 +518,7 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31));
   if (N == 0) return 0;
   if (channels_last) {
-    MRFA_CHECK_SHAPE(C % 4 == 0);
+    MRFA_CHECK_SHAPE(C % 4 == 0 && (int64_t)H * W * C < (1ll << 31));
     if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_refined) | reinterpret_cast<uintptr_t>(out_coarse)) & 15) != 0)
       return MRFA_E_ALIGN;
     const int64_t pixels = (int64_t)N * H * W;

@@ -475,3 +475,53 @@ def test_corr_channels_last_inputs_and_lookup_output(golden):
         b = ref.block(lvl)(coords, True)
         assert b.is_contiguous(memory_format=torch.channels_last)
         assert torch.equal(a, b.contiguous())
+
+
+# ------------------------------------------------------------------ fused elementwise passes
+@pytest.mark.parametrize("cl", [False, True])
+def test_channel_affine_and_blend(cl):
+    torch.manual_seed(11)
+    B, C, H, W = 2, 8, 5, 7
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    x = torch.randn(B, C, H, W, device=DEV).contiguous(memory_format=fmt)
+    r = torch.randn(B, C, H, W, device=DEV).contiguous(memory_format=fmt)
+    s, t = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    sv, tv = s.view(1, C, 1, 1), t.view(1, C, 1, 1)
+    close(torch.ops.mrfa.channel_affine(x, s, t, None, 1), torch.relu(x * sv + tv), 1e-6)
+    close(torch.ops.mrfa.channel_affine(x, None, t, r, 0), x + tv + r, 1e-6)
+    close(torch.ops.mrfa.channel_affine(x, s, None, None, 2), torch.sigmoid(x * sv), 1e-6)
+    occ = torch.rand(B, 1, H, W, device=DEV)
+    close(torch.ops.mrfa.occlusion_blend(x, r, occ), x * occ + r * (1 - occ), 1e-6)
+    close(torch.ops.mrfa.occlusion_blend(x, None, occ), x * occ, 1e-6)
+    odd = torch.randn(B, 3, H, W, device=DEV)                       # C % 4 != 0 -> NCHW path
+    close(torch.ops.mrfa.occlusion_blend(odd, odd * 2, occ), odd * occ + odd * 2 * (1 - occ), 1e-6)
+
+
+def test_fast_inference_blocks_match_plain():
+    """BN folding / fused conv-bias-ReLU / fused blends are a re-association, not new numerics."""
+    from mrfa_b200 import blocks, synthetic as syn
+    torch.manual_seed(12)
+    gen = syn.fill_state_dict_(blocks.OcclusionAwareGenerator(3, 16, 64, 3)).to(DEV).eval()
+    hg = syn.fill_state_dict_(blocks.Hourglass(8, 5, 3, 32)).to(DEV).eval()
+    x = torch.rand(2, 3, 32, 32, device=DEV)
+    z = torch.randn(2, 5, 16, 16, device=DEV)
+    with torch.no_grad():
+        for cl in (False, True):
+            if cl:
+                gen.to(memory_format=torch.channels_last)
+                hg.to(memory_format=torch.channels_last)
+            feats_fast = gen.encode(x)
+            occ = [torch.rand(2, 1, f.shape[2], f.shape[3], device=DEV) for f in feats_fast]
+            out_fast = gen.decode(feats_fast, x, occ, [f * 0.5 for f in feats_fast], occ)
+            hg_fast = hg(z)
+            blocks.FAST_INFERENCE = False
+            try:
+                feats = gen.encode(x)
+                out = gen.decode(feats, x, occ, [f * 0.5 for f in feats], occ)
+                hg_plain = hg(z)
+            finally:
+                blocks.FAST_INFERENCE = True
+            for a, b in zip(feats_fast, feats):
+                close(a, b, 2e-5, 1e-5)
+            close(out_fast, out, 2e-5)
+            close(hg_fast, hg_plain, 2e-5, 1e-5)
