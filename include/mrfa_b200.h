@@ -211,6 +211,13 @@ int mrfa_channel_affine(const float* x, const float* scale, const float* shift, 
 int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float* y,
                          int64_t pixels, int C, int HW, int channels_last, mrfa_stream_t stream);
 
+/* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) raft.py:243 (and :205,228,
+ * 266,...) fused with an optional activation (act as above).  SURVEY.md 8(f) N1: used as
+ * relu(upsample(convc1(corr))) == relu(convc1(upsample(corr))) (raft.py:241-243, :61).
+ * x (N,C,H,W) -> y (N,C,Ho,Wo); NCHW or NHWC memory (any C; vectorised when C % 4 == 0).       */
+int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
+                         int channels_last, int act, mrfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

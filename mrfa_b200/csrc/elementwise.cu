@@ -82,6 +82,89 @@ occlusion_blend_nchw_kernel(const float* __restrict__ a, const float* __restrict
   }
 }
 
+
+// Bilinear resize with align_corners=True (F.interpolate as used at raft.py:243) fused with an
+// optional activation: SURVEY.md 8(f) row N1.  A 1x1 convolution commutes with this resize, so
+// the decoder applies convc1 at the basic resolution and lets this kernel produce
+// relu(upsample(.)) directly -- the (B,98,R,R) upsampled correlation features are never written.
+// Same interpolation arithmetic as ATen upsample_bilinear2d (scale = (in-1)/(out-1) in fp32).
+__device__ __forceinline__ void resize_axis(int o, float scale, int in, int& i0, int& i1, float& l1) {
+  const float src = scale * (float)o;
+  i0 = min((int)src, in - 1);
+  i1 = min(i0 + 1, in - 1);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
+                            float sy, float sx, int64_t total4, int act) {
+  const int cq = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) * 4;
+    const int64_t pix = i / cq;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int64_t n = pix / ((int64_t)Wo * Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_axis(oy, sy, H, y0, y1, ly);
+    resize_axis(ox, sx, W, x0, x1, lx);
+    const float* base = x + n * H * W * C + c;
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * W + x0) * C));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * W + x1) * C));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * W + x0) * C));
+    const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * W + x1) * C));
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    float4 r;
+    r.x = act_fn(hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x), act);
+    r.y = act_fn(hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y), act);
+    r.z = act_fn(hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z), act);
+    r.w = act_fn(hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w), act);
+    __stcs(reinterpret_cast<float4*>(y) + i, r);
+  }
+}
+
+// NHWC with any channel count (flows / occlusion maps coming out of channels-last convolutions)
+__global__ void __launch_bounds__(256)
+resize_bilinear_nhwc_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho,
+                                   int Wo, float sy, float sx, int64_t total, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int64_t n = pix / ((int64_t)Wo * Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_axis(oy, sy, H, y0, y1, ly);
+    resize_axis(ox, sx, W, x0, x1, lx);
+    const float* base = x + n * H * W * C + c;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float v = hy * (hx * __ldg(base + ((int64_t)y0 * W + x0) * C) + lx * __ldg(base + ((int64_t)y0 * W + x1) * C)) +
+                    ly * (hx * __ldg(base + ((int64_t)y1 * W + x0) * C) + lx * __ldg(base + ((int64_t)y1 * W + x1) * C));
+    y[i] = act_fn(v, act);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int Ho, int Wo, float sy,
+                            float sx, int64_t total, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const int64_t plane = i / ((int64_t)Wo * Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_axis(oy, sy, H, y0, y1, ly);
+    resize_axis(ox, sx, W, x0, x1, lx);
+    const float* p = x + plane * H * W;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float v = hy * (hx * __ldg(p + y0 * W + x0) + lx * __ldg(p + y0 * W + x1)) +
+                    ly * (hx * __ldg(p + y1 * W + x0) + lx * __ldg(p + y1 * W + x1));
+    y[i] = act_fn(v, act);
+  }
+}
+
 static inline unsigned stream_blocks(int64_t items) {
   int64_t b = cdiv64(items, 256);
   return (unsigned)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b));
@@ -124,6 +207,26 @@ extern "C" int mrfa_occlusion_blend(const float* a, const float* b, const float*
         reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), occ, reinterpret_cast<float4*>(y), n / 4, C);
   } else {
     occlusion_blend_nchw_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(a, b, occ, y, n, C, HW);
+  }
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
+                                    int channels_last, int act, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(x && y && N >= 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && act >= 0 && act <= 2);
+  if (N == 0) return 0;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t total = (int64_t)N * C * Ho * Wo;
+  if (channels_last && C % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    resize_bilinear_nhwc_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
+                                                                                         total / 4, act);
+  } else if (channels_last) {
+    resize_bilinear_nhwc_scalar_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
+                                                                                            total, act);
+  } else {
+    resize_bilinear_nchw_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, H, W, Ho, Wo, sy, sx, total, act);
   }
   return MRFA_LAUNCH_RESULT();
 }

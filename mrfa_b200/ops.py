@@ -40,6 +40,14 @@ def _is_channels_last(t: Tensor) -> bool:
             and t.is_contiguous(memory_format=torch.channels_last))
 
 
+def _suggest_channels_last(t: Tensor) -> bool:
+    """Layout a result should take to stay in the producer's memory format (like ATen's
+    suggest_memory_format): NHWC if the tensor is channels_last or a channel slice of one."""
+    if t.dim() != 4 or t.is_contiguous():
+        return False
+    return t.is_contiguous(memory_format=torch.channels_last) or (t.stride(1) == 1 and t.shape[1] > 1)
+
+
 def _req_image(t: Tensor, name: str):
     """float32 CUDA image in either NCHW or NHWC memory; returns (tensor, channels_last flag)."""
     if not t.is_cuda:
@@ -620,3 +628,27 @@ def occlusion_blend(a: Tensor, b: Optional[Tensor], occ: Tensor) -> Tensor:
 @occlusion_blend.register_fake
 def _(a, b, occ):
     return torch.empty_like(a)
+
+
+@torch.library.custom_op("mrfa::resize_bilinear", mutates_args=(), device_types="cuda")
+def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int) -> Tensor:
+    """F.interpolate(x, (Ho,Wo), mode='bilinear', align_corners=True) + activation (0/1 relu/2 sigmoid).
+    The memory format of `x` (NCHW or channels_last, any C) is preserved."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+        raise RuntimeError("mrfa_b200: resize_bilinear expects a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    cl = _suggest_channels_last(x)
+    x = x.contiguous(memory_format=torch.channels_last) if cl else x.contiguous()
+    N, C, H, W = x.shape
+    y = _empty_image((N, C, Ho, Wo), x.device, cl)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        with _timed("resize_bilinear", 4 * (x.numel() + y.numel())):
+            check(lib.mrfa_resize_bilinear(_p(x), _p(y), N, C, H, W, Ho, Wo, int(cl), act, _stream()), "mrfa_resize_bilinear")
+    return y
+
+
+@resize_bilinear.register_fake
+def _(x, Ho, Wo, act):
+    y = x.new_empty((x.shape[0], x.shape[1], Ho, Wo))
+    return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y

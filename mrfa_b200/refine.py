@@ -12,11 +12,14 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import sampling
-from .blocks import Hourglass, OcclusionAwareGenerator, conv_relu
+from .blocks import Hourglass, OcclusionAwareGenerator, conv_relu, fast_path
 from .corr import CorrPyramid
 
 
 def _resize(x, size):
+    """F.interpolate(bilinear, align_corners=True); on the inference path one fused kernel."""
+    if x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
+        return torch.ops.mrfa.resize_bilinear(x, int(size[0]), int(size[1]), 0)
     return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
 
 
@@ -33,7 +36,15 @@ class BasicMotionEncoder(nn.Module):
         self.conv = nn.Conv2d(64 + 96, 128 - 2, 3, padding=1)
 
     def forward(self, delta_flow, corr):
-        c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
+        if corr.shape[-2:] != delta_flow.shape[-2:]:
+            # correlation features still at the basic resolution (levels above it, raft.py:241-243):
+            # the 1x1 convc1 commutes with the align_corners bilinear resize, so apply it first and
+            # let one kernel produce relu(resize(.)) -- the 98-channel upsampled tensor is never built
+            c1 = F.conv2d(corr, self.convc1.weight, self.convc1.bias)
+            c = torch.ops.mrfa.resize_bilinear(c1, delta_flow.shape[-2], delta_flow.shape[-1], 1)
+            c = conv_relu(self.convc2, c)
+        else:
+            c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
         f = conv_relu(self.convf2, conv_relu(self.convf1, delta_flow))
         y = conv_relu(self.conv, torch.cat([c, f], dim=1))
         return torch.cat([y, delta_flow], dim=1)
@@ -138,8 +149,9 @@ class RaftFlow(nn.Module):
         prior = dense_motion["deformation"]
         prior_occ = dense_motion["occlusion"]
         init_flow = torch.ops.mrfa.prior_to_flow(prior, float(self.h - 1))                    # raft.py:189-190
-        flow = F.interpolate(init_flow, scale_factor=1.0 / 8.0, mode="bilinear", align_corners=True) / 8.0
-        occlusion = F.interpolate(prior_occ, scale_factor=1.0 / 8.0, mode="bilinear", align_corners=True)
+        r0 = (self.h // 8, self.w // 8)                       # scale_factor 1/8 == size h//8 under align_corners=True
+        flow = _resize(init_flow, r0) / 8.0
+        occlusion = _resize(prior_occ, r0)
         prior_nchw = prior.permute(0, 3, 1, 2)
         ident_basic = sampling.coords_grid(B, h, w, dev)
 
@@ -156,7 +168,9 @@ class RaftFlow(nn.Module):
                 corr = pyramid.block(0)(flow + ident_basic, cl)
             else:
                 flow_sample = _resize(flow, (self.h, self.h)) * 0.5 ** (i - base)
-                corr = _resize(pyramid.block(0)(flow_sample + ident_basic, cl), (R, R))
+                corr = pyramid.block(0)(flow_sample + ident_basic, cl)
+                if not fast_path(self, corr):                   # reference order (differentiable path)
+                    corr = _resize(corr, (R, R))
             m_f = self.corr_enc(flow, corr)
 
             # ---- warps of feature[i]: refined (at flow) and coarse (prior grid) in one pass ----

@@ -525,3 +525,23 @@ def test_fast_inference_blocks_match_plain():
                 close(a, b, 2e-5, 1e-5)
             close(out_fast, out, 2e-5)
             close(hg_fast, hg_plain, 2e-5, 1e-5)
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_resize_bilinear(cl):
+    torch.manual_seed(13)
+    x = torch.randn(2, 8, 16, 16, device=DEV)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    for size in ((64, 64), (32, 32), (16, 16), (8, 8), (37, 21)):
+        ref = F.interpolate(x.cpu().contiguous(), size=size, mode="bilinear", align_corners=True)
+        out = torch.ops.mrfa.resize_bilinear(x, size[0], size[1], 0)
+        assert out.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+        close(out, ref, 2e-6)
+        close(torch.ops.mrfa.resize_bilinear(x, size[0], size[1], 1), torch.relu(ref), 2e-6)
+    flow = torch.randn(2, 2, 9, 9, device=DEV)                        # 2-channel maps keep their layout too
+    if cl:
+        flow = flow.contiguous(memory_format=torch.channels_last)
+    out = torch.ops.mrfa.resize_bilinear(flow, 18, 18, 0)
+    assert out.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+    close(out, F.interpolate(flow.cpu().contiguous(), size=(18, 18), mode="bilinear", align_corners=True), 2e-6)
