@@ -35,7 +35,7 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--config", default="vox1", choices=["vox1", "celebvhq"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep the networks in NCHW memory (default: channels_last)")
+    ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark (algorithm autotuning)")
     ap.add_argument("--ref-batch", type=int, default=0, help="pairs per step of the CPU reference arm (0 = auto)")
     return ap.parse_args()
 
@@ -192,6 +193,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = load_cfg(args.config)
@@ -294,21 +296,32 @@ def run_ours(args):
                 e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
         klist.append(e)
     ours_ms = sum(k["total_ms"] for k in kernels.values())
-    top = klist[0] if klist else None
-    roofline = None
-    if top:
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top["kernel"])
-        if top["kernel"] == "corr_volume":
-            roofline = {"kernel": "corr_volume", "bound": "tensor", "achieved": top["tflops"],
-                        "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tensor_frac"],
-                        "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
-                        "note": "output-write-bound: also see hbm_frac in kernels[]"}
+    # roofline: the dominant kernel of the hot path proper; the fused
+    # elementwise helpers of the "next" rows are listed in kernels[] only
+    helpers = ("channel_affine", "occlusion_blend", "resize_bilinear")
+    hot = [k for k in klist if k["kernel"] not in helpers]
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_tbl = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+    def roof(entry):
+        if entry is None:
+            return None
+        t = traffic_tbl.get(entry["kernel"])
+        per_step = entry["launches"] // max(1, args.steps)
+        base = {"kernel": entry["kernel"], "launches_per_step": per_step, "avg_launch_ms": entry["avg_ms"],
+                "traffic": t, "traffic_scope": "ncu dram__bytes_read+write summed over this kernel's launches in one step "
+                                               "(B=64, 256x256; profiles/r1_hot_kernels_ncu.md)" if t else None}
+        if entry["kernel"] == "corr_volume":
+            base.update({"bound": "tensor", "achieved": entry["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": entry["tensor_frac"], "peak_source": pk["source"] + " (sustained bf16)",
+                         "hbm_frac_of_output_bytes": entry["hbm_frac"]})
         else:
-            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["hbm_gbs"], "peak": pk["hbm_gbs"],
-                        "unit": "GB/s", "frac": top["hbm_frac"], "traffic": traffic, "peak_source": pk["source"]}
+            base.update({"bound": "hbm", "achieved": entry["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": entry["hbm_frac"], "peak_source": pk["source"]})
+        return base
+
+    roofline = roof(hot[0] if hot else None)
+    roofline_corr = roof(next((k for k in klist if k["kernel"] == "corr_volume"), None))
 
     line = {"metric": METRIC, "value": pairs / (dev_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -317,7 +330,7 @@ def run_ours(args):
             "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": sum(k["launches"] for k in kernels.values()),
-            "roofline": roofline, "kernels": klist,
+            "roofline": roofline, "roofline_corr": roofline_corr, "kernels": klist,
             "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
             "recon_l1_mean": float(sums[0] / sums[1]), "peaks": pk}
     if not args.no_cpu_baseline:

@@ -281,7 +281,7 @@ grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restric
 }
 
 template <int LPP, int PW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
                           float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W) {
   constexpr int PPS = (32 / LPP) < PW ? (32 / LPP) : PW;
