@@ -816,6 +816,248 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 }
 
 
+
+// ============================================================================================
+// 2-SM variant: the CTA pair of a cluster issues one `tcgen05.mma.cta_group::2` of M = 256 per
+// K step.  Each CTA keeps its own 128 A rows stationary and loads only HALF of every B tile
+// (its 128 of the 256 source columns); the tensor cores read both halves across the pair, so the
+// L2 -> SM operand traffic per output halves and the B ring needs half the shared memory.  The
+// leader CTA (cluster rank 0) issues the MMAs; TMA loads of both CTAs signal the leader's
+// barriers; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; both CTAs
+// drain their own TMEM lanes and store their own 128 rows.
+// ============================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address of the pair's even CTA
+
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {     // arrive on cluster rank 0's copy
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int kW>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+corr_volume_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1,
+                       const Gemm2Params prm) {
+  using Cfg = Gemm2Cfg<kW, 256, 1>;
+  constexpr int kBlockN = 256;
+  constexpr uint32_t kBHalfBytes = (kBlockN / 2) * kBlockK * 2;           // this CTA's half of a B stage
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                                 // [kblocks][128 x 128 B]
+  uint8_t* smem_b = smem_a + (size_t)prm.kblocks * kATileBytes;           // [b_stages][128 x 128 B]
+  uint8_t* smem_st = smem_b + (size_t)prm.b_stages * kBHalfBytes;         // [4 warps][kStageWarpBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + 4 * kStageWarpBytes);
+  uint64_t* a_full = bars;               // [8]  (leader's copy is the live one)
+  uint64_t* a_empty = bars + 8;          // [8]
+  uint64_t* b_full = bars + 16;          // [8]  (leader)
+  uint64_t* b_empty = bars + 24;         // [8]
+  uint64_t* t_full = bars + 32;          // [2]
+  uint64_t* t_empty = bars + 34;         // [2]  (leader; 8 arrivals: 4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int64_t cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v1) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_unit = prm.n_tiles / prm.n_split;
+  const int64_t units = (int64_t)prm.B * prm.m_blocks * prm.n_split;     // m_blocks counts 256-row blocks
+
+  if (warp == 0) {
+    if (lane == 0) {                                   // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int64_t u = cid; u < units; u += ncl, ++it) {
+        const int split = (int)(u % prm.n_split);
+        const int m_blk = (int)((u / prm.n_split) % prm.m_blocks) * 2 + (int)crank;
+        const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+        const uint32_t aphase = it & 1u;
+        for (int kb = 0; kb < prm.kblocks; ++kb) {
+          mbar_wait(&a_empty[kb], aphase ^ 1u);
+          if (leader) mbar_expect_tx(&a_full[kb], 2 * kATileBytes);
+          tma_load_3d_2sm(smem_a + (size_t)kb * kATileBytes, &map_a, &a_full[kb], kb * kBlockK, m_blk * kBlockM, b);
+        }
+        for (int t = 0; t < tiles_per_unit; ++t) {
+          const int nt = split * tiles_per_unit + t;
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            if (leader) mbar_expect_tx(&b_full[stage], 2 * kBHalfBytes);
+            tma_load_3d_2sm(smem_b + (size_t)stage * kBHalfBytes, &map_b, &b_full[stage], kb * kBlockK,
+                            nt * kBlockN + (int)crank * (kBlockN / 2), b);
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {                         // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(256, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0, it = 0, tcount = 0;
+      for (int64_t u = cid; u < units; u += ncl, ++it) {
+        const uint32_t aphase = it & 1u;
+        for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+          const uint32_t acc = tcount & 1u;
+          mbar_wait(&t_empty[acc], ((tcount >> 1) & 1u) ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kBlockN;
+          for (int kb = 0; kb < prm.kblocks; ++kb) {
+            if (t == 0) mbar_wait(&a_full[kb], aphase);
+            mbar_wait(&b_full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + (size_t)kb * kATileBytes);
+            const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * kBHalfBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tcgen05_mma_bf16_2sm(tmem_d, umma_desc_sw128(a_addr + k * kUmmaK * 2), umma_desc_sw128(b_addr + k * kUmmaK * 2),
+                                   idesc, (uint32_t)((kb | k) != 0));
+            tcgen05_commit_2sm(&b_empty[stage]);
+            if (t == tiles_per_unit - 1) tcgen05_commit_2sm(&a_empty[kb]);
+            if (++stage == prm.b_stages) { stage = 0; phase ^= 1u; }
+          }
+          tcgen05_commit_2sm(&t_full[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): TMEM -> registers -> swizzled smem -> TMA store =====
+    const int ew = warp - 4;
+    const float scale = prm.scale, scale4 = prm.scale * 0.25f;
+    const uint32_t st_base = smem_u32(smem_st + (size_t)ew * kStageWarpBytes);
+    const uint32_t box0 = st_base, box1 = st_base + 4096, boxl = st_base + 8192;
+    const uint32_t row128 = (uint32_t)lane * 128, row64 = (uint32_t)lane * 64;
+    const uint32_t sw128 = (uint32_t)(lane & 7), sw64 = (uint32_t)((lane >> 1) & 3);
+    uint32_t tcount = 0;
+    for (int64_t u = cid; u < units; u += ncl) {
+      const int split = (int)(u % prm.n_split);
+      const int m_blk = (int)((u / prm.n_split) % prm.m_blocks) * 2 + (int)crank;
+      const int b = (int)(u / ((int64_t)prm.n_split * prm.m_blocks));
+      const int row0 = m_blk * kBlockM + ew * 32;
+      for (int t = 0; t < tiles_per_unit; ++t, ++tcount) {
+        const int nt = split * tiles_per_unit + t;
+        const uint32_t acc = tcount & 1u;
+        mbar_wait(&t_full[acc], (tcount >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
+#pragma unroll 1
+        for (int gs = 0; gs < Cfg::kGroups * Cfg::kSteps; ++gs) {
+          const int g = gs / Cfg::kSteps, s = gs - g * Cfg::kSteps;
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int c0 = g * 2 * kW + s * 64 + sub * 32;
+            const int c1 = c0 + kW;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(taddr + c0, v0);
+            tmem_ld_32x32(taddr + c1, v1);
+            tmem_ld_wait();
+            uint32_t p0[16], p1[16], pl[8];
+            float pooled[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
+              const float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
+              p0[j] = pack_bf16(a0 * scale, a1 * scale);
+              p1[j] = pack_bf16(b0 * scale, b1 * scale);
+              pooled[j] = ((a0 + a1) + (b0 + b1)) * scale4;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t ch = (uint32_t)(sub * 4 + j) ^ sw128;
+              st_shared_v4(box0 + row128 + ch * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+              st_shared_v4(box1 + row128 + ch * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t ch = (uint32_t)(sub * 2 + j) ^ sw64;
+              st_shared_v4(boxl + row64 + ch * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+          }
+          if (gs == Cfg::kGroups * Cfg::kSteps - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&t_empty[acc]);       // the leader's MMA warp owns the wait
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int col = nt * kBlockN + g * 2 * kW + s * 64;
+            const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+            tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes, col, row0, b);
+            tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + kW, row0, b);
+            tma_store_3d(&map_v1, smem_st + (size_t)ew * kStageWarpBytes + 8192, colp, row0, b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)512) : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -913,6 +1155,63 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_v0, map_v1, prm);
+  return (int)e;
+}
+
+template <int kW>
+static int launch_corr_volume_2sm(const void* a_op, const void* b_op, void* v0, void* v1, int B, int C, int h, int w,
+                                  float scale, int num_sms, cudaStream_t st) {
+  constexpr int kBlockN = 256;
+  Gemm2Params prm = {};
+  prm.B = B;
+  prm.kblocks = C / kBlockK;
+  const int N = h * w;
+  const int64_t rows_total = mrfa_corr_rows_total(h, w);
+  prm.m_blocks = (int)cdiv64(rows_total, 2 * kBlockM);
+  prm.n_tiles = N / kBlockN;
+  prm.scale = scale;
+  prm.N = N;
+  prm.rows_total = rows_total;
+  const uint32_t half = (kBlockN / 2) * kBlockK * 2;
+  const uint32_t fixed = (uint32_t)prm.kblocks * kATileBytes + 4 * kStageWarpBytes + 2048;
+  const uint32_t budget = 227 * 1024;
+  if (fixed + 2 * half > budget) return MRFA_E_SHAPE;
+  int stages = (int)((budget - fixed) / half);
+  prm.b_stages = stages > 8 ? 8 : stages;
+  const uint32_t smem_bytes = fixed + prm.b_stages * half;
+  int n_split = 1;
+  while ((int64_t)B * prm.m_blocks * n_split < 2ll * (num_sms / 2) && n_split * 2 <= prm.n_tiles &&
+         prm.n_tiles % (n_split * 2) == 0)
+    n_split *= 2;
+  prm.n_split = n_split;
+  CUtensorMap map_a, map_b, map_v0, map_v1;
+  int rc = make_operand_map(&map_a, a_op, C, rows_total, B, kBlockM);
+  if (rc) return rc;
+  rc = make_operand_map(&map_b, b_op, C, N, B, kBlockN / 2);
+  if (rc) return rc;
+  rc = make_bf16_map(&map_v0, v0, N, rows_total, B, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_bf16_map(&map_v1, v1, N / 4, rows_total, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  auto kern = corr_volume_2sm_kernel<kW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t units = (int64_t)B * prm.m_blocks * n_split;
+  int64_t clusters = num_sms / 2;
+  if (units < clusters) clusters = units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -1041,12 +1340,14 @@ extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume
       // 128-row units, 256-wide tiles (two source row pairs): every B tile (32 KiB per K block) feeds
       // 128x256 outputs and ~96 KiB of B stay in flight; deeper K falls back to 128-wide tiles
       if (corr_variant() == 1) return launch_corr_volume_tma<64, 128, 2, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 5 && N % 256 == 0) return launch_corr_volume_2sm<64>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       if (corr_variant() == 4 && C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       if (C <= 256 && N % 256 == 0) return launch_corr_volume_tma<64, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       return launch_corr_volume_tma<64, 128, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 128:
       MRFA_CHECK_SHAPE(N % 256 == 0);
       if (use_direct_epilogue()) return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
+      if (corr_variant() == 5) return launch_corr_volume_2sm<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       if (corr_variant() == 4) return launch_corr_volume_tma<128, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       return launch_corr_volume_tma<128, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     default: return MRFA_E_SHAPE;

@@ -120,7 +120,7 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
     r.y = act_fn(hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y), act);
     r.z = act_fn(hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z), act);
     r.w = act_fn(hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w), act);
-    __stcs(reinterpret_cast<float4*>(y) + i, r);
+    *(reinterpret_cast<float4*>(y) + i) = r;
   }
 }
 

@@ -98,7 +98,7 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
         acc = fmaf(c[1], fx * (1.f - fy), acc);
         acc = fmaf(c[F], (1.f - fx) * fy, acc);
         acc = fmaf(c[F + 1], fx * fy, acc);
-        __stcs(dst + k, acc);
+        *(dst + k) = acc;
       }
     }
     return;
@@ -120,7 +120,7 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
       acc = fmaf(c[1], w_ne, acc);
       acc = fmaf(c[F], w_sw, acc);
       acc = fmaf(c[F + 1], w_se, acc);
-      __stcs(dst + (int64_t)(lvl * n * n + k) * Q, acc);
+      *(dst + (int64_t)(lvl * n * n + k) * Q) = acc;
     }
   }
 }

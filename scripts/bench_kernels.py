@@ -110,6 +110,14 @@ with torch.no_grad():
             nb = min(B, 16)
             ms = timeit(lambda: torch.einsum("bic,bjc->bij", qf[:nb], kf[:nb]) * C ** -0.5)
             report("stock_einsum_fp32(+scale)", ms * B / nb, 0, 2 * B * N * N * C, note=f"timed on {nb} pairs, scaled")
+            # cuBLAS bf16 on the same packed operands: basic-resolution rows only (no pooled rows, no level 1)
+            ab, bb = a_op[:, :N], b_op.transpose(1, 2)
+            ms = timeit(lambda: torch.bmm(ab, bb))
+            report("cublas_bmm_bf16[4096x4096x256 -> bf16]", ms, 2 * (ab.numel() + b_op.numel() + B * N * N), 2 * B * N * N * C,
+                   note="plain product: 0.60x of our output bytes, 0.75x of our executed FLOPs, no scale / pooling")
+            ms = timeit(lambda: torch.bmm(a_op, bb))
+            report("cublas_bmm_bf16[5440x4096x256 -> bf16]", ms, 2 * (a_op.numel() + b_op.numel() + B * rows * N), 2 * B * N * N * C,
+                   note="all driving levels, still without the source-pooled level 1 (0.8x of our output bytes)")
         # lookups at the six levels
         for i, R in enumerate([S // 32 * 2 ** j for j in range(6)]):
             Rq = min(R, h)
