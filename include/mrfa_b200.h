@@ -211,12 +211,25 @@ int mrfa_channel_affine(const float* x, const float* scale, const float* shift, 
 int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float* y,
                          int64_t pixels, int C, int HW, int channels_last, mrfa_stream_t stream);
 
+/* Same blend with b given as a sub-pixel up-convolution result (UpBlock2d util.py:160-177 as one 2x2
+ * conv with 4*C phase-major outputs on the padded low-resolution map): a, y (N,C,2H,2W) NHWC;
+ * b2 (N,4C,H+1,W+1) NHWC, phase (Y&1, X&1) of pixel (Y,X) at b2[n, Y/2+(Y&1), X/2+(X&1), (2(Y&1)+(X&1))*C+c];
+ * occ (N,1,2H,2W).  C % 4 == 0.                                                               */
+int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y,
+                                  int N, int C, int H, int W, mrfa_stream_t stream);
+
 /* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) raft.py:243 (and :205,228,
  * 266,...) fused with an optional activation (act as above).  SURVEY.md 8(f) N1: used as
  * relu(upsample(convc1(corr))) == relu(convc1(upsample(corr))) (raft.py:241-243, :61).
  * x (N,C,H,W) -> y (N,C,Ho,Wo); NCHW or NHWC memory (any C; vectorised when C % 4 == 0).       */
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
+
+/* AntiAliasInterpolation2d.forward util.py:318-326 for scale = 1/stride:
+ * F.pad(ka) -> depthwise KxK conv with weight (C,1,K,K) -> nearest sub-sampling, evaluated only at
+ * the kept pixels.  in (N,C,H,W) NCHW -> out (N,C,H/stride,W/stride).  K odd (ka == kb).      */
+int mrfa_antialias_down(const float* in, const float* weight, float* out, int N, int C, int H, int W, int K,
+                        int ka, int stride, mrfa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,32 @@ class SameBlock2d(_ConvNormAct):
 class UpBlock2d(_ConvNormAct):
     pre_upsample = True
 
+    def subpixel_ok(self, x):
+        c = self.conv
+        return (fast_path(self, x) and tuple(c.kernel_size) == (3, 3) and tuple(c.padding) == (1, 1)
+                and tuple(c.stride) == (1, 1) and c.groups == 1 and c.out_channels % 4 == 0
+                and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+
+    def forward_subpixel(self, x):
+        """relu(norm(conv(upsample_x2_nearest(x)))) as ONE 2x2 convolution on the padded low-res
+        input with 4*Cout phase-major outputs (B, 4*Cout, H+1, W+1): output parity (a,b) of pixel
+        (Y,X) lives at [Y//2 + a, X//2 + b, (2a+b)*Cout + c].  3x3 rows {0,1,2} over a nearest x2
+        map collapse to low-res rows {y-1, y, y} (a=0) or {y, y, y+1} (a=1): 16/36 of the FLOPs and
+        no upsampled tensor.  Consumed by mrfa::occlusion_blend_subpixel."""
+        c, n = self.conv, self.norm
+        if not hasattr(self, "_sub"):
+            self._sub = _Cache()
+
+        def build():
+            w, b = _fold(c, n)
+            R = [torch.tensor([[1., 0., 0.], [0., 1., 1.]], device=w.device), torch.tensor([[1., 1., 0.], [0., 0., 1.]], device=w.device)]
+            w2 = torch.cat([torch.einsum("pi,ocij,qj->ocpq", R[a], w, R[q]) for a in (0, 1) for q in (0, 1)], dim=0)
+            return w2.contiguous(memory_format=torch.channels_last), b.repeat(4).contiguous()
+
+        w2, b2 = self._sub.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), build)
+        xp = F.pad(x, (1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+        return torch.cudnn_convolution_relu(xp, w2, b2, (1, 1), (0, 0), (1, 1), 1)
+
 
 class DownBlock2d(_ConvNormAct):
     post_pool = True
@@ -219,6 +245,11 @@ class AntiAliasInterpolation2d(nn.Module):
     def forward(self, x):
         if self.scale == 1.0:
             return x
+        stride = round(1 / self.scale)
+        if (fast_path(self, x) and self.ka == self.kb and abs(stride * self.scale - 1) < 1e-9
+                and x.shape[2] % stride == 0 and x.shape[3] % stride == 0):
+            # evaluate the Gaussian only at the pixels the nearest sub-sampling keeps
+            return torch.ops.mrfa.antialias_down(x, self.weight, self.ka, stride)
         y = F.pad(x, (self.ka, self.kb, self.ka, self.kb))
         y = F.conv2d(y, weight=self.weight, groups=self.groups)
         return F.interpolate(y, scale_factor=(self.scale, self.scale))
@@ -277,8 +308,13 @@ class OcclusionAwareGenerator(nn.Module):
         for i in range(self.num_up_blocks):
             if use_coarse:
                 y = self.channel_block[i](y)
-            y = self.up_blocks[i](self.resblock[i](y))
-            y = blend(warp_f[i + 1], y, occlusion[i + 1])
+            y = self.resblock[i](y)
+            up = self.up_blocks[i]
+            if up.subpixel_ok(y) and warp_f[i + 1].is_contiguous(memory_format=torch.channels_last) \
+                    and not warp_f[i + 1].is_contiguous():
+                y = torch.ops.mrfa.occlusion_blend_subpixel(warp_f[i + 1], up.forward_subpixel(y), occlusion[i + 1])
+            else:
+                y = blend(warp_f[i + 1], up(y), occlusion[i + 1])
             if use_coarse and i != self.num_up_blocks - 1:
                 y = torch.cat([y, warp_f_c[i + 1]], dim=1)
         y = torch.sigmoid(self.final(y))

@@ -165,6 +165,63 @@ resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, 
   }
 }
 
+
+// AntiAliasInterpolation2d (util.py:282-326): zero-padded depthwise
+// KxK Gaussian followed by nearest sub-sampling by `stride`.  The reference convolves at full
+// resolution and throws 15/16 of the result away; this evaluates only the kept pixels.
+// NCHW in / out; out[b,c,y,x] = sum_ij w[c,i,j] * in[b,c, y*stride + i - ka, x*stride + j - ka].
+__global__ void __launch_bounds__(256)
+antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ weight, float* __restrict__ out, int C,
+                      int H, int W, int Ho, int Wo, int K, int ka, int stride, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int64_t plane = i / ((int64_t)Wo * Ho);
+    const int c = (int)(plane % C);
+    const float* src = in + plane * H * W;
+    const float* wc = weight + (int64_t)c * K * K;
+    const int y0 = y * stride - ka, x0 = x * stride - ka;
+    float acc = 0.f;
+    for (int a = 0; a < K; ++a) {
+      const int yy = y0 + a;
+      if (yy < 0 || yy >= H) continue;
+      for (int b = 0; b < K; ++b) {
+        const int xx = x0 + b;
+        if (xx >= 0 && xx < W) acc = fmaf(__ldg(src + (int64_t)yy * W + xx), __ldg(wc + a * K + b), acc);
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+
+// Occlusion blend whose second operand is a "sub-pixel" up-convolution result: a 3x3 conv on a
+// x2 nearest-upsampled map equals four 2x2 convs on the low-resolution map (one per output
+// parity), so UpBlock2d (util.py:160-177) runs as ONE 2x2 conv with 4*C outputs on the padded
+// low-res input (16/36 of the FLOPs, no upsampled tensor) and this kernel reads phase (a,b) of
+// full-res pixel (Y,X) at b2[n, Y/2 + a, X/2 + b, (2a+b)*C + c] with a = Y&1, b = X&1.
+// y = a * occ + b2_shuffled * (1 - occ);  a, y: (N, 2H, 2W, C) NHWC;  b2: (N, H+1, W+1, 4C) NHWC.
+__global__ void __launch_bounds__(256)
+occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ occ,
+                                float4* __restrict__ y, int64_t n4, int C, int H, int W) {
+  const int cq = C / 4, W2 = 2 * W, H2 = 2 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) * 4;
+    const int64_t pix = i / cq;
+    const int X = (int)(pix % W2);
+    const int Y = (int)((pix / W2) % H2);
+    const int64_t n = pix / ((int64_t)W2 * H2);
+    const int pa = Y & 1, pb = X & 1;
+    const float o = __ldg(occ + pix);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(
+        b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C + c));
+    float4 v = __ldg(a + i);
+    const float q = 1.f - o;
+    v.x = fmaf(w.x, q, v.x * o); v.y = fmaf(w.y, q, v.y * o); v.z = fmaf(w.z, q, v.z * o); v.w = fmaf(w.w, q, v.w * o);
+    y[i] = v;
+  }
+}
+
 static inline unsigned stream_blocks(int64_t items) {
   int64_t b = cdiv64(items, 256);
   return (unsigned)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b));
@@ -228,5 +285,29 @@ extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int 
   } else {
     resize_bilinear_nchw_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, H, W, Ho, Wo, sy, sx, total, act);
   }
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_antialias_down(const float* in, const float* weight, float* out, int N, int C, int H, int W, int K,
+                                   int ka, int stride, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(in && weight && out && N >= 0 && C > 0 && H > 0 && W > 0 && K > 0 && ka >= 0 && stride > 0);
+  if (N == 0) return 0;
+  const int Ho = H / stride, Wo = W / stride;       // floor(H * scale) of F.interpolate(scale_factor = 1/stride)
+  MRFA_CHECK_SHAPE(Ho > 0 && Wo > 0);
+  const int64_t total = (int64_t)N * C * Ho * Wo;
+  antialias_down_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(in, weight, out, C, H, W, Ho, Wo, K, ka, stride, total);
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y, int N, int C,
+                                             int H, int W, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(a && b2 && occ && y && N >= 0 && C > 0 && H > 0 && W > 0);
+  MRFA_CHECK_SHAPE(C % 4 == 0);
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
+    return MRFA_E_ALIGN;
+  if (N == 0) return 0;
+  const int64_t n4 = (int64_t)N * 4 * H * W * C / 4;
+  occlusion_blend_subpixel_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W);
   return MRFA_LAUNCH_RESULT();
 }

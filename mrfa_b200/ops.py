@@ -652,3 +652,46 @@ def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int) -> Tensor:
 def _(x, Ho, Wo, act):
     y = x.new_empty((x.shape[0], x.shape[1], Ho, Wo))
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
+
+
+@torch.library.custom_op("mrfa::antialias_down", mutates_args=(), device_types="cuda")
+def antialias_down(x: Tensor, weight: Tensor, ka: int, stride: int) -> Tensor:
+    """AntiAliasInterpolation2d for scale 1/stride, computing only the kept pixels (NCHW)."""
+    x, weight = _req(x, "x"), _req(weight, "weight")
+    N, C, H, W = x.shape
+    K = weight.shape[-1]
+    y = torch.empty((N, C, H // stride, W // stride), device=x.device, dtype=torch.float32)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        with _timed("antialias_down", 4 * (x.numel() + y.numel())):
+            check(lib.mrfa_antialias_down(_p(x), _p(weight), _p(y), N, C, H, W, K, ka, stride, _stream()), "mrfa_antialias_down")
+    return y
+
+
+@antialias_down.register_fake
+def _(x, weight, ka, stride):
+    return x.new_empty((x.shape[0], x.shape[1], x.shape[2] // stride, x.shape[3] // stride))
+
+
+@torch.library.custom_op("mrfa::occlusion_blend_subpixel", mutates_args=(), device_types="cuda")
+def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor) -> Tensor:
+    """a * occ + shuffle(b2) * (1 - occ) with b2 the phase-major sub-pixel up-conv output (see header)."""
+    a, cl = _req_image(a, "a")
+    b2, cl2 = _req_image(b2, "b2")
+    occ = _req(occ, "occ")
+    N, C, H2, W2 = a.shape
+    H, W = H2 // 2, W2 // 2
+    if not (cl and cl2) or tuple(b2.shape) != (N, 4 * C, H + 1, W + 1) or tuple(occ.shape) != (N, 1, H2, W2):
+        raise RuntimeError("mrfa_b200: occlusion_blend_subpixel expects channels_last a (N,C,2H,2W), b2 (N,4C,H+1,W+1), occ (N,1,2H,2W)")
+    y = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        with _timed("occlusion_blend", 4 * (2 * a.numel() + a.numel() + occ.numel())):
+            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(y), N, C, H, W, _stream()),
+                  "mrfa_occlusion_blend_subpixel")
+    return y
+
+
+@occlusion_blend_subpixel.register_fake
+def _(a, b2, occ):
+    return torch.empty_like(a)

@@ -545,3 +545,20 @@ def test_resize_bilinear(cl):
     out = torch.ops.mrfa.resize_bilinear(flow, 18, 18, 0)
     assert out.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
     close(out, F.interpolate(flow.cpu().contiguous(), size=(18, 18), mode="bilinear", align_corners=True), 2e-6)
+
+
+def test_antialias_down_matches_reference_order():
+    from mrfa_b200 import blocks
+    torch.manual_seed(14)
+    for scale, size in ((0.25, 64), (0.25, 256), (0.5, 32)):
+        aa = blocks.AntiAliasInterpolation2d(3, scale).to(DEV).eval()
+        x = torch.rand(2, 3, size, size, device=DEV)
+        with torch.no_grad():
+            fast = aa(x)
+            blocks.FAST_INFERENCE = False
+            try:
+                plain = aa(x)
+            finally:
+                blocks.FAST_INFERENCE = True
+        assert fast.shape == plain.shape
+        close(fast, plain, 2e-6)
