@@ -88,52 +88,65 @@ corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, _
 
 // channels-last inputs: (B,h,w,C) in memory is already "(h w) c" row-major, so the pack is a
 // vectorised cast (float4 -> 4 x bf16) plus the pooled driving rows; one thread per (row, 4 ch).
-// grid (row chunks, B): blockIdx.y = pair; thread = (row, channel quad) with 32-bit indexing only
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  return make_uint2(
+      (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.y)) << 16),
+      (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.z)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.w)) << 16));
+}
+
+// Driving operand: thread = (pair, 8x8 pixel block, channel quad).  Every input pixel is read
+// exactly once; the 2x2 / 4x4 / 8x8 means are built hierarchically in registers and written as
+// the pooled rows of a_op.  Lanes run along the channel quads -> 512-byte loads, 256-byte stores.
 __global__ void __launch_bounds__(256)
-corr_pack_nhwc_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, __nv_bfloat16* __restrict__ a_op,
-                      __nv_bfloat16* __restrict__ b_op, int C, int h, int w, int rows_total) {
-  const int hw = h * w, cq = C / 4;
+corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, __nv_bfloat16* __restrict__ a_op, int C, int h, int w,
+                        int rows_total) {
+  const int cq = C / 4, bw = w / 8;
+  const int nblk = (h / 8) * bw;
   const int b = blockIdx.y;
-  const int rows_all = rows_total + hw;
-  const uint32_t total = (uint32_t)rows_all * (uint32_t)cq;
+  const int hw = h * w;
+  const int off1 = hw, off2 = hw + hw / 4, off3 = hw + hw / 4 + hw / 16;
   const float* qb = q_d + (int64_t)b * hw * C;
-  const float* kb = k_s + (int64_t)b * hw * C;
   __nv_bfloat16* ab = a_op + (int64_t)b * rows_total * C;
-  __nv_bfloat16* bb = b_op + (int64_t)b * hw * C;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r_ = (int)(i / (uint32_t)cq);
-    const int c = (int)(i - (uint32_t)r_ * (uint32_t)cq) * 4;
-    float4 acc;
-    __nv_bfloat16* dst;
-    if (r_ < hw) {                                              // driving level 0: plain cast
-      acc = __ldg(reinterpret_cast<const float4*>(qb + (int64_t)r_ * C + c));
-      dst = ab + (int64_t)r_ * C + c;
-    } else if (r_ >= rows_total) {                              // source operand: plain cast
-      const int r = r_ - rows_total;
-      acc = __ldg(reinterpret_cast<const float4*>(kb + (int64_t)r * C + c));
-      dst = bb + (int64_t)r * C + c;
-    } else {                                                    // pooled driving rows
-      int lvl = 1, r = r_ - hw;
-      while (r >= (hw >> (2 * lvl))) { r -= hw >> (2 * lvl); ++lvl; }
-      const int k = 1 << lvl, wl = w >> lvl;
-      const int py = r / wl, px = r - py * wl;
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int dy = 0; dy < k; ++dy) {
-        const float* row = qb + ((int64_t)(py * k + dy) * w + px * k) * C + c;
-        for (int dx = 0; dx < k; ++dx) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(row + (int64_t)dx * C));
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)nblk * cq; i += gridDim.x * blockDim.x) {
+    const int blk = (int)(i / (uint32_t)cq);
+    const int c = (int)(i - (uint32_t)blk * cq) * 4;
+    const int by = blk / bw, bx = blk - by * bw;
+    float4 s8 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q8 = 0; q8 < 4; ++q8) {                      // 4x4 quadrants of the 8x8 block
+      const int y4 = by * 8 + (q8 >> 1) * 4, x4 = bx * 8 + (q8 & 1) * 4;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {                    // 2x2 blocks of the quadrant
+        const int y2 = y4 + (q4 >> 1) * 2, x2 = x4 + (q4 & 1) * 2;
+        float4 v[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          v[p] = __ldg(reinterpret_cast<const float4*>(qb + ((int64_t)(y2 + (p >> 1)) * w + x2 + (p & 1)) * C + c));
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          *reinterpret_cast<uint2*>(ab + ((int64_t)(y2 + (p >> 1)) * w + x2 + (p & 1)) * C + c) = pack_bf16x4(v[p]);
+        float4 s2;
+        s2.x = (v[0].x + v[1].x) + (v[2].x + v[3].x); s2.y = (v[0].y + v[1].y) + (v[2].y + v[3].y);
+        s2.z = (v[0].z + v[1].z) + (v[2].z + v[3].z); s2.w = (v[0].w + v[1].w) + (v[2].w + v[3].w);
+        *reinterpret_cast<uint2*>(ab + ((int64_t)off1 + (y2 / 2) * (w / 2) + x2 / 2) * C + c) =
+            pack_bf16x4(make_float4(s2.x * 0.25f, s2.y * 0.25f, s2.z * 0.25f, s2.w * 0.25f));
+        s4.x += s2.x; s4.y += s2.y; s4.z += s2.z; s4.w += s2.w;
       }
-      const float inv = 1.f / (float)(k * k);
-      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-      dst = ab + (int64_t)r_ * C + c;
+      *reinterpret_cast<uint2*>(ab + ((int64_t)off2 + (y4 / 4) * (w / 4) + x4 / 4) * C + c) =
+          pack_bf16x4(make_float4(s4.x * 0.0625f, s4.y * 0.0625f, s4.z * 0.0625f, s4.w * 0.0625f));
+      s8.x += s4.x; s8.y += s4.y; s8.z += s4.z; s8.w += s4.w;
     }
-    const uint2 packed = make_uint2(
-        (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.y)) << 16),
-        (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.z)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc.w)) << 16));
-    *reinterpret_cast<uint2*>(dst) = packed;
+    *reinterpret_cast<uint2*>(ab + ((int64_t)off3 + by * bw + bx) * C + c) =
+        pack_bf16x4(make_float4(s8.x * 0.015625f, s8.y * 0.015625f, s8.z * 0.015625f, s8.w * 0.015625f));
   }
+}
+
+// Source operand: a plain vectorised cast
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = pack_bf16x4(__ldg(x + i));
 }
 
 // ============================================================================================
@@ -1283,12 +1296,19 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
   if (channels_last) {
     if (((reinterpret_cast<uintptr_t>(q_d) | reinterpret_cast<uintptr_t>(k_s)) & 15) != 0) return MRFA_E_ALIGN;
     const int64_t rows_total = mrfa_corr_rows_total(h, w);
-    const int64_t total = (rows_total + (int64_t)h * w) * (C / 4);
-    MRFA_CHECK_SHAPE(total < (1ll << 31));
-    int64_t blocks = cdiv64(total, 256);
+    const int64_t items = (int64_t)(h / 8) * (w / 8) * (C / 4);
+    MRFA_CHECK_SHAPE(items < (1ll << 31) && rows_total < (1ll << 31));
+    int64_t blocks = cdiv64(items, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    corr_pack_nhwc_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, as_stream(stream)>>>(
-        q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), C, h, w, (int)rows_total);
+    corr_pack_nhwc_q_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, as_stream(stream)>>>(
+        q_d, static_cast<__nv_bfloat16*>(a_op), C, h, w, (int)rows_total);
+    int rc = MRFA_LAUNCH_RESULT();
+    if (rc) return rc;
+    const int64_t n4 = (int64_t)B * h * w * C / 4;
+    int64_t cblocks = cdiv64(n4, 256);
+    if (cblocks > 148 * 32) cblocks = 148 * 32;
+    cast_bf16_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(k_s),
+                                                                      static_cast<uint2*>(b_op), n4);
     return MRFA_LAUNCH_RESULT();
   }
   const int tile_w = w < 32 ? w : 32;

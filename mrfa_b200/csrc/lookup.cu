@@ -51,29 +51,44 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   constexpr int kStride = 2 * FF + 1;                 // odd -> conflict-free lane-per-query reads
   __shared__ float foot[kQPB * kStride];
   __shared__ float frac[kQPB][4];
+  __shared__ int org[kQPB][4];                        // footprint origin (x0, y0) per level
 
   const int b = blockIdx.y;
   const int q0 = blockIdx.x * kQPB;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int H1 = H / 2, W1 = W / 2;
 
-  // ---- phase 1: gather footprints -------------------------------------------------------
+  // ---- phase 0: lane = query.  The IEEE coordinate round trip is evaluated once per query
+  //      (not once per lane of the gathering warp) and parked in shared memory. ----
+  if (warp == 0) {
+    const int q = q0 + lane;
+    if (q < Q) {
+      const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
+      const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
+#pragma unroll
+      for (int lvl = 0; lvl < 2; ++lvl) {
+        const QueryGeom g = query_geom(cx, cy, lvl, lvl ? H1 : H, lvl ? W1 : W, R);
+        frac[lane][2 * lvl] = g.fx; frac[lane][2 * lvl + 1] = g.fy;
+        org[lane][2 * lvl] = g.x0; org[lane][2 * lvl + 1] = g.y0;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: warp per query, gather both footprints ------------------------------------
   for (int qi = warp; qi < kQPB; qi += kLookupThreads / 32) {
     const int q = q0 + qi;
     if (q >= Q) break;
-    const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
-    const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
     const int64_t map = (int64_t)b * map_batch_stride + row_offset + q;
 #pragma unroll
     for (int lvl = 0; lvl < 2; ++lvl) {
       const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
-      const QueryGeom g = query_geom(cx, cy, lvl, Hl, Wl, R);
+      const int gx0 = org[qi][2 * lvl], gy0 = org[qi][2 * lvl + 1];
       const T* base = (lvl ? level1 : level0) + map * ((int64_t)Hl * Wl);
-      if (lane == 0) { frac[qi][2 * lvl] = g.fx; frac[qi][2 * lvl + 1] = g.fy; }
 #pragma unroll
       for (int e = lane; e < FF; e += 32) {
         const int fy_ = e / F, fx_ = e - fy_ * F;
-        const int yy = g.y0 + fy_, xx = g.x0 + fx_;
+        const int yy = gy0 + fy_, xx = gx0 + fx_;
         float v = 0.f;
         if (yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) v = ld_elem<T>(base + (int64_t)yy * Wl + xx);
         foot[qi * kStride + lvl * FF + e] = v;
