@@ -225,6 +225,10 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* F.avg_pool2d(x, (2,2)) of DownBlock2d (util.py:190-196) in NHWC memory: x (N,C,H,W) -> y (N,C,H/2,W/2),
+ * C % 4 == 0, 16-byte aligned.                                                               */
+int mrfa_avg_pool2x2_nhwc(const float* x, float* y, int N, int C, int H, int W, mrfa_stream_t stream);
+
 /* AntiAliasInterpolation2d.forward util.py:318-326 for scale = 1/stride:
  * F.pad(ka) -> depthwise KxK conv with weight (C,1,K,K) -> nearest sub-sampling, evaluated only at
  * the kept pixels.  in (N,C,H,W) NCHW -> out (N,C,H/stride,W/stride).  K odd (ka == kb).      */

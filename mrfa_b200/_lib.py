@@ -45,6 +45,7 @@ SIGNATURES = {
                              + [c_int64, c_int64, c_int, c_int, c_void_p]),
     "mrfa_channel_affine": (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mrfa_occlusion_blend_subpixel": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
+    "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_antialias_down": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),

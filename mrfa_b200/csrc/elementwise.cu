@@ -222,6 +222,30 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
   }
 }
 
+
+// 2x2 average pooling in NHWC (DownBlock2d, util.py:190-196): one float4 per thread, 4 loads +
+// 1 store, window summed row-major then divided by 4 like ATen.  (The stock NHWC avg_pool2d
+// kernel runs at ~0.8 TB/s on the 2 GB encoder maps.)
+__global__ void __launch_bounds__(256)
+avg_pool2x2_nhwc_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int H, int W, int64_t n4) {
+  const int cq = C / 4, Wo = W / 2, Ho = H / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) * 4;
+    const int64_t pix = i / cq;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int64_t n = pix / ((int64_t)Wo * Ho);
+    const float* p = x + ((n * H + 2 * oy) * W + 2 * ox) * (int64_t)C + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + C));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * C));
+    const float4 e = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * C + C));
+    float4 r;
+    r.x = (((a.x + b.x) + d.x) + e.x) * 0.25f; r.y = (((a.y + b.y) + d.y) + e.y) * 0.25f;
+    r.z = (((a.z + b.z) + d.z) + e.z) * 0.25f; r.w = (((a.w + b.w) + d.w) + e.w) * 0.25f;
+    y[i] = r;
+  }
+}
+
 static inline unsigned stream_blocks(int64_t items) {
   int64_t b = cdiv64(items, 256);
   return (unsigned)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b));
@@ -309,5 +333,15 @@ extern "C" int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, co
   const int64_t n4 = (int64_t)N * 4 * H * W * C / 4;
   occlusion_blend_subpixel_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W);
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_avg_pool2x2_nhwc(const float* x, float* y, int N, int C, int H, int W, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(x && y && N >= 0 && C > 0 && H >= 2 && W >= 2);
+  MRFA_CHECK_SHAPE(C % 4 == 0);
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return MRFA_E_ALIGN;
+  if (N == 0) return 0;
+  const int64_t n4 = (int64_t)N * (H / 2) * (W / 2) * C / 4;
+  avg_pool2x2_nhwc_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, H, W, n4);
   return MRFA_LAUNCH_RESULT();
 }

@@ -695,3 +695,25 @@ def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor) -> Tensor:
 @occlusion_blend_subpixel.register_fake
 def _(a, b2, occ):
     return torch.empty_like(a)
+
+
+@torch.library.custom_op("mrfa::avg_pool2x2_nhwc", mutates_args=(), device_types="cuda")
+def avg_pool2x2_nhwc(x: Tensor) -> Tensor:
+    """F.avg_pool2d(x, (2, 2)) for channels_last activations (C % 4 == 0)."""
+    x, cl = _req_image(x, "x")
+    if not cl:
+        raise RuntimeError("mrfa_b200: avg_pool2x2_nhwc expects a channels_last tensor with C % 4 == 0")
+    N, C, H, W = x.shape
+    y = _empty_image((N, C, H // 2, W // 2), x.device, True)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        with _timed("avg_pool2x2_nhwc", 4 * (x.numel() + y.numel())):
+            check(lib.mrfa_avg_pool2x2_nhwc(_p(x), _p(y), N, C, H, W, _stream()), "mrfa_avg_pool2x2_nhwc")
+    return y
+
+
+@avg_pool2x2_nhwc.register_fake
+def _(x):
+    y = x.new_empty((x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2))
+    return y.contiguous(memory_format=torch.channels_last)

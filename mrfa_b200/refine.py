@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import sampling
-from .blocks import Hourglass, OcclusionAwareGenerator, conv_relu, fast_path
+from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_path
 from .corr import CorrPyramid
 
 
@@ -46,7 +46,27 @@ class BasicMotionEncoder(nn.Module):
         else:
             c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
         f = conv_relu(self.convf2, conv_relu(self.convf1, delta_flow))
-        y = conv_relu(self.conv, torch.cat([c, f], dim=1))
+        cf = torch.cat([c, f], dim=1)
+        if fast_path(self, cf) and self.conv.out_channels + delta_flow.shape[1] == 128:
+            # 126 output channels force cuDNN through pad / un-pad copies of the whole map: run the
+            # convolution with two zero filters appended (128 channels) and drop the flow into
+            # those two channels -- same values as cat([relu(conv(.)), flow]) without the cat.
+            if not hasattr(self, "_pad"):
+                self._pad = _Cache()
+            cv = self.conv
+
+            def build():
+                w = torch.cat([cv.weight, cv.weight.new_zeros((2,) + tuple(cv.weight.shape[1:]))], dim=0)
+                b = torch.cat([cv.bias, cv.bias.new_zeros(2)])
+                if cv.weight.is_contiguous(memory_format=torch.channels_last):
+                    w = w.contiguous(memory_format=torch.channels_last)
+                return w, b
+
+            w, b = self._pad.get((cv.weight, cv.bias), build)
+            y = torch.cudnn_convolution_relu(cf, w, b, cv.stride, cv.padding, cv.dilation, cv.groups)
+            y[:, 126:128] = delta_flow
+            return y
+        y = conv_relu(self.conv, cf)
         return torch.cat([y, delta_flow], dim=1)
 
 

@@ -30,6 +30,7 @@ a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
@@ -86,7 +87,7 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": "vox1 training step (L1 loss, Adam), fwd+bwd", "pairs_per_gpu": a.batch, "n_gpus": world,
-                      "ms_per_step": float(ms), "pairs_per_s": a.batch * world / float(ms) * 1e3, "loss": float(loss),
+                      "ms_per_step": float(ms), "pairs_per_s": a.batch * world / float(ms) * 1e3, "loss": float(loss.detach()),
                       "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
 if world > 1:
     dist.destroy_process_group()

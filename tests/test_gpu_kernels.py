@@ -562,3 +562,11 @@ def test_antialias_down_matches_reference_order():
                 blocks.FAST_INFERENCE = True
         assert fast.shape == plain.shape
         close(fast, plain, 2e-6)
+
+
+def test_avg_pool2x2_nhwc():
+    torch.manual_seed(15)
+    x = torch.randn(3, 8, 10, 6, device=DEV).contiguous(memory_format=torch.channels_last)
+    out = torch.ops.mrfa.avg_pool2x2_nhwc(x)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    close(out, F.avg_pool2d(x.cpu().contiguous(), (2, 2)), 1e-6)
