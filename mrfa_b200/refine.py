@@ -83,6 +83,31 @@ class RefineFlow(nn.Module):
 
     def forward(self, m_f, warp_f):
         inp = torch.cat([m_f, conv_relu(self.convc1, warp_f)], dim=1)
+        if fast_path(self, inp):
+            # conv1 | convo1 read the same 256-channel input: run them as one 256 -> 256 convolution
+            # (one pass over `inp`), then conv2 / convo2 as one block-diagonal 256 -> 4 convolution
+            # whose channels are [flow_x, flow_y, occlusion, 0] -- identical arithmetic per output.
+            if not hasattr(self, "_merged"):
+                self._merged = _Cache()
+
+            def build():
+                cl = self.conv1.weight.is_contiguous(memory_format=torch.channels_last)
+                w1 = torch.cat([self.conv1.weight, self.convo1.weight], dim=0)
+                b1 = torch.cat([self.conv1.bias, self.convo1.bias])
+                z2 = self.conv2.weight.new_zeros(self.conv2.weight.shape)
+                zo = self.convo2.weight.new_zeros(self.convo2.weight.shape)
+                w2 = torch.cat([torch.cat([self.conv2.weight, z2], dim=1), torch.cat([zo, self.convo2.weight], dim=1),
+                                self.conv2.weight.new_zeros((1, 256) + tuple(self.conv2.weight.shape[2:]))], dim=0)
+                b2 = torch.cat([self.conv2.bias, self.convo2.bias, self.conv2.bias.new_zeros(1)])
+                if cl:
+                    w1, w2 = w1.contiguous(memory_format=torch.channels_last), w2.contiguous(memory_format=torch.channels_last)
+                return w1, b1, w2, b2
+
+            w1, b1, w2, b2 = self._merged.get((self.conv1.weight, self.conv1.bias, self.convo1.weight, self.convo1.bias,
+                                               self.conv2.weight, self.conv2.bias, self.convo2.weight, self.convo2.bias), build)
+            hdn = torch.cudnn_convolution_relu(inp, w1, b1, self.conv1.stride, self.conv1.padding, self.conv1.dilation, 1)
+            out = F.conv2d(hdn, w2, b2, self.conv2.stride, self.conv2.padding)
+            return out[:, :3], inp
         flow = self.conv2(conv_relu(self.conv1, inp))
         occ = self.convo2(conv_relu(self.convo1, inp))
         return torch.cat([flow, occ], dim=1), inp
