@@ -116,3 +116,28 @@ def test_bench_reference_arm_skips_nonzero_ranks():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_patch_reference_rebinds_names():
+    """patch_reference() swaps the hot-path names inside an imported reference checkout (only
+    runs where the reference is mounted; the GPU box has no reference)."""
+    ref = os.environ.get("MRFA_REF", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "modules")):
+        pytest.skip("reference checkout not available")
+    code = f"""
+import sys, types, torch
+for n in ("timm", "timm.models", "timm.models.layers", "timm.models.layers.weight_init"):
+    sys.modules.setdefault(n, types.ModuleType(n))
+sys.modules["timm.models.layers.weight_init"].trunc_normal_ = torch.nn.init.trunc_normal_
+sys.path.insert(0, {ref!r}); sys.path.insert(0, {ROOT!r})
+import mrfa_b200
+mods = mrfa_b200.patch_reference("modules")
+import modules.raft as raft, modules.dense_motion as dm, modules.util as util
+assert raft.CorrBlock is mrfa_b200.CorrBlock and raft.RaftFlow is mrfa_b200.RaftFlow
+assert raft.bilinear_sampler is mrfa_b200.bilinear_sampler and raft.coords_grid is mrfa_b200.coords_grid
+assert dm.DenseMotionNetwork is mrfa_b200.DenseMotionNetwork and dm.TPS is mrfa_b200.TPS
+assert util.kp2gaussian is mrfa_b200.kp2gaussian and util.deform_input is mrfa_b200.deform_input
+print("PATCHED")
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0 and "PATCHED" in res.stdout, res.stderr[-1500:]
