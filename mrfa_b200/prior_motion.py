@@ -59,9 +59,13 @@ class DenseMotionNetwork(nn.Module):
         if self.scale_factor != 1:
             self.down = AntiAliasInterpolation2d(num_channels, self.scale_factor)
 
+    channels_last = False
+    auto_channels_last = True
+
     def channels_last_(self, enable: bool = True):
         """Run the hourglass convolutions in NHWC memory (see RaftFlow.channels_last_)."""
         self.to(memory_format=torch.channels_last if enable else torch.contiguous_format)
+        self.channels_last = enable
         return self
 
     # --- the three reference helper methods, each backed by the fused kernel -------------------
@@ -115,6 +119,8 @@ class DenseMotionNetwork(nn.Module):
         return out.view(B, K1, -1, h, w)
 
     def forward(self, source_image, kp_driving, kp_source, bg_param=None, dropout_flag=False, dropout_p=0):
+        if self.auto_channels_last and not self.channels_last and not self.training and source_image.is_cuda:
+            self.channels_last_()
         if self.scale_factor != 1:
             source_image = self.down(source_image)
         B, C, h, w = source_image.shape

@@ -138,6 +138,7 @@ class RaftFlow(nn.Module):
         self.to_context = nn.ModuleList(nn.Conv2d(widths[i], 192, 1, padding=0) for i in range(self.num_iter))
 
     channels_last = False
+    auto_channels_last = True      # inference on CUDA switches to NHWC memory on first use (values unchanged)
 
     def channels_last_(self, enable: bool = True):
         """Run the decoder in NHWC memory (torch.channels_last): the layout the sm_100 tensor-core
@@ -175,6 +176,8 @@ class RaftFlow(nn.Module):
         return q_d, k_s
 
     def forward(self, kp_s, kp_d, dense_motion, img, img_full):
+        if self.auto_channels_last and not self.channels_last and not self.training and img_full.is_cuda:
+            self.channels_last_()
         cl = self.channels_last
         if cl:
             img_full = img_full.contiguous(memory_format=torch.channels_last)

@@ -97,9 +97,11 @@ def test_channels_last_matches_nchw(golden):
     src, kp_s, kp_d, dense, small = _inputs(golden)
     with torch.no_grad():
         net = syn.fill_state_dict_(mrfa_b200.RaftFlow(**_rf_cfg())).to(DEV).eval()
+        net.auto_channels_last = False                    # first pass in the reference's NCHW memory
         dd = {k: v.to(DEV) for k, v in dense.items()}
         args = (kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), dd)
         out0, warp0, occ0 = net(*args, img=small.to(DEV), img_full=src.to(DEV))
+        assert not net.channels_last
         net.channels_last_()
         out1, warp1, occ1 = net(*args, img=small.to(DEV), img_full=src.to(DEV))
         # cuDNN may pick different (still fp32) algorithms per layout: allow conv round-off only
@@ -175,3 +177,55 @@ def test_cuda_graph_replay_is_bit_identical(golden):
             dense = dm(src.to(DEV), c(kd), c(ks))
             out, warp, occ = rf(ks["kp"].to(DEV), kd["kp"].to(DEV), dense, img=dm.down(src.to(DEV)), img_full=src.to(DEV))
             assert torch.equal(out_g, out) and torch.equal(warp_g, warp) and torch.equal(occ_g, occ)
+
+
+def test_full_size_vox1_vs_oracle():
+    """BASELINE.json configs[0]/[1] at their real size: unchanged vox1.yaml (full network widths),
+    one 256x256 pair, product on the GPU vs the CPU oracle with identical weights and inputs."""
+    import mrfa_b200
+    cfg = _cfg()
+    src, drv = syn.frame_pairs(1, 256, seed=6)
+    kp_s, kp_d = syn.keypoints(1, 10, seed=6)
+    with torch.no_grad():
+        o_dm = syn.fill_state_dict_(TP.DenseMotionOracle(**cfg["dense_motion"])).eval()
+        o_rf = syn.fill_state_dict_(TP.RaftFlowOracle(**cfg["raft_flow"])).eval()
+        dense = o_dm(src, kp_d, kp_s)
+        ref_out, ref_warp, ref_occ = o_rf(kp_s["kp"], kp_d["kp"], dense, img=o_dm.down(src), img_full=src)
+        dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).eval()
+        rf = mrfa_b200.RaftFlow(**cfg["raft_flow"]).eval()
+        dm.load_state_dict(o_dm.state_dict())
+        rf.load_state_dict(o_rf.state_dict())
+        dm, rf = dm.to(DEV), rf.to(DEV)
+        c = lambda d: {k: v.to(DEV) for k, v in d.items()}
+        got = dm(src.to(DEV), c(kp_d), c(kp_s))
+        np.testing.assert_allclose(got["deformation"].cpu().numpy(), dense["deformation"].numpy(), atol=2e-4)
+        out, warp_img, occ = rf(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), got, img=dm.down(src.to(DEV)), img_full=src.to(DEV))
+        assert rf.channels_last and dm.channels_last               # inference switched itself to NHWC
+        # The synthetic frames are white noise (0.5 intensity change per pixel), the harshest case for a
+        # warp: a 0.03 px flow difference from the bf16 volume already moves a pixel by 1.5e-2.  Bound
+        # the error in norm (2e-2 relative, the north_star tolerance) and against the dynamic range.
+        for name, a, b in (("out", out, ref_out), ("warp_img", warp_img, ref_warp), ("occlusion", occ, ref_occ)):
+            a, b = a.double().cpu(), b.double()
+            rel_l2 = float((a - b).norm() / b.norm())
+            max_abs = float((a - b).abs().max())
+            print(f"full-size {name}: rel-L2 {rel_l2:.3e}, max|err| {max_abs:.3e}, mean|err| {float((a - b).abs().mean()):.3e}, max|ref| {float(b.abs().max()):.3f}")
+            assert rel_l2 < 2e-2, (name, rel_l2)
+            assert max_abs < 2e-2 * (1.0 + float(b.abs().max())), (name, max_abs)
+
+
+def test_custom_op_schemas_and_fake_impls():
+    """torch.library.opcheck: schema + fake (meta) implementations agree with the CUDA kernels."""
+    from torch.library import opcheck
+    torch.manual_seed(20)
+    feat = torch.randn(2, 8, 6, 7, device=DEV)
+    grid = torch.rand(2, 5, 4, 2, device=DEV) * 2 - 1
+    tests = ("test_schema", "test_faketensor")
+    opcheck(torch.ops.mrfa.grid_sample.default, (feat, grid, 0, 0, False, 1), test_utils=tests)
+    opcheck(torch.ops.mrfa.grid_sample.default, (feat.contiguous(memory_format=torch.channels_last), grid, 2, 0, True, 1), test_utils=tests)
+    opcheck(torch.ops.mrfa.dual_warp.default, (feat, torch.randn(2, 2, 6, 7, device=DEV), torch.rand(2, 6, 7, 2, device=DEV)), test_utils=tests)
+    corr = torch.randn(2 * 9, 1, 8, 8, device=DEV)
+    opcheck(torch.ops.mrfa.corr_lookup.default, (corr, torch.ops.mrfa.avg_pool2x2(corr), torch.rand(2, 2, 3, 3, device=DEV) * 8, 8, 8, 9, 0, 3, False), test_utils=tests)
+    opcheck(torch.ops.mrfa.corr_pyramid.default, (torch.randn(1, 64, 16, 16, device=DEV), torch.randn(1, 64, 16, 16, device=DEV), 0.125), test_utils=tests)
+    opcheck(torch.ops.mrfa.kp2gaussian.default, (torch.rand(2, 10, 2, device=DEV), None, 8, 8, 0.1), test_utils=tests)
+    opcheck(torch.ops.mrfa.resize_bilinear.default, (feat, 12, 9, 1), test_utils=tests)
+    opcheck(torch.ops.mrfa.channel_affine.default, (feat, torch.rand(8, device=DEV), None, None, 1), test_utils=tests)
