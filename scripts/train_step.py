@@ -25,6 +25,8 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--nchw", action="store_true", help="keep NCHW memory (default: channels_last)")
+ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch.profiler)")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,6 +54,9 @@ class Refiner(torch.nn.Module):
 
 
 model = Refiner().to(dev).train()
+if not a.nchw:
+    model.dense_motion.channels_last_()
+    model.decoder.channels_last_()
 if world > 1:
     model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
@@ -85,6 +90,12 @@ torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if a.profile and rank == 0:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70), file=sys.stderr)
 if rank == 0:
     print(json.dumps({"workload": "vox1 training step (L1 loss, Adam), fwd+bwd", "pairs_per_gpu": a.batch, "n_gpus": world,
                       "ms_per_step": float(ms), "pairs_per_s": a.batch * world / float(ms) * 1e3, "loss": float(loss.detach()),
