@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 2
+#define MRFA_B200_ABI_VERSION 3
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -224,6 +224,17 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
  * x (N,C,H,W) -> y (N,C,Ho,Wo); NCHW or NHWC memory (any C; vectorised when C % 4 == 0).       */
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
+
+/* Flow / occlusion carry to the next, 2x finer refinement level (raft.py:276-295) as one pass:
+ *   d_f = 2*up(d_flow[:,0:2]);  flow = d_f + up(init_flow)/scale;  d_o = up(d_flow[:,2]);  occ = d_o + up(prior_occ)
+ *   if d_f_pre: up_f = 2*up(d_f_pre), up_o = up(d_occ_pre); flow += up_f; occ += up_o; d_f_acc = d_f + up_f; d_occ_acc = d_o + up_o
+ *   else d_f_acc = d_f, d_occ_acc = d_o.            up(.) = bilinear, align_corners=True, to (2R, 2R).
+ * d_flow (B,>=3,R,R) with element strides d_strides {sn, sy, sx, sc}; init_flow (B,2,h,h) and prior_occ (B,1,h,h)
+ * NCHW-contiguous; d_f_pre (B,2,R,R) / d_occ_pre (B,1,R,R) or both NULL.  Outputs flow, d_f_acc (B,2,2R,2R) and
+ * occ, d_occ_acc (B,1,2R,2R); `channels_last` gives the memory format of d_f_pre, flow and d_f_acc.            */
+int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_strides, const float* init_flow, const float* prior_occ,
+                    const float* d_f_pre, const float* d_occ_pre, float* flow, float* occ, float* d_f_acc,
+                    float* d_occ_acc, int B, int R, int h, float scale, int channels_last, mrfa_stream_t stream);
 
 /* F.avg_pool2d(x, (2,2)) of DownBlock2d (util.py:190-196) in NHWC memory: x (N,C,H,W) -> y (N,C,H/2,W/2),
  * C % 4 == 0, 16-byte aligned.                                                               */

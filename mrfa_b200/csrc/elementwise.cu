@@ -166,6 +166,75 @@ resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, 
 }
 
 
+// Flow / occlusion carry to the next (2x finer) level (raft.py:276-295).
+// The reference issues ~10 align_corners bilinear resizes of 1-2 channel maps plus as many
+// elementwise kernels per level; here one thread per fine pixel evaluates the whole update:
+//   d_f   = 2 * up(d_flow[:, 0:2])                 flow = d_f + up(init_flow) / scale
+//   d_o   = up(d_flow[:, 2:3])                     occ  = d_o + up(prior_occ)
+//   with a previous accumulated update (level > 0):
+//   up_f  = 2 * up(d_f_pre), up_o = up(d_occ_pre)  flow += up_f, occ += up_o,
+//   d_f_acc = d_f + up_f, d_occ_acc = d_o + up_o   (else d_f_acc = d_f, d_occ_acc = d_o)
+// Every product / sum is rounded separately, in the order of the reference expression.
+struct CarryTaps {
+  int y0, y1, x0, x1;
+  float ly, lx;
+};
+
+__device__ __forceinline__ float carry_interp(const float* __restrict__ p, int64_t sy, int64_t sx, const CarryTaps& t) {
+  const float hy = 1.f - t.ly, hx = 1.f - t.lx;
+  return hy * (hx * __ldg(p + t.y0 * sy + t.x0 * sx) + t.lx * __ldg(p + t.y0 * sy + t.x1 * sx)) +
+         t.ly * (hx * __ldg(p + t.y1 * sy + t.x0 * sx) + t.lx * __ldg(p + t.y1 * sy + t.x1 * sx));
+}
+
+__global__ void __launch_bounds__(256)
+flow_carry_kernel(const float* __restrict__ d_flow, mrfa_grid_strides_t ds, const float* __restrict__ init_flow,
+                  const float* __restrict__ prior_occ, const float* __restrict__ d_f_pre,
+                  const float* __restrict__ d_occ_pre, float* __restrict__ flow, float* __restrict__ occ,
+                  float* __restrict__ d_f_acc, float* __restrict__ d_occ_acc, int R, int h, float scale, int cl,
+                  float s_r, float s_h, int64_t total) {
+  const int Ro = 2 * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Ro);
+    const int oy = (int)((i / Ro) % Ro);
+    const int64_t n = i / ((int64_t)Ro * Ro);
+    CarryTaps tr, th;
+    resize_axis(oy, s_r, R, tr.y0, tr.y1, tr.ly);
+    resize_axis(ox, s_r, R, tr.x0, tr.x1, tr.lx);
+    resize_axis(oy, s_h, h, th.y0, th.y1, th.ly);
+    resize_axis(ox, s_h, h, th.x0, th.x1, th.lx);
+    const float* df = d_flow + n * ds.sn;
+    const float dfx = __fmul_rn(carry_interp(df, ds.sy, ds.sx, tr), 2.f);
+    const float dfy = __fmul_rn(carry_interp(df + ds.sc, ds.sy, ds.sx, tr), 2.f);
+    const float dov = carry_interp(df + 2 * ds.sc, ds.sy, ds.sx, tr);
+    const float* fi = init_flow + n * 2 * h * h;
+    float fx = __fadd_rn(dfx, __fdiv_rn(carry_interp(fi, h, 1, th), scale));
+    float fy = __fadd_rn(dfy, __fdiv_rn(carry_interp(fi + (int64_t)h * h, h, 1, th), scale));
+    float oc = __fadd_rn(dov, carry_interp(prior_occ + n * h * h, h, 1, th));
+    float ax = dfx, ay = dfy, ao = dov;
+    if (d_f_pre != nullptr) {
+      // the accumulated update of the previous level lives at R x R in the caller's memory format
+      const float* pp = d_f_pre + n * 2 * R * R;
+      const int64_t psy = cl ? 2 * R : R, psx = cl ? 2 : 1, psc = cl ? 1 : (int64_t)R * R;
+      const float ux = __fmul_rn(carry_interp(pp, psy, psx, tr), 2.f);
+      const float uy = __fmul_rn(carry_interp(pp + psc, psy, psx, tr), 2.f);
+      const float uo = carry_interp(d_occ_pre + n * R * R, R, 1, tr);
+      fx = __fadd_rn(fx, ux); fy = __fadd_rn(fy, uy); oc = __fadd_rn(oc, uo);
+      ax = __fadd_rn(dfx, ux); ay = __fadd_rn(dfy, uy); ao = __fadd_rn(dov, uo);
+    }
+    const int64_t pix = (int64_t)oy * Ro + ox, plane = (int64_t)Ro * Ro;
+    if (cl) {
+      *reinterpret_cast<float2*>(flow + (n * plane + pix) * 2) = make_float2(fx, fy);
+      *reinterpret_cast<float2*>(d_f_acc + (n * plane + pix) * 2) = make_float2(ax, ay);
+    } else {
+      flow[n * 2 * plane + pix] = fx; flow[n * 2 * plane + plane + pix] = fy;
+      d_f_acc[n * 2 * plane + pix] = ax; d_f_acc[n * 2 * plane + plane + pix] = ay;
+    }
+    occ[n * plane + pix] = oc;
+    d_occ_acc[n * plane + pix] = ao;
+  }
+}
+
+
 // AntiAliasInterpolation2d (util.py:282-326): zero-padded depthwise
 // KxK Gaussian followed by nearest sub-sampling by `stride`.  The reference convolves at full
 // resolution and throws 15/16 of the result away; this evaluates only the kept pixels.
@@ -343,5 +412,25 @@ extern "C" int mrfa_avg_pool2x2_nhwc(const float* x, float* y, int N, int C, int
   if (N == 0) return 0;
   const int64_t n4 = (int64_t)N * (H / 2) * (W / 2) * C / 4;
   avg_pool2x2_nhwc_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, H, W, n4);
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_strides, const float* init_flow,
+                               const float* prior_occ, const float* d_f_pre, const float* d_occ_pre, float* flow,
+                               float* occ, float* d_f_acc, float* d_occ_acc, int B, int R, int h, float scale,
+                               int channels_last, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(d_flow && init_flow && prior_occ && flow && occ && d_f_acc && d_occ_acc);
+  MRFA_CHECK_ARG((d_f_pre == nullptr) == (d_occ_pre == nullptr));
+  MRFA_CHECK_ARG(B >= 0 && R > 0 && h > 0 && scale != 0.f);
+  if (B == 0) return 0;
+  if (channels_last && ((reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(d_f_acc)) & 7) != 0)
+    return MRFA_E_ALIGN;
+  const int Ro = 2 * R;
+  const float s_r = (float)(R - 1) / (float)(Ro - 1);
+  const float s_h = (float)(h - 1) / (float)(Ro - 1);
+  const int64_t total = (int64_t)B * Ro * Ro;
+  flow_carry_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(d_flow, d_strides, init_flow, prior_occ, d_f_pre,
+                                                                         d_occ_pre, flow, occ, d_f_acc, d_occ_acc, R, h,
+                                                                         scale, channels_last, s_r, s_h, total);
   return MRFA_LAUNCH_RESULT();
 }

@@ -75,24 +75,49 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   }
   __syncthreads();
 
-  // ---- phase 1: warp per query, gather both footprints ------------------------------------
-  for (int qi = warp; qi < kQPB; qi += kLookupThreads / 32) {
-    const int q = q0 + qi;
-    if (q >= Q) break;
-    const int64_t map = (int64_t)b * map_batch_stride + row_offset + q;
+  // ---- phase 1: warp per query, gather both footprints.  kGroup queries are gathered per
+  //      round so every lane has 2*kGroup*ceil(FF/32) independent loads in flight before the
+  //      first shared-memory store: the gather is latency-bound (each 2/4-byte load pulls its
+  //      own 32-byte sector), so bytes in flight per SM set the achieved bandwidth. ----
+  constexpr int kWarps = kLookupThreads / 32;
+  constexpr int kPerWarp = kQPB / kWarps;
+  constexpr int kGroup = 4;
+  constexpr int kIter = (FF + 31) / 32;
+  static_assert(kPerWarp % kGroup == 0, "query grouping");
+#pragma unroll 1
+  for (int g0 = 0; g0 < kPerWarp; g0 += kGroup) {
+    float v[kGroup][2][kIter];
 #pragma unroll
-    for (int lvl = 0; lvl < 2; ++lvl) {
-      const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
-      const int gx0 = org[qi][2 * lvl], gy0 = org[qi][2 * lvl + 1];
-      const T* base = (lvl ? level1 : level0) + map * ((int64_t)Hl * Wl);
+    for (int g = 0; g < kGroup; ++g) {
+      const int qi = warp + (g0 + g) * kWarps;
+      const bool live = q0 + qi < Q;
+      const int64_t map = (int64_t)b * map_batch_stride + row_offset + q0 + qi;
 #pragma unroll
-      for (int e = lane; e < FF; e += 32) {
-        const int fy_ = e / F, fx_ = e - fy_ * F;
-        const int yy = gy0 + fy_, xx = gx0 + fx_;
-        float v = 0.f;
-        if (yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) v = ld_elem<T>(base + (int64_t)yy * Wl + xx);
-        foot[qi * kStride + lvl * FF + e] = v;
+      for (int lvl = 0; lvl < 2; ++lvl) {
+        const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
+        const int gx0 = org[qi][2 * lvl], gy0 = org[qi][2 * lvl + 1];
+        const T* base = (lvl ? level1 : level0) + map * ((int64_t)Hl * Wl);
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+          const int e = lane + 32 * it;
+          const int fy_ = e / F, fx_ = e - fy_ * F;
+          const int yy = gy0 + fy_, xx = gx0 + fx_;
+          float t = 0.f;
+          if (live && e < FF && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) t = ld_elem<T>(base + yy * Wl + xx);
+          v[g][lvl][it] = t;
+        }
       }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) {
+      const int qi = warp + (g0 + g) * kWarps;
+#pragma unroll
+      for (int lvl = 0; lvl < 2; ++lvl)
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+          const int e = lane + 32 * it;
+          if (e < FF) foot[qi * kStride + lvl * FF + e] = v[g][lvl][it];
+        }
     }
   }
   __syncthreads();

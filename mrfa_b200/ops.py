@@ -654,6 +654,55 @@ def _(x, Ho, Wo, act):
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
 
 
+@torch.library.custom_op("mrfa::flow_carry", mutates_args=(), device_types="cuda")
+def flow_carry(d_flow: Tensor, init_flow: Tensor, prior_occ: Tensor, d_f_pre: Optional[Tensor],
+               d_occ_pre: Optional[Tensor], scale: float, channels_last: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """raft.py:276-295 as one kernel: (flow, occlusion, d_f_acc, d_occ_acc) at twice the resolution of
+    `d_flow` (B,3,R,R: flow update ++ occlusion update, any strides).  See include/mrfa_b200.h."""
+    for t, name in ((d_flow, "d_flow"), (init_flow, "init_flow"), (prior_occ, "prior_occ")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+            raise RuntimeError(f"mrfa_b200: flow_carry `{name}` must be a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    B, Cd, R, R2 = d_flow.shape
+    if Cd < 3 or R != R2 or init_flow.shape[1] != 2 or prior_occ.shape[1] != 1 or init_flow.shape[2] != init_flow.shape[3] \
+            or tuple(prior_occ.shape[2:]) != tuple(init_flow.shape[2:]):
+        raise RuntimeError("mrfa_b200: flow_carry shape mismatch")
+    if (d_f_pre is None) != (d_occ_pre is None):
+        raise RuntimeError("mrfa_b200: flow_carry needs both or neither of d_f_pre / d_occ_pre")
+    h = init_flow.shape[2]
+    init_flow, prior_occ = init_flow.contiguous(), prior_occ.contiguous()
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    if d_f_pre is not None:
+        if tuple(d_f_pre.shape) != (B, 2, R, R) or tuple(d_occ_pre.shape) != (B, 1, R, R):
+            raise RuntimeError("mrfa_b200: flow_carry previous-update shape mismatch")
+        if not d_f_pre.is_cuda or d_f_pre.dtype != torch.float32:
+            raise RuntimeError("mrfa_b200: flow_carry `d_f_pre` must be a float32 CUDA tensor (there is no CPU fallback)")
+        d_f_pre, d_occ_pre = d_f_pre.contiguous(memory_format=fmt), _req(d_occ_pre, "d_occ_pre")
+    dev = d_flow.device
+    flow, d_f_acc = _empty_image((B, 2, 2 * R, 2 * R), dev, channels_last), _empty_image((B, 2, 2 * R, 2 * R), dev, channels_last)
+    occ = torch.empty((B, 1, 2 * R, 2 * R), device=dev, dtype=torch.float32)
+    d_occ_acc = torch.empty_like(occ)
+    if flow.numel() == 0:
+        return flow, occ, d_f_acc, d_occ_acc
+    st = d_flow.stride()
+    with torch.cuda.device(dev):
+        with _timed("flow_carry", 4 * 6 * flow.numel() // 2):
+            check(lib.mrfa_flow_carry(_p(d_flow), GridStrides(st[0], st[2], st[3], st[1]), _p(init_flow), _p(prior_occ),
+                                      _p(d_f_pre) if d_f_pre is not None else None,
+                                      _p(d_occ_pre) if d_occ_pre is not None else None,
+                                      _p(flow), _p(occ), _p(d_f_acc), _p(d_occ_acc), B, R, h, float(scale),
+                                      int(channels_last), _stream()), "mrfa_flow_carry")
+    return flow, occ, d_f_acc, d_occ_acc
+
+
+@flow_carry.register_fake
+def _(d_flow, init_flow, prior_occ, d_f_pre, d_occ_pre, scale, channels_last):
+    B, _, R, _ = d_flow.shape
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    f = d_flow.new_empty((B, 2, 2 * R, 2 * R)).contiguous(memory_format=fmt)
+    o = d_flow.new_empty((B, 1, 2 * R, 2 * R))
+    return f, o, torch.empty_like(f), torch.empty_like(o)
+
+
 @torch.library.custom_op("mrfa::antialias_down", mutates_args=(), device_types="cuda")
 def antialias_down(x: Tensor, weight: Tensor, ka: int, stride: int) -> Tensor:
     """AntiAliasInterpolation2d for scale 1/stride, computing only the kept pixels (NCHW)."""

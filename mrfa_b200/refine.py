@@ -6,6 +6,7 @@ signature, return values and state_dict keys as the reference class.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -14,6 +15,9 @@ from torch import nn
 from . import sampling
 from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_path
 from .corr import CorrPyramid
+
+
+FUSED_CARRY = os.environ.get("MRFA_FUSED_CARRY", "1") != "0"     # A/B switch for the fused level hand-over
 
 
 def _resize(x, size):
@@ -244,6 +248,11 @@ class RaftFlow(nn.Module):
             if i < self.num_iter - 1:
                 R2 = 2 * R
                 scale = 2 ** (base - i) / 2.0
+                if flow.is_cuda and not torch.is_grad_enabled() and FUSED_CARRY:
+                    # the whole update below as one kernel
+                    flow, occlusion, d_f_pre, d_occ_pre = torch.ops.mrfa.flow_carry(
+                        d_flow, init_flow, prior_occ, d_f_pre, d_occ_pre, scale, bool(cl))
+                    continue
                 d_f = _resize(d_flow[:, 0:2], (R2, R2)) * 2
                 flow = d_f + _resize(init_flow, (R2, R2)) / scale
                 d_o = _resize(d_occ, (R2, R2))

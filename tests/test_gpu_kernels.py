@@ -547,6 +547,41 @@ def test_resize_bilinear(cl):
     close(out, F.interpolate(flow.cpu().contiguous(), size=(18, 18), mode="bilinear", align_corners=True), 2e-6)
 
 
+@pytest.mark.parametrize("cl", [False, True])
+def test_flow_carry_matches_reference_chain(cl):
+    """raft.py:276-295 (the per-level flow / occlusion hand-over) as one kernel vs the torch op chain on CPU."""
+    torch.manual_seed(21)
+    B, h = 2, 16
+    init_flow = torch.randn(B, 2, h, h) * 3
+    prior_occ = torch.randn(B, 1, h, h)
+    up = lambda t, R: F.interpolate(t, size=(R, R), mode="bilinear", align_corners=True)
+    d_f_pre = d_occ_pre = g_pre = go_pre = None
+    for i, R in enumerate((2, 4, 8, 16, 32)):
+        d4 = torch.randn(B, 4, R, R)                                   # merged conv2|convo2 output: [fx, fy, occ, 0]
+        scale = 2 ** (3 - i) / 2.0
+        d_f = up(d4[:, 0:2], 2 * R) * 2
+        flow = d_f + up(init_flow, 2 * R) / scale
+        d_o = up(d4[:, 2:3], 2 * R)
+        occ = d_o + up(prior_occ, 2 * R)
+        if i == 0:
+            d_f_pre, d_occ_pre = d_f, d_o
+        else:
+            up_f, up_o = up(d_f_pre, 2 * R) * 2, up(d_occ_pre, 2 * R)
+            flow, occ = flow + up_f, occ + up_o
+            d_f_pre, d_occ_pre = d_f + up_f, d_o + up_o
+        g4 = d4.to(DEV)
+        if cl:
+            g4 = g4.contiguous(memory_format=torch.channels_last)
+        got = torch.ops.mrfa.flow_carry(g4[:, :3], init_flow.to(DEV), prior_occ.to(DEV), g_pre, go_pre, scale, cl)
+        assert got[0].shape == (B, 2, 2 * R, 2 * R) and got[1].shape == (B, 1, 2 * R, 2 * R)
+        assert got[0].is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+        for a, b in zip(got, (flow, occ, d_f_pre, d_occ_pre)):
+            close(a, b, 1e-5, 1e-5)
+        g_pre, go_pre = got[2], got[3]
+    with pytest.raises(Exception):
+        torch.ops.mrfa.flow_carry(torch.zeros(1, 3, 4, 4), init_flow.to(DEV), prior_occ.to(DEV), None, None, 1.0, False)
+
+
 def test_antialias_down_matches_reference_order():
     from mrfa_b200 import blocks
     torch.manual_seed(14)
