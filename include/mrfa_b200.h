@@ -225,6 +225,15 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* Random affine + thin-plate warp of the identity grid -- the training-only equivariance warps.
+ * metric MRFA_TPS_L1   : Transform.warp_coordinates model.py:50-70 (d = |dx|+|dy|, U = d^2 log(d + 1e-6));
+ * metric MRFA_TPS_L2SQ : TPS mode 'random' util.py:412-423 (r2 = dx^2+dy^2, U = r2 log(r2 + 1e-9)).
+ * theta (B,2,3); control_points (P,2) and control_params (B,P), or control_params NULL for the affine-only
+ * Transform; grid (B,h,w,2) receives theta . p + sum_k U_k * params[b,k] (the same term on x and y).     */
+enum { MRFA_TPS_L1 = 0, MRFA_TPS_L2SQ = 1 };
+int mrfa_random_warp_grid(const float* theta, const float* control_points, const float* control_params, float* grid,
+                          int B, int P, int h, int w, int metric, mrfa_stream_t stream);
+
 /* Flow / occlusion carry to the next, 2x finer refinement level (raft.py:276-295) as one pass:
  *   d_f = 2*up(d_flow[:,0:2]);  flow = d_f + up(init_flow)/scale;  d_o = up(d_flow[:,2]);  occ = d_o + up(prior_occ)
  *   if d_f_pre: up_f = 2*up(d_f_pre), up_o = up(d_occ_pre); flow += up_f; occ += up_o; d_f_acc = d_f + up_f; d_occ_acc = d_o + up_o

@@ -12,6 +12,7 @@ from .refine import BasicMotionEncoder, RaftFlow, RefineFlow
 from .sampling import (TPS, batch_bilinear_sampler, bilinear_sampler, coords_grid, deform_input, from_homogeneous,
                        grid_sample, kp2gaussian, make_coordinate_grid, to_homogeneous, warp_by_flow)
 from .blocks import AntiAliasInterpolation2d, Hourglass, OcclusionAwareGenerator
+from .equivariance import Transform
 from .graphs import GraphedRefiner
 from .patch import patch_reference
 
@@ -19,5 +20,5 @@ __all__ = [
     "CorrBlock", "CorrPyramid", "DenseMotionNetwork", "TPSDenseMotionNetwork", "RaftFlow", "BasicMotionEncoder",
     "RefineFlow", "TPS", "batch_bilinear_sampler", "bilinear_sampler", "coords_grid", "deform_input",
     "from_homogeneous", "to_homogeneous", "grid_sample", "kp2gaussian", "make_coordinate_grid", "warp_by_flow",
-    "AntiAliasInterpolation2d", "Hourglass", "OcclusionAwareGenerator", "patch_reference", "GraphedRefiner",
+    "AntiAliasInterpolation2d", "Hourglass", "OcclusionAwareGenerator", "patch_reference", "GraphedRefiner", "Transform",
 ]

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 ABI_VERSION = 3
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
+TPS_L1, TPS_L2SQ = 0, 1
 
 
 class GridStrides(ctypes.Structure):
@@ -48,6 +49,7 @@ SIGNATURES = {
     "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_antialias_down": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "mrfa_random_warp_grid": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_flow_carry": (c_int, [c_void_p, GridStrides] + [c_void_p] * 8 + [c_int] * 3 + [c_float, c_int, c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4

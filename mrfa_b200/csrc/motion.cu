@@ -220,6 +220,53 @@ tps_motion_prior_kernel(const float* __restrict__ kp_d, const float* __restrict_
   sample_source<MRFA_COORD_NORM_ACT>(source + (int64_t)b * C * hw, dst, C, h, w, m, r);
 }
 
+// Random affine + thin-plate warp of the identity grid: the equivariance branch of training
+// (SURVEY.md 8(f) N4).  metric 0 = Transform.warp_coordinates (model.py:50-70): d = |dx| + |dy|,
+// U = d^2 * log(d + 1e-6);  metric 1 = TPS mode 'random' (util.py:412-423): r2 = dx^2 + dy^2,
+// U = r2 * log(r2 + 1e-9).  The reference materialises (B, HW, P, 2) temporaries; here one
+// thread per grid point walks the P control points held in shared memory.
+constexpr int kMaxCtrl = 256;
+
+__global__ void __launch_bounds__(256)
+random_warp_grid_kernel(const float* __restrict__ theta, const float* __restrict__ control_points,
+                        const float* __restrict__ control_params, float* __restrict__ grid, int P, int h, int w,
+                        int metric) {
+  __shared__ float2 cp[kMaxCtrl];
+  __shared__ float cw[kMaxCtrl];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < P; k += blockDim.x) {
+    cp[k] = make_float2(__ldg(control_points + 2 * k), __ldg(control_points + 2 * k + 1));
+    cw[k] = control_params ? __ldg(control_params + (int64_t)b * P + k) : 0.f;
+  }
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h * w) return;
+  const int y = r / w, x = r - y * w;
+  const float gx = norm_coord(x, w), gy = norm_coord(y, h);
+  const float* th = theta + (int64_t)b * 6;
+  float ox = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(th + 0), gx), __fmul_rn(__ldg(th + 1), gy)), __ldg(th + 2));
+  float oy = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(th + 3), gx), __fmul_rn(__ldg(th + 4), gy)), __ldg(th + 5));
+  if (control_params != nullptr) {
+    float acc = 0.f;
+    for (int k = 0; k < P; ++k) {
+      const float dx = __fsub_rn(gx, cp[k].x), dy = __fsub_rn(gy, cp[k].y);
+      float u;
+      if (metric == 0) {
+        const float d = __fadd_rn(fabsf(dx), fabsf(dy));
+        u = __fmul_rn(__fmul_rn(d, d), logf(__fadd_rn(d, 1e-6f)));
+      } else {
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        u = __fmul_rn(d2, logf(__fadd_rn(d2, 1e-9f)));
+      }
+      acc = __fadd_rn(acc, __fmul_rn(u, cw[k]));
+    }
+    ox = __fadd_rn(ox, acc);
+    oy = __fadd_rn(oy, acc);
+  }
+  reinterpret_cast<float2*>(grid)[(int64_t)b * h * w + r] = make_float2(ox, oy);
+}
+
+
 }  // namespace mrfa
 
 using namespace mrfa;
@@ -261,5 +308,17 @@ extern "C" int mrfa_tps_motion_prior(const float* kp_d, const float* kp_s, const
   const int64_t t2 = (int64_t)B * (G + 1) * h * w;
   tps_motion_prior_kernel<<<(unsigned)cdiv64(t2, 256), 256, 0, as_stream(stream)>>>(
       kp_d, theta, control_params, bg_param, source, motions, hg_input, B, G, C, chan_total, KP + 1, h, w);
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_random_warp_grid(const float* theta, const float* control_points, const float* control_params,
+                                     float* grid, int B, int P, int h, int w, int metric, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(theta && grid && B >= 0 && h > 0 && w > 0 && (metric == 0 || metric == 1));
+  MRFA_CHECK_ARG(control_params == nullptr || (control_points != nullptr && P > 0));
+  MRFA_CHECK_SHAPE(P <= kMaxCtrl && B <= 65535);
+  if (B == 0) return 0;
+  dim3 g((unsigned)cdiv64((int64_t)h * w, 256), (unsigned)B);
+  random_warp_grid_kernel<<<g, 256, 0, as_stream(stream)>>>(theta, control_points, control_params, grid,
+                                                            control_params ? P : 0, h, w, metric);
   return MRFA_LAUNCH_RESULT();
 }

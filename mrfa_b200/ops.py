@@ -654,6 +654,36 @@ def _(x, Ho, Wo, act):
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
 
 
+@torch.library.custom_op("mrfa::random_warp_grid", mutates_args=(), device_types="cuda")
+def random_warp_grid(theta: Tensor, control_points: Optional[Tensor], control_params: Optional[Tensor], h: int, w: int,
+                     metric: int) -> Tensor:
+    """Grid (B,h,w,2) of the random affine + TPS equivariance warp (model.py:44-70 metric 0; util.py TPS 'random' 1)."""
+    theta = _req(theta, "theta")
+    B = theta.shape[0]
+    if tuple(theta.shape) != (B, 2, 3):
+        raise RuntimeError("mrfa_b200: random_warp_grid expects theta of shape (B,2,3)")
+    P = 0
+    if control_params is not None:
+        control_points = _req(control_points, "control_points").reshape(-1, 2)
+        control_params = _req(control_params, "control_params").reshape(B, -1)
+        P = control_points.shape[0]
+        if control_params.shape[1] != P:
+            raise RuntimeError("mrfa_b200: random_warp_grid control_params / control_points mismatch")
+    grid = torch.empty((B, h, w, 2), device=theta.device, dtype=torch.float32)
+    if grid.numel() == 0:
+        return grid
+    with torch.cuda.device(theta.device):
+        with _timed("random_warp_grid", 4 * grid.numel()):
+            check(lib.mrfa_random_warp_grid(_p(theta), _p(control_points) if P else None, _p(control_params) if P else None,
+                                            _p(grid), B, P, h, w, metric, _stream()), "mrfa_random_warp_grid")
+    return grid
+
+
+@random_warp_grid.register_fake
+def _(theta, control_points, control_params, h, w, metric):
+    return theta.new_empty((theta.shape[0], h, w, 2))
+
+
 @torch.library.custom_op("mrfa::flow_carry", mutates_args=(), device_types="cuda")
 def flow_carry(d_flow: Tensor, init_flow: Tensor, prior_occ: Tensor, d_f_pre: Optional[Tensor],
                d_occ_pre: Optional[Tensor], scale: float, channels_last: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

@@ -11,7 +11,7 @@ import importlib
 
 
 def patch_reference(modules_pkg: str = "modules"):
-    from . import corr, prior_motion, refine, sampling
+    from . import corr, equivariance, prior_motion, refine, sampling
 
     util = importlib.import_module(modules_pkg + ".util")
     raft = importlib.import_module(modules_pkg + ".raft")
@@ -34,6 +34,7 @@ def patch_reference(modules_pkg: str = "modules"):
         model.RaftFlow = refine.RaftFlow
         model.DenseMotionNetwork = prior_motion.DenseMotionNetwork
         model.TPSDenseMotionNetwork = prior_motion.TPSDenseMotionNetwork
+        model.Transform = equivariance.Transform
     except Exception:                      # model.py needs torchvision weights / .cuda(); optional
         pass
     return {"util": util, "raft": raft, "dense_motion": dense}

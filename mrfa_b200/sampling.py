@@ -130,6 +130,10 @@ class TPS:
 
     def transform_frame(self, frame):
         h, w = frame.shape[2:]
+        if self.mode == "random":            # one kernel instead of the (B, HW, P, 2) temporaries
+            dev = frame.device
+            return torch.ops.mrfa.random_warp_grid(self.theta.to(dev, torch.float32), self.control_points.to(dev, torch.float32),
+                                                   self.control_params.to(dev, torch.float32), h, w, _lib.TPS_L2SQ)
         grid = ops.make_coordinate_grid_cuda(h, w, frame.device).view(1, h * w, 2)
         shape = [self.bs, h, w, 2]
         if self.mode == "kp":

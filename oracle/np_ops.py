@@ -367,6 +367,40 @@ def tps_transformations(kp_d, kp_s, h, w, bg_param=None) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# training-only random warps (equivariance branch)
+# --------------------------------------------------------------------------------------
+def random_warp_coordinates(theta, control_points, control_params, coords, metric: str = "l1") -> np.ndarray:
+    """Transform.warp_coordinates model.py:50-70 (metric 'l1': d = |dx|+|dy|, U = d^2 log(d+1e-6)) and
+    TPS.warp_coordinates mode 'random' util.py:412-423 ('l2sq': r2 = dx^2+dy^2, U = r2 log(r2+1e-9)).
+    theta (B,2,3), control_points (P,2), control_params (B,P) or None, coords (B|1,M,2) -> (B,M,2)."""
+    theta = theta.astype(F32)
+    c = np.broadcast_to(coords.astype(F32), (theta.shape[0],) + coords.shape[1:])
+    out = (theta[:, None, :, 0] * c[..., 0:1] + theta[:, None, :, 1] * c[..., 1:2]).astype(F32) + theta[:, None, :, 2]
+    if control_params is not None:
+        d = c[:, :, None, :] - control_points.astype(F32).reshape(1, 1, -1, 2)
+        if metric == "l1":
+            r = np.abs(d).sum(-1, dtype=F32)
+            U = (r * r).astype(F32) * np.log(r + F32(1e-6)).astype(F32)
+        else:
+            r = (d * d).sum(-1, dtype=F32)
+            U = r * np.log(r + F32(1e-9)).astype(F32)
+        out = out + (U.astype(F32) * control_params.astype(F32).reshape(theta.shape[0], 1, -1)).sum(-1, dtype=F32)[..., None]
+    return out.astype(F32)
+
+
+def random_warp_grid(theta, control_points, control_params, h: int, w: int, metric: str = "l1") -> np.ndarray:
+    """Transform.transform_frame's grid (model.py:44-47) / TPS.transform_frame mode 'random' (util.py:387-395)."""
+    grid = make_coordinate_grid(h, w).reshape(1, h * w, 2)
+    return random_warp_coordinates(theta, control_points, control_params, grid, metric).reshape(-1, h, w, 2)
+
+
+def transform_frame(frame, theta, control_points, control_params) -> np.ndarray:
+    """Transform.transform_frame model.py:44-48: reflection-padded grid_sample (align_corners=False)."""
+    g = random_warp_grid(theta, control_points, control_params, frame.shape[2], frame.shape[3], "l1")
+    return grid_sample(frame, g, align_corners=False, padding_mode="reflection")
+
+
+# --------------------------------------------------------------------------------------
 # prior -> flow conversion
 # --------------------------------------------------------------------------------------
 def init_flow_from_prior(deformation: np.ndarray, h: int) -> np.ndarray:

@@ -174,5 +174,44 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
+def equivariance():
+    """Training-only random warps: model.py:26-77 `Transform` and util.py TPS mode 'random'.
+    Written to its own file so the other fixtures stay byte-identical:  python make_golden.py equivariance"""
+    from mrfa_b200 import synthetic as syn
+    util, _, _ = import_reference()
+    from modules.model import Transform
+    T = syn.tensor
+    e = {}
+    params = {"sigma_affine": 0.05, "sigma_tps": 0.005, "points_tps": 5}          # config/vox1.yaml transform_params
+    frame = T("eq.frame", (2, 3, 32, 40), "uniform")
+    kp = T("eq.kp", (2, 10, 2), "uniform", 1.6, -0.8)
+    e["frame"], e["kp"] = npy(frame), npy(kp)
+    torch.manual_seed(7)
+    tr = Transform(2, **params)
+    e["theta"], e["control_points"], e["control_params"] = npy(tr.theta), npy(tr.control_points), npy(tr.control_params)
+    with torch.no_grad():
+        e["transform_frame"] = npy(tr.transform_frame(frame))
+        e["warp_kp"] = npy(tr.warp_coordinates(kp))
+    kpg = kp.clone().requires_grad_(True)
+    e["jacobian_kp"] = npy(tr.jacobian(kpg))
+    torch.manual_seed(7)
+    aff = Transform(2, sigma_affine=0.05)                                            # affine-only branch (tps False)
+    with torch.no_grad():
+        e["affine_theta"] = npy(aff.theta)
+        e["affine_transform_frame"] = npy(aff.transform_frame(frame))
+    torch.manual_seed(7)
+    tps = util.TPS("random", 2, **params)
+    with torch.no_grad():
+        e["tps_random_theta"], e["tps_random_params"] = npy(tps.theta), npy(tps.control_params)
+        e["tps_random_grid"] = npy(tps.transform_frame(frame))
+        e["tps_random_warp_kp"] = npy(tps.warp_coordinates(kp))
+    np.savez_compressed(os.path.join(HERE, "equivariance.npz"), **e)
+    print("equivariance.npz", os.path.getsize(os.path.join(HERE, "equivariance.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["equivariance"]:
+        equivariance()
+    else:
+        main()
+        equivariance()

@@ -605,3 +605,41 @@ def test_avg_pool2x2_nhwc():
     out = torch.ops.mrfa.avg_pool2x2_nhwc(x)
     assert out.is_contiguous(memory_format=torch.channels_last)
     close(out, F.avg_pool2d(x.cpu().contiguous(), (2, 2)), 1e-6)
+
+
+def test_equivariance_transform_matches_reference_golden(golden):
+    """model.py:26-77 Transform (reflection-padded random affine + TPS warp, its key-point warp and Jacobian) and
+    util.py TPS mode 'random', against vectors produced by the reference (tests/golden/make_golden.py equivariance)."""
+    m = mb()
+    e = golden("equivariance")
+    params = {"sigma_affine": 0.05, "sigma_tps": 0.005, "points_tps": 5}
+    frame = torch.from_numpy(e["frame"]).to(DEV)
+    kp = torch.from_numpy(e["kp"]).to(DEV)
+    torch.manual_seed(7)
+    tr = m.Transform(2, **params)
+    np.testing.assert_array_equal(tr.theta.numpy(), e["theta"])                     # same RNG draws as the reference
+    np.testing.assert_array_equal(tr.control_params.numpy(), e["control_params"])
+    np.testing.assert_array_equal(tr.control_points.numpy(), e["control_points"])
+    close(tr.transform_frame(frame), e["transform_frame"], 1e-5)
+    close(tr.warp_coordinates(kp), e["warp_kp"], 1e-6)
+    kpg = kp.clone().requires_grad_(True)
+    close(tr.jacobian(kpg), e["jacobian_kp"], 1e-5)
+    torch.manual_seed(7)
+    aff = m.Transform(2, sigma_affine=0.05)
+    close(aff.transform_frame(frame), e["affine_transform_frame"], 1e-5)
+    torch.manual_seed(7)
+    tps = m.TPS("random", 2, **params)
+    close(tps.transform_frame(frame), e["tps_random_grid"], 2e-6)
+    close(tps.warp_coordinates(kp), e["tps_random_warp_kp"], 1e-6)
+    # the oracle agrees with the kernel at a size the fixtures do not cover, and the warp is differentiable
+    cp, cw = e["control_points"].reshape(-1, 2), e["control_params"].reshape(2, -1)
+    grid = torch.ops.mrfa.random_warp_grid(cu(e["theta"]), cu(cp), cu(cw), 96, 128, 0)
+    close(grid, O.random_warp_grid(e["theta"], cp, cw, 96, 128, "l1"), 1e-6)
+    # (a smooth frame: on white noise a 1-ulp grid difference times W/2 pixels already reaches 1e-5)
+    big = F.interpolate(torch.rand(2, 3, 12, 16, device=DEV), size=(96, 128), mode="bilinear").requires_grad_(True)
+    out = tr.transform_frame(big)
+    close(out, O.transform_frame(big.detach().cpu().numpy(), e["theta"], cp, cw), 1e-5)
+    out.sum().backward()
+    assert big.grad is not None and torch.isfinite(big.grad).all() and float(big.grad.abs().sum()) > 0
+    with pytest.raises(RuntimeError):
+        tr.transform_frame(torch.zeros(2, 3, 8, 8))

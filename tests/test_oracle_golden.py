@@ -174,3 +174,19 @@ def test_raft_flow_forward(golden, prior_inputs):
         close(out.numpy(), r["prior_only_out"], 5e-5)
         close(warp_img.numpy(), r["prior_only_warp_img"], 5e-5)
         close(occ.numpy(), r["prior_only_occlusion"], 5e-5)
+
+
+def test_equivariance_warps_match_reference(golden):
+    """model.py:26-77 Transform and util.py TPS mode 'random' (SURVEY.md 8(f) N4)."""
+    e = golden("equivariance")
+    cp = e["control_points"].reshape(-1, 2)
+    par = e["control_params"].reshape(2, -1)
+    out = O.transform_frame(e["frame"], e["theta"], cp, par)
+    np.testing.assert_allclose(out, e["transform_frame"], atol=1e-5)
+    np.testing.assert_allclose(O.transform_frame(e["frame"], e["affine_theta"], cp, None), e["affine_transform_frame"], atol=1e-5)
+    np.testing.assert_allclose(O.random_warp_coordinates(e["theta"], cp, par, e["kp"], "l1"), e["warp_kp"], atol=1e-6)
+    h, w = e["frame"].shape[2:]
+    g = O.random_warp_grid(e["tps_random_theta"], cp, e["tps_random_params"].reshape(2, -1), h, w, "l2sq")
+    np.testing.assert_allclose(g, e["tps_random_grid"], atol=2e-6)
+    np.testing.assert_allclose(O.random_warp_coordinates(e["tps_random_theta"], cp, e["tps_random_params"].reshape(2, -1),
+                                                         e["kp"], "l2sq"), e["tps_random_warp_kp"], atol=1e-6)
