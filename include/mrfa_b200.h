@@ -225,6 +225,16 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* 7x7 / stride 1 / pad 3 convolution with 2-3 input channels, + bias (BatchNorm pre-folded by the caller) and
+ * optional ReLU, as a TF32 implicit GEMM on the tcgen05 tensor cores: BasicMotionEncoder.convf1 (2 -> 128,
+ * raft.py:57) and the generator's `first` block (3 -> 64, generator.py:23).  Supported (Cin, Cout): (2,128), (3,64);
+ * W % 128 == 0.  x (B,Cin,H,W) with element strides xs {sn, sy, sx, sc}; w_packed (Cout, KP) with
+ * KP = mrfa_conv7x7_small_kpad(Cin), element [o][(ky*7+kx)*Cin + c] = weight[o][c][ky][kx], zero padded;
+ * bias (Cout) or NULL; y (B,H,W,Cout) NHWC, 32-byte aligned.  sm_count sizes the persistent grid.            */
+int mrfa_conv7x7_small_kpad(int Cin);
+int mrfa_conv7x7_small(const float* x, mrfa_grid_strides_t xs, const float* w_packed, const float* bias, float* y,
+                       int B, int Cin, int Cout, int H, int W, int relu, int sm_count, mrfa_stream_t stream);
+
 /* Random affine + thin-plate warp of the identity grid -- the training-only equivariance warps.
  * metric MRFA_TPS_L1   : Transform.warp_coordinates model.py:50-70 (d = |dx|+|dy|, U = d^2 log(d + 1e-6));
  * metric MRFA_TPS_L2SQ : TPS mode 'random' util.py:412-423 (r2 = dx^2+dy^2, U = r2 log(r2 + 1e-9)).

@@ -10,10 +10,11 @@ from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
+import os
+
 from torch import nn
 
-
-import os
+from . import ops
 
 # Inference fast path (CUDA, eval mode, grad disabled): BatchNorm folded into the preceding
 # convolution, bias + ReLU fused into the cuDNN convolution (aten::cudnn_convolution_relu) and
@@ -62,9 +63,25 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
     return w, b.contiguous()
 
 
+SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for mrfa::conv7x7_small
+
+
+def _small7_ok(conv: nn.Conv2d, x: torch.Tensor) -> bool:
+    """7x7 / pad 3 / stride 1 with 2-3 input channels: served by the tcgen05 TF32 kernel instead of cuDNN's
+    legacy indexed path (raft.py:57 convf1, generator.py:23 first)."""
+    return (SMALL_CONV and tuple(conv.kernel_size) == (7, 7) and tuple(conv.padding) == (3, 3)
+            and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
+            and ops.conv7x7_small_ok(x, conv.in_channels, conv.out_channels))
+
+
 def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """relu(conv(x)); bias and ReLU ride in the cuDNN convolution epilogue on the fast path."""
+    """relu(conv(x)); bias and ReLU ride in the convolution epilogue on the fast path."""
     if fast_path(conv, x):
+        if _small7_ok(conv, x):
+            if not hasattr(conv, "_pk"):
+                conv._pk = _Cache()
+            wp = conv._pk.get((conv.weight,), lambda: ops.conv7x7_small_pack(conv.weight))
+            return torch.ops.mrfa.conv7x7_small(x, wp, conv.bias, True)
         return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
     return F.relu(conv(x))
 
@@ -88,7 +105,12 @@ class _ConvNormAct(nn.Module):
         if fast_path(self, x):
             c, n = self.conv, self.norm
             w, b = self._folded.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), lambda: _fold(c, n))
-            x = torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, c.groups)
+            if _small7_ok(c, x):
+                if not hasattr(self, "_pk"):
+                    self._pk = _Cache()
+                x = torch.ops.mrfa.conv7x7_small(x, self._pk.get((w,), lambda: ops.conv7x7_small_pack(w)), b, True)
+            else:
+                x = torch.cudnn_convolution_relu(x, w, b, c.stride, c.padding, c.dilation, c.groups)
         else:
             x = F.relu(self.norm(self.conv(x)))
         if self.post_pool:

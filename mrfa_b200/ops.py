@@ -654,6 +654,49 @@ def _(x, Ho, Wo, act):
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
 
 
+def conv7x7_small_pack(weight: Tensor) -> Tensor:
+    """(Cout, Cin, 7, 7) -> the (Cout, KP) K-major operand of mrfa_conv7x7_small (k = (ky*7+kx)*Cin + c)."""
+    Cout, Cin = weight.shape[:2]
+    kp = lib.mrfa_conv7x7_small_kpad(Cin)
+    w = weight.detach().permute(0, 2, 3, 1).reshape(Cout, 49 * Cin)
+    return torch.nn.functional.pad(w, (0, kp - 49 * Cin)).contiguous()
+
+
+def conv7x7_small_ok(x: Tensor, Cin: int, Cout: int) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and (Cin, Cout) in ((2, 128), (3, 64))
+            and x.shape[1] == Cin and x.shape[3] % 128 == 0)
+
+
+@torch.library.custom_op("mrfa::conv7x7_small", mutates_args=(), device_types="cuda")
+def conv7x7_small(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], relu: bool) -> Tensor:
+    """relu?(conv2d(x, w, bias, padding=3)) for 7x7 kernels with 2-3 input channels, TF32 tensor cores;
+    x in any strides, result channels_last.  See include/mrfa_b200.h."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+        raise RuntimeError("mrfa_b200: conv7x7_small expects a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    w_packed = _req(w_packed, "w_packed")
+    B, Cin, H, W = x.shape
+    Cout = w_packed.shape[0]
+    if w_packed.shape[1] != lib.mrfa_conv7x7_small_kpad(Cin):
+        raise RuntimeError("mrfa_b200: conv7x7_small weight operand does not match the input channel count")
+    if bias is not None:
+        bias = _req(bias, "bias")
+    y = _empty_image((B, Cout, H, W), x.device, True)
+    if y.numel() == 0:
+        return y
+    st = x.stride()
+    with torch.cuda.device(x.device):
+        with _timed("conv7x7_small", 4 * (x.numel() + y.numel())):
+            check(lib.mrfa_conv7x7_small(_p(x), GridStrides(st[0], st[2], st[3], st[1]), _p(w_packed),
+                                         _p(bias) if bias is not None else None, _p(y), B, Cin, Cout, H, W, int(relu),
+                                         sm_count(x.device), _stream()), "mrfa_conv7x7_small")
+    return y
+
+
+@conv7x7_small.register_fake
+def _(x, w_packed, bias, relu):
+    return x.new_empty((x.shape[0], w_packed.shape[0], x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
+
+
 @torch.library.custom_op("mrfa::random_warp_grid", mutates_args=(), device_types="cuda")
 def random_warp_grid(theta: Tensor, control_points: Optional[Tensor], control_params: Optional[Tensor], h: int, w: int,
                      metric: int) -> Tensor:

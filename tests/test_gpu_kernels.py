@@ -643,3 +643,50 @@ def test_equivariance_transform_matches_reference_golden(golden):
     assert big.grad is not None and torch.isfinite(big.grad).all() and float(big.grad.abs().sum()) > 0
     with pytest.raises(RuntimeError):
         tr.transform_frame(torch.zeros(2, 3, 8, 8))
+
+
+@pytest.mark.parametrize("cin,cout,layout", [(2, 128, "nhwc"), (2, 128, "nchw"), (3, 64, "nchw"), (3, 64, "nhwc")])
+def test_conv7x7_small_matches_fp32_convolution(cin, cout, layout):
+    """tcgen05 TF32 implicit-GEMM 7x7 convolution (raft.py:57 convf1, generator.py:23 first) vs F.conv2d in fp32 on
+    the CPU.  TF32 operands (10-bit mantissa, round-to-nearest) with fp32 accumulation: 5e-3 relative."""
+    m = mb()
+    torch.manual_seed(31 + cin)
+    for (B, H, W) in ((2, 5, 128), (1, 37, 256), (3, 130, 128)):            # ragged heights, 1 and 2 tiles per row
+        x = torch.randn(B, cin, H, W)
+        w = torch.randn(cout, cin, 7, 7) * 0.1
+        b = torch.randn(cout)
+        ref = F.conv2d(x, w, b, padding=3)
+        xg = x.to(DEV)
+        if layout == "nhwc":
+            xg = xg.contiguous(memory_format=torch.channels_last)
+        wp = m.ops.conv7x7_small_pack(w.to(DEV))
+        out = torch.ops.mrfa.conv7x7_small(xg, wp, b.to(DEV), False)
+        assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+        rel_close(out, ref, 5e-3)
+        rel_close(torch.ops.mrfa.conv7x7_small(xg, wp, b.to(DEV), True), torch.relu(ref), 5e-3)
+        rel_close(torch.ops.mrfa.conv7x7_small(xg, wp, None, False), F.conv2d(x, w, None, padding=3), 5e-3)
+    # a strided (channel-sliced) input, as the refinement loop passes d_flow[:, 0:2]
+    big = torch.randn(2, 4, 16, 128, device=DEV).contiguous(memory_format=torch.channels_last)
+    if cin == 2:
+        rel_close(torch.ops.mrfa.conv7x7_small(big[:, 0:2], wp, None, False), F.conv2d(big[:, 0:2].cpu().contiguous(), w, None, padding=3), 5e-3)
+    with pytest.raises(RuntimeError):
+        torch.ops.mrfa.conv7x7_small(torch.randn(1, cin, 8, 64, device=DEV), wp, None, False)      # W % 128 != 0
+
+
+def test_small_conv_blocks_match_cudnn_path():
+    """BasicMotionEncoder / SameBlock2d routed through mrfa::conv7x7_small agree with the cuDNN fast path."""
+    from mrfa_b200 import blocks
+    torch.manual_seed(33)
+    blk = blocks.SameBlock2d(3, 64, kernel_size=7, padding=3).to(DEV).eval()
+    conv = torch.nn.Conv2d(2, 128, 7, padding=3).to(DEV).eval()
+    x3 = torch.rand(2, 3, 128, 128, device=DEV)
+    x2 = torch.randn(2, 2, 128, 128, device=DEV)
+    with torch.no_grad():
+        a3, a2 = blk(x3), blocks.conv_relu(conv, x2)
+        blocks.SMALL_CONV = False
+        try:
+            b3, b2 = blk(x3), blocks.conv_relu(conv, x2)
+        finally:
+            blocks.SMALL_CONV = True
+    rel_close(a3, b3, 5e-3)
+    rel_close(a2, b2, 5e-3)
