@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 3
+#define MRFA_B200_ABI_VERSION 4
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -214,9 +214,11 @@ int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float
 /* Same blend with b given as a sub-pixel up-convolution result (UpBlock2d util.py:160-177 as one 2x2
  * conv with 4*C phase-major outputs on the padded low-resolution map): a, y (N,C,2H,2W) NHWC;
  * b2 (N,4C,H+1,W+1) NHWC, phase (Y&1, X&1) of pixel (Y,X) at b2[n, Y/2+(Y&1), X/2+(X&1), (2(Y&1)+(X&1))*C+c];
- * occ (N,1,2H,2W).  C % 4 == 0.                                                               */
+ * occ (N,1,2H,2W).  C % 4 == 0.  out_block r = 1: y plain NHWC; r > 1 (dividing 2H and 2W): y in r x r
+ * space-to-depth order, pixel (Y,X) at y[n, Y/r, X/r, ((Y%r)*r + X%r)*C + c] = an (N, r*r*C, 2H/r, 2W/r) NHWC
+ * tensor -- the layout in which the generator's final 7x7 convolution (generator.py:66) is a 3x3 one.     */
 int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y,
-                                  int N, int C, int H, int W, mrfa_stream_t stream);
+                                  int N, int C, int H, int W, int out_block, mrfa_stream_t stream);
 
 /* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) raft.py:243 (and :205,228,
  * 266,...) fused with an optional activation (act as above).  SURVEY.md 8(f) N1: used as

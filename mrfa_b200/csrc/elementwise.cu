@@ -270,9 +270,12 @@ antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ we
 // low-res input (16/36 of the FLOPs, no upsampled tensor) and this kernel reads phase (a,b) of
 // full-res pixel (Y,X) at b2[n, Y/2 + a, X/2 + b, (2a+b)*C + c] with a = Y&1, b = X&1.
 // y = a * occ + b2_shuffled * (1 - occ);  a, y: (N, 2H, 2W, C) NHWC;  b2: (N, H+1, W+1, 4C) NHWC.
+// out_block r > 1 writes y in r x r space-to-depth order -- pixel (Y,X) at
+// [n, Y/r, X/r, ((Y%r)*r + X%r)*C + c], i.e. an (N, r*r*C, 2H/r, 2W/r) NHWC tensor -- so the generator's final
+// 7x7 convolution (generator.py:66) can run as a 3x3 convolution with r*r*3 outputs.
 __global__ void __launch_bounds__(256)
 occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ occ,
-                                float4* __restrict__ y, int64_t n4, int C, int H, int W) {
+                                float4* __restrict__ y, int64_t n4, int C, int H, int W, int r) {
   const int cq = C / 4, W2 = 2 * W, H2 = 2 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cq) * 4;
@@ -287,7 +290,12 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
     float4 v = __ldg(a + i);
     const float q = 1.f - o;
     v.x = fmaf(w.x, q, v.x * o); v.y = fmaf(w.y, q, v.y * o); v.z = fmaf(w.z, q, v.z * o); v.w = fmaf(w.w, q, v.w * o);
-    y[i] = v;
+    if (r == 1) {
+      y[i] = v;
+    } else {
+      const int64_t blk = (n * (H2 / r) + Y / r) * (W2 / r) + X / r;
+      y[(blk * (r * r) + (Y % r) * r + (X % r)) * cq + c / 4] = v;
+    }
   }
 }
 
@@ -393,15 +401,15 @@ extern "C" int mrfa_antialias_down(const float* in, const float* weight, float* 
 }
 
 extern "C" int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y, int N, int C,
-                                             int H, int W, mrfa_stream_t stream) {
-  MRFA_CHECK_ARG(a && b2 && occ && y && N >= 0 && C > 0 && H > 0 && W > 0);
-  MRFA_CHECK_SHAPE(C % 4 == 0);
+                                             int H, int W, int out_block, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(a && b2 && occ && y && N >= 0 && C > 0 && H > 0 && W > 0 && out_block >= 1);
+  MRFA_CHECK_SHAPE(C % 4 == 0 && (2 * H) % out_block == 0 && (2 * W) % out_block == 0);
   if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
     return MRFA_E_ALIGN;
   if (N == 0) return 0;
   const int64_t n4 = (int64_t)N * 4 * H * W * C / 4;
   occlusion_blend_subpixel_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W);
+      reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W, out_block);
   return MRFA_LAUNCH_RESULT();
 }
 

@@ -797,8 +797,9 @@ def _(x, weight, ka, stride):
 
 
 @torch.library.custom_op("mrfa::occlusion_blend_subpixel", mutates_args=(), device_types="cuda")
-def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor) -> Tensor:
-    """a * occ + shuffle(b2) * (1 - occ) with b2 the phase-major sub-pixel up-conv output (see header)."""
+def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor, out_block: int = 1) -> Tensor:
+    """a * occ + shuffle(b2) * (1 - occ) with b2 the phase-major sub-pixel up-conv output (see header).
+    out_block r > 1 returns the result in r x r space-to-depth form: (N, r*r*C, 2H/r, 2W/r) channels_last."""
     a, cl = _req_image(a, "a")
     b2, cl2 = _req_image(b2, "b2")
     occ = _req(occ, "occ")
@@ -806,17 +807,26 @@ def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor) -> Tensor:
     H, W = H2 // 2, W2 // 2
     if not (cl and cl2) or tuple(b2.shape) != (N, 4 * C, H + 1, W + 1) or tuple(occ.shape) != (N, 1, H2, W2):
         raise RuntimeError("mrfa_b200: occlusion_blend_subpixel expects channels_last a (N,C,2H,2W), b2 (N,4C,H+1,W+1), occ (N,1,2H,2W)")
-    y = torch.empty_like(a)
+    r = int(out_block)
+    if r < 1 or H2 % r or W2 % r:
+        raise RuntimeError("mrfa_b200: occlusion_blend_subpixel out_block must divide the output size")
+    y = torch.empty_like(a) if r == 1 else _empty_image((N, r * r * C, H2 // r, W2 // r), a.device, True)
+    if y.numel() == 0:
+        return y
     with torch.cuda.device(a.device):
         with _timed("occlusion_blend", 4 * (2 * a.numel() + a.numel() + occ.numel())):
-            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(y), N, C, H, W, _stream()),
+            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(y), N, C, H, W, r, _stream()),
                   "mrfa_occlusion_blend_subpixel")
     return y
 
 
 @occlusion_blend_subpixel.register_fake
-def _(a, b2, occ):
-    return torch.empty_like(a)
+def _(a, b2, occ, out_block=1):
+    if out_block == 1:
+        return torch.empty_like(a)
+    N, C, H2, W2 = a.shape
+    r = out_block
+    return a.new_empty((N, r * r * C, H2 // r, W2 // r)).contiguous(memory_format=torch.channels_last)
 
 
 @torch.library.custom_op("mrfa::avg_pool2x2_nhwc", mutates_args=(), device_types="cuda")

@@ -690,3 +690,29 @@ def test_small_conv_blocks_match_cudnn_path():
             blocks.SMALL_CONV = True
     rel_close(a3, b3, 5e-3)
     rel_close(a2, b2, 5e-3)
+
+
+def test_blend_subpixel_space_to_depth_output_and_final_conv():
+    """The r x r space-to-depth output of the last blend is a pure re-layout, and the generator's final 7x7
+    convolution evaluated on it as a 3x3 convolution (blocks._final_s2d) equals the direct one."""
+    from mrfa_b200 import blocks, synthetic as syn
+    torch.manual_seed(41)
+    N, C, H, W = 2, 8, 6, 10
+    a = torch.randn(N, C, 2 * H, 2 * W, device=DEV).contiguous(memory_format=torch.channels_last)
+    b2 = torch.randn(N, 4 * C, H + 1, W + 1, device=DEV).contiguous(memory_format=torch.channels_last)
+    occ = torch.rand(N, 1, 2 * H, 2 * W, device=DEV)
+    plain = torch.ops.mrfa.occlusion_blend_subpixel(a, b2, occ, 1)
+    for r in (2, 4):
+        got = torch.ops.mrfa.occlusion_blend_subpixel(a, b2, occ, r)
+        assert got.shape == (N, r * r * C, 2 * H // r, 2 * W // r) and got.is_contiguous(memory_format=torch.channels_last)
+        # channel index (iy*r + ix)*C + c of block (Y/r, X/r)  <->  pixel (Y, X), channel c
+        want = plain.reshape(N, C, 2 * H // r, r, 2 * W // r, r).permute(0, 3, 5, 1, 2, 4).reshape(N, r * r * C, 2 * H // r, 2 * W // r)
+        assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        torch.ops.mrfa.occlusion_blend_subpixel(a, b2, occ, 8)             # 8 does not divide 12
+    gen = syn.fill_state_dict_(blocks.OcclusionAwareGenerator(3, 16, 64, 3)).to(DEV).eval()
+    x = torch.randn(2, 16, 24, 40, device=DEV)
+    with torch.no_grad():
+        ref = gen.final(x)
+        xs = x.reshape(2, 16, 6, 4, 10, 4).permute(0, 3, 5, 1, 2, 4).reshape(2, 256, 6, 10).contiguous(memory_format=torch.channels_last)
+        close(gen._final_s2d(xs), ref, 1e-5, 1e-5)
