@@ -227,6 +227,12 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* Hourglass decoder step `out = cat([up_block(out), skip], dim=1)` (util.py:246-278) with the up-block evaluated as
+ * the sub-pixel 2x2 convolution (see mrfa_occlusion_blend_subpixel): b2 (N,4C,H+1,W+1) NHWC phase-major;
+ * skip (N,Cs,2H,2W) with element strides {sn, sy, sx, sc}; y (N,C+Cs,2H,2W) NHWC = [shuffle(b2), skip].         */
+int mrfa_subpixel_shuffle_cat(const float* b2, const float* skip, mrfa_grid_strides_t skip_strides, float* y,
+                              int N, int C, int Cs, int H, int W, mrfa_stream_t stream);
+
 /* 7x7 / stride 1 / pad 3 convolution with 2-3 input channels, + bias (BatchNorm pre-folded by the caller) and
  * optional ReLU, as a TF32 implicit GEMM on the tcgen05 tensor cores: BasicMotionEncoder.convf1 (2 -> 128,
  * raft.py:57) and the generator's `first` block (3 -> 64, generator.py:23).  Supported (Cin, Cout): (2,128), (3,64);

@@ -65,6 +65,7 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
 
 S2D_FINAL = os.environ.get("MRFA_S2D_FINAL", "1") != "0"      # A/B switch for the space-to-depth final convolution
 S2D_BLOCK = 4
+HG_SUBPIXEL = os.environ.get("MRFA_HG_SUBPIXEL", "1") != "0"  # A/B switch for the hourglass sub-pixel up-blocks
 SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for mrfa::conv7x7_small
 
 
@@ -155,8 +156,8 @@ class UpBlock2d(_ConvNormAct):
             return w2.contiguous(memory_format=torch.channels_last), b.repeat(4).contiguous()
 
         w2, b2 = self._sub.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), build)
-        xp = F.pad(x, (1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
-        return torch.cudnn_convolution_relu(xp, w2, b2, (1, 1), (0, 0), (1, 1), 1)
+        # 2x2 kernel with padding 1: (H, W) -> (H+1, W+1), the zero border supplied by the convolution itself
+        return torch.cudnn_convolution_relu(x, w2, b2, (1, 1), (1, 1), (1, 1), 1)
 
 
 class DownBlock2d(_ConvNormAct):
@@ -235,7 +236,12 @@ class _HGDecoder(nn.Module):
         feats = list(feats)
         y = feats.pop()
         for blk in self.up_blocks:
-            y = torch.cat([blk(y), feats.pop()], dim=1)
+            skip = feats.pop()
+            if HG_SUBPIXEL and blk.subpixel_ok(y) and tuple(skip.shape[2:]) == (2 * y.shape[2], 2 * y.shape[3]):
+                # sub-pixel up-convolution; its de-interleave and the cat are one kernel
+                y = torch.ops.mrfa.subpixel_shuffle_cat(blk.forward_subpixel(y), skip)
+            else:
+                y = torch.cat([blk(y), skip], dim=1)
         return y
 
 

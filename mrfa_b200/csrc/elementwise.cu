@@ -300,6 +300,55 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
 }
 
 
+// Hourglass decoder step (util.py:246-278: out = cat([up_block(out), skip], 1)) with the up-block run as
+// the sub-pixel 2x2 convolution above: this kernel de-interleaves the four phases of b2 into
+// channels [0, C) of the full-resolution map and copies the skip connection into [C, C+Cs) --
+// the nearest-upsampled tensor, the 3x3 convolution on it and the separate cat pass disappear.
+// b2 (N, H+1, W+1, 4C) NHWC; skip (N, Cs, 2H, 2W) with element strides; y (N, 2H, 2W, C+Cs) NHWC.
+__global__ void __launch_bounds__(256)
+subpixel_shuffle_cat_v4_kernel(const float* __restrict__ b2, const float4* __restrict__ skip, float4* __restrict__ y,
+                               int64_t n4, int C, int Cs, int H, int W) {
+  const int ct = C + Cs, cq = ct / 4, W2 = 2 * W, H2 = 2 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cq) * 4;
+    const int64_t pix = i / cq;
+    float4 v;
+    if (c < C) {
+      const int X = (int)(pix % W2);
+      const int Y = (int)((pix / W2) % H2);
+      const int64_t n = pix / ((int64_t)W2 * H2);
+      const int pa = Y & 1, pb = X & 1;
+      v = __ldg(reinterpret_cast<const float4*>(
+          b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C + c));
+    } else {
+      v = __ldg(skip + (pix * Cs + (c - C)) / 4);
+    }
+    y[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+subpixel_shuffle_cat_kernel(const float* __restrict__ b2, const float* __restrict__ skip, mrfa_grid_strides_t ss,
+                            float* __restrict__ y, int64_t total, int C, int Cs, int H, int W) {
+  const int ct = C + Cs, W2 = 2 * W, H2 = 2 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ct);
+    const int64_t pix = i / ct;
+    const int X = (int)(pix % W2);
+    const int Y = (int)((pix / W2) % H2);
+    const int64_t n = pix / ((int64_t)W2 * H2);
+    float v;
+    if (c < C) {
+      const int pa = Y & 1, pb = X & 1;
+      v = __ldg(b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C + c);
+    } else {
+      v = __ldg(skip + n * ss.sn + (int64_t)(c - C) * ss.sc + (int64_t)Y * ss.sy + (int64_t)X * ss.sx);
+    }
+    y[i] = v;
+  }
+}
+
+
 // 2x2 average pooling in NHWC (DownBlock2d, util.py:190-196): one float4 per thread, 4 loads +
 // 1 store, window summed row-major then divided by 4 like ATen.  (The stock NHWC avg_pool2d
 // kernel runs at ~0.8 TB/s on the 2 GB encoder maps.)
@@ -440,5 +489,23 @@ extern "C" int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_stride
   flow_carry_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(d_flow, d_strides, init_flow, prior_occ, d_f_pre,
                                                                          d_occ_pre, flow, occ, d_f_acc, d_occ_acc, R, h,
                                                                          scale, channels_last, s_r, s_h, total);
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_subpixel_shuffle_cat(const float* b2, const float* skip, mrfa_grid_strides_t skip_strides, float* y,
+                                         int N, int C, int Cs, int H, int W, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(b2 && y && N >= 0 && C > 0 && Cs >= 0 && H > 0 && W > 0 && (skip || Cs == 0));
+  if (N == 0) return 0;
+  const int64_t total = (int64_t)N * 4 * H * W * (C + Cs);
+  const bool dense_nhwc = skip_strides.sc == 1 && skip_strides.sx == Cs && skip_strides.sy == (int64_t)Cs * 2 * W &&
+                          skip_strides.sn == (int64_t)Cs * 4 * H * W;
+  if (C % 4 == 0 && Cs % 4 == 0 && (Cs == 0 || dense_nhwc) &&
+      ((reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    subpixel_shuffle_cat_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+        b2, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(y), total / 4, C, Cs, H, W);
+  } else {
+    subpixel_shuffle_cat_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(b2, skip, skip_strides, y, total, C, Cs,
+                                                                                    H, W);
+  }
   return MRFA_LAUNCH_RESULT();
 }

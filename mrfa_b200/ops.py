@@ -697,6 +697,35 @@ def _(x, w_packed, bias, relu):
     return x.new_empty((x.shape[0], w_packed.shape[0], x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
 
 
+@torch.library.custom_op("mrfa::subpixel_shuffle_cat", mutates_args=(), device_types="cuda")
+def subpixel_shuffle_cat(b2: Tensor, skip: Tensor) -> Tensor:
+    """cat([shuffle(b2), skip], 1) with b2 the phase-major sub-pixel up-conv output (N,4C,H+1,W+1) channels_last and
+    skip (N,Cs,2H,2W) in any strides; result (N,C+Cs,2H,2W) channels_last.  See include/mrfa_b200.h."""
+    b2, cl = _req_image(b2, "b2")
+    if not skip.is_cuda or skip.dtype != torch.float32 or skip.dim() != 4:
+        raise RuntimeError("mrfa_b200: subpixel_shuffle_cat `skip` must be a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    N, C4, H1, W1 = b2.shape
+    C, H, W = C4 // 4, H1 - 1, W1 - 1
+    Cs = skip.shape[1]
+    if not cl or C4 % 4 or tuple(skip.shape) != (N, Cs, 2 * H, 2 * W):
+        raise RuntimeError("mrfa_b200: subpixel_shuffle_cat expects channels_last b2 (N,4C,H+1,W+1) and skip (N,Cs,2H,2W)")
+    y = _empty_image((N, C + Cs, 2 * H, 2 * W), b2.device, True)
+    if y.numel() == 0:
+        return y
+    st = skip.stride()
+    with torch.cuda.device(b2.device):
+        with _timed("subpixel_shuffle_cat", 4 * 2 * y.numel()):
+            check(lib.mrfa_subpixel_shuffle_cat(_p(b2), _p(skip), GridStrides(st[0], st[2], st[3], st[1]), _p(y), N, C, Cs, H, W,
+                                                _stream()), "mrfa_subpixel_shuffle_cat")
+    return y
+
+
+@subpixel_shuffle_cat.register_fake
+def _(b2, skip):
+    N, C4, H1, W1 = b2.shape
+    return b2.new_empty((N, C4 // 4 + skip.shape[1], 2 * (H1 - 1), 2 * (W1 - 1))).contiguous(memory_format=torch.channels_last)
+
+
 @torch.library.custom_op("mrfa::random_warp_grid", mutates_args=(), device_types="cuda")
 def random_warp_grid(theta: Tensor, control_points: Optional[Tensor], control_params: Optional[Tensor], h: int, w: int,
                      metric: int) -> Tensor:

@@ -716,3 +716,21 @@ def test_blend_subpixel_space_to_depth_output_and_final_conv():
         ref = gen.final(x)
         xs = x.reshape(2, 16, 6, 4, 10, 4).permute(0, 3, 5, 1, 2, 4).reshape(2, 256, 6, 10).contiguous(memory_format=torch.channels_last)
         close(gen._final_s2d(xs), ref, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("C,Cs,skip_cl", [(8, 12, True), (8, 5, False), (6, 13, True), (16, 0, True)])
+def test_subpixel_shuffle_cat(C, Cs, skip_cl):
+    """Hourglass decoder step (util.py:246-278) as shuffle + cat in one pass; vector and scalar paths."""
+    torch.manual_seed(43)
+    N, H, W = 2, 5, 7
+    b2 = torch.randn(N, 4 * C, H + 1, W + 1, device=DEV).contiguous(memory_format=torch.channels_last)
+    skip = torch.randn(N, Cs, 2 * H, 2 * W, device=DEV)
+    if skip_cl:
+        skip = skip.contiguous(memory_format=torch.channels_last)
+    Y, X = torch.meshgrid(torch.arange(2 * H, device=DEV), torch.arange(2 * W, device=DEV), indexing="ij")
+    pa, pb = Y & 1, X & 1
+    b2v = b2.reshape(N, 4, C, H + 1, W + 1)                      # channel (2a+b)*C + c
+    shuf = b2v[:, (2 * pa + pb), :, (Y >> 1) + pa, (X >> 1) + pb].permute(2, 3, 0, 1)     # (2H,2W,N,C) -> (N,C,2H,2W)
+    want = torch.cat([shuf, skip], dim=1)
+    got = torch.ops.mrfa.subpixel_shuffle_cat(b2, skip)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
