@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 4
+#define MRFA_B200_ABI_VERSION 5
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -79,10 +79,13 @@ int mrfa_grid_sample_bwd(const float* grad_out, const float* in, const float* gr
 
 /* Two warps of the same feature map in one pass: refined (pixel flow + identity, raft.py:247)
  * and coarse/prior (normalised grid, align_corners=False, raft.py:271).  flow (B,2,Ho,Wo)
- * planar; prior_grid (B,Ho,Wo,2).  Reads `in` once from HBM.                                */
+ * planar; prior_grid (B,Ho,Wo,2).  Reads `in` once from HBM.  coarse_pixel_stride (NHWC only; 0 = C): element
+ * stride between pixels of out_coarse, so the coarse warp can be written straight into a channel slice of the
+ * buffer the decoder would otherwise build with cat([y, warp_c]) (generator.py:58-59).                  */
 int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid,
                        float* out_refined, float* out_coarse,
-                       int N, int C, int H, int W, int channels_last, mrfa_stream_t stream);
+                       int N, int C, int H, int W, int channels_last, int64_t coarse_pixel_stride,
+                       mrfa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Coordinate grids and key-point heat-maps
@@ -216,9 +219,12 @@ int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float
  * b2 (N,4C,H+1,W+1) NHWC, phase (Y&1, X&1) of pixel (Y,X) at b2[n, Y/2+(Y&1), X/2+(X&1), (2(Y&1)+(X&1))*C+c];
  * occ (N,1,2H,2W).  C % 4 == 0.  out_block r = 1: y plain NHWC; r > 1 (dividing 2H and 2W): y in r x r
  * space-to-depth order, pixel (Y,X) at y[n, Y/r, X/r, ((Y%r)*r + X%r)*C + c] = an (N, r*r*C, 2H/r, 2W/r) NHWC
- * tensor -- the layout in which the generator's final 7x7 convolution (generator.py:66) is a 3x3 one.     */
+ * tensor -- the layout in which the generator's final 7x7 convolution (generator.py:66) is a 3x3 one.
+ * out_pixel_stride (out_block 1 only; 0 = C): element stride between pixels of y (a channel slice of a wider
+ * NHWC buffer, see mrfa_dual_warp_fwd).                                                         */
 int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y,
-                                  int N, int C, int H, int W, int out_block, mrfa_stream_t stream);
+                                  int N, int C, int H, int W, int out_block, int64_t out_pixel_stride,
+                                  mrfa_stream_t stream);
 
 /* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) raft.py:243 (and :205,228,
  * 266,...) fused with an optional activation (act as above).  SURVEY.md 8(f) N1: used as

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
 TPS_L1, TPS_L2SQ = 0, 1
@@ -29,7 +29,7 @@ SIGNATURES = {
     "mrfa_grid_sample_fwd": (c_int, [c_void_p, c_void_p, GridStrides, c_void_p] + [c_int] * 11 + [c_void_p]),
     "mrfa_grid_sample_bwd": (c_int, [c_void_p, c_void_p, c_void_p, GridStrides, c_void_p, c_void_p]
                              + [c_int] * 11 + [c_void_p]),
-    "mrfa_dual_warp_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "mrfa_dual_warp_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_int64, c_void_p]),
     "mrfa_coords_grid": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mrfa_make_coordinate_grid": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mrfa_kp2gaussian": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
@@ -45,7 +45,7 @@ SIGNATURES = {
     "mrfa_corr_lookup_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 4
                              + [c_int64, c_int64, c_int, c_int, c_void_p]),
     "mrfa_channel_affine": (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
-    "mrfa_occlusion_blend_subpixel": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    "mrfa_occlusion_blend_subpixel": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_int64, c_void_p]),
     "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_antialias_down": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),

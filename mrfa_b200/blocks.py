@@ -314,9 +314,11 @@ class OcclusionAwareGenerator(nn.Module):
             feats.append(blk(feats[-1]))
         return feats[::-1]          # coarsest first: R = S/32 ... S
 
-    def decode(self, warp_f, warp_img, occlusion, warp_f_c=None, occlusion_c=None):
+    def decode(self, warp_f, warp_img, occlusion, warp_f_c=None, occlusion_c=None, coarse_cat=None):
+        """`coarse_cat[i]` (optional, inference): the (N,2C,H,W) buffer of mrfa::dual_warp_cat whose upper half is
+        warp_f_c[i]; the blend of that level is then written into its lower half instead of a cat."""
         if fast_path(self, warp_img):
-            return self._decode_fast(warp_f, warp_img, occlusion, warp_f_c)
+            return self._decode_fast(warp_f, warp_img, occlusion, warp_f_c, coarse_cat)
         use_coarse = warp_f_c is not None
         y = warp_f[0] * occlusion[0]
         if use_coarse:
@@ -362,7 +364,7 @@ class OcclusionAwareGenerator(nn.Module):
         w2, b2 = self._s2d.get((c.weight, c.bias), build)
         return F.pixel_shuffle(F.conv2d(ys, w2, b2, padding=1), S2D_BLOCK)
 
-    def _decode_fast(self, warp_f, warp_img, occlusion, warp_f_c):
+    def _decode_fast(self, warp_f, warp_img, occlusion, warp_f_c, coarse_cat=None):
         """Same dataflow as decode(); the occlusion blends are single fused passes."""
         blend = torch.ops.mrfa.occlusion_blend
         use_coarse = warp_f_c is not None
@@ -384,6 +386,11 @@ class OcclusionAwareGenerator(nn.Module):
                     # the last blend writes its result in 4x4 space-to-depth order for the final convolution
                     ys = torch.ops.mrfa.occlusion_blend_subpixel(warp_f[i + 1], up.forward_subpixel(y), occlusion[i + 1], S2D_BLOCK)
                     return blend(warp_img, torch.sigmoid(self._final_s2d(ys)), occlusion[-1])
+                buf = coarse_cat[i + 1] if (coarse_cat is not None and use_coarse and not last) else None
+                if buf is not None and buf.shape[1] == 2 * warp_f[i + 1].shape[1]:
+                    torch.ops.mrfa.occlusion_blend_subpixel_into(warp_f[i + 1], up.forward_subpixel(y), occlusion[i + 1], buf)
+                    y = buf                                   # == cat([blend, warp_f_c[i + 1]], 1), no copy
+                    continue
                 y = torch.ops.mrfa.occlusion_blend_subpixel(warp_f[i + 1], up.forward_subpixel(y), occlusion[i + 1], 1)
             else:
                 y = blend(warp_f[i + 1], up(y), occlusion[i + 1])

@@ -95,32 +95,65 @@ __device__ __forceinline__ void resize_axis(int o, float scale, int in, int& i0,
   l1 = src - (float)i0;
 }
 
+// One thread produces kResizeRun consecutive output pixels of one row for one channel quad and keeps the four
+// source taps in registers, reloading a column only when the left tap index advances: for the x2 / x4
+// up-samplings of the decoder that is ~0.5-1 instead of 4 vector loads per output (the plain form is bound by
+// L1/L2 load traffic at 4x the output bytes).  Lanes run along the channel quads, so every load and store of
+// a warp is one contiguous pixel.
+constexpr int kResizeRun = 8;
+
 __global__ void __launch_bounds__(256)
 resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
-                            float sy, float sx, int64_t total4, int act) {
+                            float sy, float sx, int64_t total_runs, int act) {
   const int cq = C / 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+  const int runs_per_row = (Wo + kResizeRun - 1) / kResizeRun;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_runs; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cq) * 4;
-    const int64_t pix = i / cq;
-    const int ox = (int)(pix % Wo);
-    const int oy = (int)((pix / Wo) % Ho);
-    const int64_t n = pix / ((int64_t)Wo * Ho);
-    int y0, y1, x0, x1;
-    float ly, lx;
+    int64_t rem = i / cq;
+    const int run = (int)(rem % runs_per_row);
+    rem /= runs_per_row;
+    const int oy = (int)(rem % Ho);
+    const int64_t n = rem / Ho;
+    int y0, y1;
+    float ly;
     resize_axis(oy, sy, H, y0, y1, ly);
-    resize_axis(ox, sx, W, x0, x1, lx);
-    const float* base = x + n * H * W * C + c;
-    const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * W + x0) * C));
-    const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * W + x1) * C));
-    const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * W + x0) * C));
-    const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * W + x1) * C));
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    float4 r;
-    r.x = act_fn(hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x), act);
-    r.y = act_fn(hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y), act);
-    r.z = act_fn(hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z), act);
-    r.w = act_fn(hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w), act);
-    *(reinterpret_cast<float4*>(y) + i) = r;
+    const float hy = 1.f - ly;
+    const float* r0 = x + (n * H + y0) * (int64_t)W * C + c;
+    const float* r1 = x + (n * H + y1) * (int64_t)W * C + c;
+    float4* dst = reinterpret_cast<float4*>(y + ((n * Ho + oy) * (int64_t)Wo + run * kResizeRun) * C + c);
+    int cx0 = -1, cx1 = -1;
+    float4 v00 = make_float4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
+#pragma unroll
+    for (int j = 0; j < kResizeRun; ++j) {
+      const int ox = run * kResizeRun + j;
+      if (ox >= Wo) break;
+      int x0, x1;
+      float lx;
+      resize_axis(ox, sx, W, x0, x1, lx);
+      if (x0 != cx0) {
+        if (x0 == cx1) { v00 = v01; v10 = v11; }          // slide: the old right column becomes the left one
+        else {
+          v00 = __ldg(reinterpret_cast<const float4*>(r0 + (int64_t)x0 * C));
+          v10 = __ldg(reinterpret_cast<const float4*>(r1 + (int64_t)x0 * C));
+        }
+        cx0 = x0;
+      }
+      if (x1 != cx1) {
+        if (x1 == x0) { v01 = v00; v11 = v10; }
+        else {
+          v01 = __ldg(reinterpret_cast<const float4*>(r0 + (int64_t)x1 * C));
+          v11 = __ldg(reinterpret_cast<const float4*>(r1 + (int64_t)x1 * C));
+        }
+        cx1 = x1;
+      }
+      const float hx = 1.f - lx;
+      float4 r;
+      r.x = act_fn(hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x), act);
+      r.y = act_fn(hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y), act);
+      r.z = act_fn(hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z), act);
+      r.w = act_fn(hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w), act);
+      dst[(int64_t)j * cq] = r;
+    }
   }
 }
 
@@ -275,7 +308,7 @@ antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ we
 // 7x7 convolution (generator.py:66) can run as a 3x3 convolution with r*r*3 outputs.
 __global__ void __launch_bounds__(256)
 occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ occ,
-                                float4* __restrict__ y, int64_t n4, int C, int H, int W, int r) {
+                                float4* __restrict__ y, int64_t n4, int C, int H, int W, int r, int64_t ostride) {
   const int cq = C / 4, W2 = 2 * W, H2 = 2 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cq) * 4;
@@ -291,7 +324,7 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
     const float q = 1.f - o;
     v.x = fmaf(w.x, q, v.x * o); v.y = fmaf(w.y, q, v.y * o); v.z = fmaf(w.z, q, v.z * o); v.w = fmaf(w.w, q, v.w * o);
     if (r == 1) {
-      y[i] = v;
+      y[(pix * ostride + c) / 4] = v;
     } else {
       const int64_t blk = (n * (H2 / r) + Y / r) * (W2 / r) + X / r;
       y[(blk * (r * r) + (Y % r) * r + (X % r)) * cq + c / 4] = v;
@@ -427,8 +460,8 @@ extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int 
   const int64_t total = (int64_t)N * C * Ho * Wo;
   if (channels_last && C % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
-    resize_bilinear_nhwc_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
-                                                                                         total / 4, act);
+    const int64_t runs = (int64_t)N * Ho * ((Wo + kResizeRun - 1) / kResizeRun) * (C / 4);
+    resize_bilinear_nhwc_kernel<<<stream_blocks(runs), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, act);
   } else if (channels_last) {
     resize_bilinear_nhwc_scalar_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
                                                                                             total, act);
@@ -450,15 +483,17 @@ extern "C" int mrfa_antialias_down(const float* in, const float* weight, float* 
 }
 
 extern "C" int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y, int N, int C,
-                                             int H, int W, int out_block, mrfa_stream_t stream) {
+                                             int H, int W, int out_block, int64_t out_pixel_stride, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(a && b2 && occ && y && N >= 0 && C > 0 && H > 0 && W > 0 && out_block >= 1);
+  MRFA_CHECK_ARG(out_pixel_stride == 0 || (out_block == 1 && out_pixel_stride >= C && out_pixel_stride % 4 == 0));
   MRFA_CHECK_SHAPE(C % 4 == 0 && (2 * H) % out_block == 0 && (2 * W) % out_block == 0);
   if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
     return MRFA_E_ALIGN;
   if (N == 0) return 0;
   const int64_t n4 = (int64_t)N * 4 * H * W * C / 4;
   occlusion_blend_subpixel_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W, out_block);
+      reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W, out_block,
+      out_pixel_stride > 0 ? out_pixel_stride : (int64_t)C);
   return MRFA_LAUNCH_RESULT();
 }
 

@@ -283,7 +283,8 @@ grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restric
 template <int LPP, int PW>
 __global__ void __launch_bounds__(kThreads, 3)
 dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
-                          float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W) {
+                          float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W,
+                          int64_t cstride) {
   constexpr int PPS = (32 / LPP) < PW ? (32 / LPP) : PW;
   constexpr int LPPE = 32 / PPS;
   const int HW = H * W;
@@ -313,7 +314,7 @@ dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict_
     if (gp >= total) continue;
     const float* src = in + (int64_t)tr.n_in * plane + cl;
     float* dr = out_r + gp * C + cl;
-    float* dc = out_c + gp * C + cl;
+    float* dc = out_c + gp * cstride + cl;     // the coarse warp may land in a channel slice of a wider NHWC buffer
     for (int c = 0; c < C - cl; c += LPPE * 4) {
       {
         const float4 a0 = ldg4(src + (tr.o_nw + c)), a1 = ldg4(src + (tr.o_ne + c));
@@ -512,7 +513,8 @@ extern "C" int mrfa_grid_sample_bwd(const float* grad_out, const float* in, cons
 
 extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid, float* out_refined,
                                   float* out_coarse, int N, int C, int H, int W, int channels_last,
-                                  mrfa_stream_t stream) {
+                                  int64_t coarse_pixel_stride, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(coarse_pixel_stride == 0 || (channels_last && coarse_pixel_stride >= C && coarse_pixel_stride % 4 == 0));
   MRFA_CHECK_ARG(in && flow && prior_grid && out_refined && out_coarse);
   MRFA_CHECK_ARG(N >= 0 && C > 0 && H > 0 && W > 0);
   MRFA_CHECK_SHAPE((int64_t)H * W < (1ll << 31));
@@ -525,10 +527,11 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
     const bool small = pixels < kSmallPixels;
     dim3 gn((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
     cudaStream_t st = as_stream(stream);
+    const int64_t cs = coarse_pixel_stride > 0 ? coarse_pixel_stride : C;
 #define MRFA_DW_CASE(L)                                                                                              \
   case L:                                                                                                            \
-    if (small) dual_warp_fwd_nhwc_kernel<L, 4><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W); \
-    else dual_warp_fwd_nhwc_kernel<L, 32><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W);   \
+    if (small) dual_warp_fwd_nhwc_kernel<L, 4><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs); \
+    else dual_warp_fwd_nhwc_kernel<L, 32><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs);   \
     break;
     switch (lanes_per_pixel(C)) {
       MRFA_DW_CASE(1) MRFA_DW_CASE(2) MRFA_DW_CASE(4) MRFA_DW_CASE(8) MRFA_DW_CASE(16) MRFA_DW_CASE(32)

@@ -213,9 +213,35 @@ def dual_warp(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Te
     out_r, out_c = torch.empty_like(inp), torch.empty_like(inp)
     with torch.cuda.device(inp.device):
         with _timed("dual_warp_fwd", 4 * (3 * inp.numel() + 4 * N * H * W)):
-            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, int(cl), _stream()),
+            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), _p(out_c), N, C, H, W, int(cl), 0, _stream()),
                   "mrfa_dual_warp_fwd")
     return out_r, out_c
+
+
+@torch.library.custom_op("mrfa::dual_warp_cat", mutates_args=(), device_types="cuda")
+def dual_warp_cat(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Tensor]:
+    """dual_warp whose coarse result is written into channels [C, 2C) of a fresh (N,2C,H,W) channels_last buffer --
+    the tensor the decoder would build with cat([y, warp_c], 1) (generator.py:58-59); channels [0, C) are left for
+    mrfa::occlusion_blend_subpixel_into.  channels_last input only (inference path)."""
+    (inp, cl), flow, prior_grid = _req_image(inp, "input"), _req(flow, "flow"), _req(prior_grid, "prior_grid")
+    N, C, H, W = inp.shape
+    if not cl or tuple(flow.shape) != (N, 2, H, W) or tuple(prior_grid.shape) != (N, H, W, 2):
+        raise RuntimeError("mrfa_b200: dual_warp_cat expects a channels_last input, flow (N,2,H,W) and prior_grid (N,H,W,2)")
+    out_r = torch.empty_like(inp)
+    buf = _empty_image((N, 2 * C, H, W), inp.device, True)
+    if inp.numel() == 0:
+        return out_r, buf
+    with torch.cuda.device(inp.device):
+        with _timed("dual_warp_fwd", 4 * (3 * inp.numel() + 4 * N * H * W)):
+            check(lib.mrfa_dual_warp_fwd(_p(inp), _p(flow), _p(prior_grid), _p(out_r), buf.data_ptr() + 4 * C, N, C, H, W, 1,
+                                         2 * C, _stream()), "mrfa_dual_warp_fwd")
+    return out_r, buf
+
+
+@dual_warp_cat.register_fake
+def _(inp, flow, prior_grid):
+    N, C, H, W = inp.shape
+    return torch.empty_like(inp), inp.new_empty((N, 2 * C, H, W)).contiguous(memory_format=torch.channels_last)
 
 
 @dual_warp.register_fake
@@ -844,7 +870,7 @@ def occlusion_blend_subpixel(a: Tensor, b2: Tensor, occ: Tensor, out_block: int 
         return y
     with torch.cuda.device(a.device):
         with _timed("occlusion_blend", 4 * (2 * a.numel() + a.numel() + occ.numel())):
-            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(y), N, C, H, W, r, _stream()),
+            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(y), N, C, H, W, r, 0, _stream()),
                   "mrfa_occlusion_blend_subpixel")
     return y
 
@@ -856,6 +882,29 @@ def _(a, b2, occ, out_block=1):
     N, C, H2, W2 = a.shape
     r = out_block
     return a.new_empty((N, r * r * C, H2 // r, W2 // r)).contiguous(memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("mrfa::occlusion_blend_subpixel_into", mutates_args=("dst",), device_types="cuda")
+def occlusion_blend_subpixel_into(a: Tensor, b2: Tensor, occ: Tensor, dst: Tensor) -> None:
+    """occlusion_blend_subpixel written into channels [0, C) of `dst` (N,C',2H,2W) channels_last, C' >= C: the other
+    half of the cat buffer started by mrfa::dual_warp_cat."""
+    a, cl = _req_image(a, "a")
+    b2, cl2 = _req_image(b2, "b2")
+    occ = _req(occ, "occ")
+    N, C, H2, W2 = a.shape
+    H, W = H2 // 2, W2 // 2
+    Ct = dst.shape[1]
+    if not (cl and cl2) or tuple(b2.shape) != (N, 4 * C, H + 1, W + 1) or tuple(occ.shape) != (N, 1, H2, W2):
+        raise RuntimeError("mrfa_b200: occlusion_blend_subpixel_into expects channels_last a (N,C,2H,2W), b2 (N,4C,H+1,W+1), occ (N,1,2H,2W)")
+    if (not dst.is_cuda or dst.dtype != torch.float32 or tuple(dst.shape) != (N, Ct, H2, W2) or Ct < C or Ct % 4
+            or not dst.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("mrfa_b200: occlusion_blend_subpixel_into expects a channels_last float32 dst (N,C'>=C,2H,2W)")
+    if a.numel() == 0:
+        return
+    with torch.cuda.device(a.device):
+        with _timed("occlusion_blend", 4 * (2 * a.numel() + a.numel() + occ.numel())):
+            check(lib.mrfa_occlusion_blend_subpixel(_p(a), _p(b2), _p(occ), _p(dst), N, C, H, W, 1, Ct, _stream()),
+                  "mrfa_occlusion_blend_subpixel")
 
 
 @torch.library.custom_op("mrfa::avg_pool2x2_nhwc", mutates_args=(), device_types="cuda")

@@ -17,6 +17,7 @@ from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_
 from .corr import CorrPyramid
 
 
+CAT_SLICES = os.environ.get("MRFA_CAT_SLICES", "1") != "0"       # A/B switch: coarse warps written into the decoder's cat buffers
 FUSED_CARRY = os.environ.get("MRFA_FUSED_CARRY", "1") != "0"     # A/B switch for the fused level hand-over
 
 
@@ -208,6 +209,7 @@ class RaftFlow(nn.Module):
         ident_basic = sampling.coords_grid(B, h, w, dev)
 
         out_warp_f, out_occlusion, out_warp_f_c, out_occlusion_c = [], [], [], []
+        cat_bufs = [None] * self.total_iter if (CAT_SLICES and fast_path(self, img) and cl) else None
         d_f_pre = d_occ_pre = None
         for i in range(self.total_iter):
             R = self.size // 32 * 2 ** i
@@ -231,7 +233,14 @@ class RaftFlow(nn.Module):
                 occ_res = _resize(prior_occ, (R, R))
             else:
                 prior_grid, occ_res = prior, prior_occ
-            warp_f, warp_c = torch.ops.mrfa.dual_warp(feature[i], flow, prior_grid)       # raft.py:247, :271
+            if cat_bufs is not None and 0 < i < self.num_iter - 1 and feature[i].shape[1] % 4 == 0 \
+                    and feature[i].is_contiguous(memory_format=torch.channels_last) and not feature[i].is_contiguous():
+                # the coarse warp lands in the upper half of the decoder's cat([y, warp_c]) buffer of this level
+                warp_f, buf = torch.ops.mrfa.dual_warp_cat(feature[i], flow, prior_grid)
+                warp_c = buf[:, feature[i].shape[1]:]
+                cat_bufs[i] = buf
+            else:
+                warp_f, warp_c = torch.ops.mrfa.dual_warp(feature[i], flow, prior_grid)   # raft.py:247, :271
             warp_f = conv_relu(self.to_context[i], warp_f)
 
             d_flow, _ = self.refine(m_f, warp_f)
@@ -267,7 +276,7 @@ class RaftFlow(nn.Module):
                     d_f_pre, d_occ_pre = d_f + up_f, d_o + up_o
 
         warp_img = sampling.warp_by_flow(img_full, flow)                                   # raft.py:302
-        out = self.generator.decode(out_warp_f, warp_img, out_occlusion, out_warp_f_c, out_occlusion_c)
+        out = self.generator.decode(out_warp_f, warp_img, out_occlusion, out_warp_f_c, out_occlusion_c, coarse_cat=cat_bufs)
         vis = out_occlusion + [torch.sigmoid(prior_occ)]
         occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in vis], dim=3)
         return out, warp_img, occlusion

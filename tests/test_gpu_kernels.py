@@ -734,3 +734,25 @@ def test_subpixel_shuffle_cat(C, Cs, skip_cl):
     want = torch.cat([shuf, skip], dim=1)
     got = torch.ops.mrfa.subpixel_shuffle_cat(b2, skip)
     assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
+
+
+def test_cat_slice_outputs_match_plain_ops():
+    """dual_warp_cat + occlusion_blend_subpixel_into fill the decoder's cat([y, warp_c]) buffer in place."""
+    torch.manual_seed(47)
+    N, C, H, W = 2, 8, 6, 10
+    feat = torch.randn(N, C, 2 * H, 2 * W, device=DEV).contiguous(memory_format=torch.channels_last)
+    flow = torch.randn(N, 2, 2 * H, 2 * W, device=DEV) * 2
+    prior = (torch.rand(N, 2 * H, 2 * W, 2, device=DEV) * 2.2 - 1.1)
+    wr, wc = torch.ops.mrfa.dual_warp(feat, flow, prior)
+    wr2, buf = torch.ops.mrfa.dual_warp_cat(feat, flow, prior)
+    assert buf.shape == (N, 2 * C, 2 * H, 2 * W) and buf.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(wr, wr2) and torch.equal(buf[:, C:], wc)
+    b2 = torch.randn(N, 4 * C, H + 1, W + 1, device=DEV).contiguous(memory_format=torch.channels_last)
+    occ = torch.rand(N, 1, 2 * H, 2 * W, device=DEV)
+    want = torch.ops.mrfa.occlusion_blend_subpixel(wr, b2, occ, 1)
+    torch.ops.mrfa.occlusion_blend_subpixel_into(wr, b2, occ, buf)
+    assert torch.equal(buf, torch.cat([want, wc], dim=1))
+    with pytest.raises(RuntimeError):
+        torch.ops.mrfa.dual_warp_cat(feat.contiguous(), flow, prior)                        # NCHW input
+    with pytest.raises(RuntimeError):
+        torch.ops.mrfa.occlusion_blend_subpixel_into(wr, b2, occ, buf[:, :C].contiguous())   # not channels_last / too narrow
