@@ -233,6 +233,10 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* cat([a, b], dim=1) of two NHWC maps over `pixels` = N*H*W pixels (raft.py:64 cat([cor, flo]), :82
+ * cat([motion_feature, context])): a (.., Ca), b (.., Cb) -> y (.., Ca+Cb); Ca % 4 == Cb % 4 == 0, 16-byte aligned. */
+int mrfa_cat2_nhwc(const float* a, const float* b, float* y, int64_t pixels, int Ca, int Cb, mrfa_stream_t stream);
+
 /* Hourglass decoder step `out = cat([up_block(out), skip], dim=1)` (util.py:246-278) with the up-block evaluated as
  * the sub-pixel 2x2 convolution (see mrfa_occlusion_blend_subpixel): b2 (N,4C,H+1,W+1) NHWC phase-major;
  * skip (N,Cs,2H,2W) with element strides {sn, sy, sx, sc}; y (N,C+Cs,2H,2W) NHWC = [shuffle(b2), skip].         */

@@ -723,6 +723,32 @@ def _(x, w_packed, bias, relu):
     return x.new_empty((x.shape[0], w_packed.shape[0], x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
 
 
+@torch.library.custom_op("mrfa::cat2", mutates_args=(), device_types="cuda")
+def cat2(a: Tensor, b: Tensor) -> Tensor:
+    """torch.cat([a, b], 1) for two channels_last maps with channel counts divisible by 4."""
+    (a, cla), (b, clb) = _req_image(a, "a"), _req_image(b, "b")
+    N, Ca, H, W = a.shape
+    Cb = b.shape[1]
+    if not (cla and clb) or tuple(b.shape) != (N, Cb, H, W):
+        raise RuntimeError("mrfa_b200: cat2 expects two channels_last maps of the same size with C % 4 == 0")
+    y = _empty_image((N, Ca + Cb, H, W), a.device, True)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(a.device):
+        with _timed("cat2", 4 * 2 * y.numel()):
+            check(lib.mrfa_cat2_nhwc(_p(a), _p(b), _p(y), N * H * W, Ca, Cb, _stream()), "mrfa_cat2_nhwc")
+    return y
+
+
+@cat2.register_fake
+def _(a, b):
+    return a.new_empty((a.shape[0], a.shape[1] + b.shape[1], a.shape[2], a.shape[3])).contiguous(memory_format=torch.channels_last)
+
+
+def cat2_ok(a: Tensor, b: Tensor) -> bool:
+    return _is_channels_last(a) and _is_channels_last(b) and a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
+
+
 @torch.library.custom_op("mrfa::subpixel_shuffle_cat", mutates_args=(), device_types="cuda")
 def subpixel_shuffle_cat(b2: Tensor, skip: Tensor) -> Tensor:
     """cat([shuffle(b2), skip], 1) with b2 the phase-major sub-pixel up-conv output (N,4C,H+1,W+1) channels_last and

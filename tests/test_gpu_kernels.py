@@ -756,3 +756,13 @@ def test_cat_slice_outputs_match_plain_ops():
         torch.ops.mrfa.dual_warp_cat(feat.contiguous(), flow, prior)                        # NCHW input
     with pytest.raises(RuntimeError):
         torch.ops.mrfa.occlusion_blend_subpixel_into(wr, b2, occ, buf[:, :C].contiguous())   # not channels_last / too narrow
+
+
+def test_cat2_matches_torch_cat():
+    torch.manual_seed(49)
+    a = torch.randn(2, 96, 9, 7, device=DEV).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(2, 64, 9, 7, device=DEV).contiguous(memory_format=torch.channels_last)
+    y = torch.ops.mrfa.cat2(a, b)
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, torch.cat([a, b], 1))
+    with pytest.raises(RuntimeError):
+        torch.ops.mrfa.cat2(a.contiguous(), b)
