@@ -280,8 +280,11 @@ grid_sample_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restric
   }
 }
 
+// Two passes over the warp's pixels -- refined (pixel flow + identity), then coarse (normalised prior grid) --
+// so only one tap set is live at a time (64 registers, 4 blocks per SM, no spills); the second pass finds
+// the feature rows of its neighbourhood in L1/L2, so `in` still leaves HBM once.
 template <int LPP, int PW>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
                           float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W,
                           int64_t cstride) {
@@ -292,39 +295,38 @@ dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict_
   const int64_t total = (int64_t)N * HW;
   const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * PW;
   if (gp0 >= total) return;
-  TapsB mr, mc;
-  {
-    const int64_t gp = min(gp0 + (lane % PW), total - 1);
-    const int n = (int)(gp / HW);
-    const int p = (int)(gp - (int64_t)n * HW);
-    const int y = p / W, x = p - y * W;
-    const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
-    const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
-    mr = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n, C);
-    const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
-    mc = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n, C);
-  }
   const int sub = lane / LPPE, cl = (lane % LPPE) * 4;
   const int64_t plane = (int64_t)HW * C;
-#pragma unroll 2
-  for (int s = 0; s < PW; s += PPS) {
-    const TapsB tr = shfl_taps(mr, s + sub);
-    const TapsB tc = shfl_taps(mc, s + sub);
-    const int64_t gp = gp0 + s + sub;
-    if (gp >= total) continue;
-    const float* src = in + (int64_t)tr.n_in * plane + cl;
-    float* dr = out_r + gp * C + cl;
-    float* dc = out_c + gp * cstride + cl;     // the coarse warp may land in a channel slice of a wider NHWC buffer
-    for (int c = 0; c < C - cl; c += LPPE * 4) {
-      {
-        const float4 a0 = ldg4(src + (tr.o_nw + c)), a1 = ldg4(src + (tr.o_ne + c));
-        const float4 a2 = ldg4(src + (tr.o_sw + c)), a3 = ldg4(src + (tr.o_se + c));
-        stcs4(dr + c, blend4b(a0, a1, a2, a3, tr));
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    TapsB m;
+    {
+      const int64_t gp = min(gp0 + (lane % PW), total - 1);
+      const int n = (int)(gp / HW);
+      const int p = (int)(gp - (int64_t)n * HW);
+      if (pass == 0) {
+        const int y = p / W, x = p - y * W;
+        const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
+        const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
+        m = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n, C);
+      } else {
+        const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
+        m = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n, C);
       }
-      {
-        const float4 b0 = ldg4(src + (tc.o_nw + c)), b1 = ldg4(src + (tc.o_ne + c));
-        const float4 b2 = ldg4(src + (tc.o_sw + c)), b3 = ldg4(src + (tc.o_se + c));
-        stcs4(dc + c, blend4b(b0, b1, b2, b3, tc));
+    }
+    float* const out = pass == 0 ? out_r : out_c;     // the coarse warp may land in a channel slice of a wider NHWC buffer
+    const int64_t ostride = pass == 0 ? (int64_t)C : cstride;
+#pragma unroll 2
+    for (int s = 0; s < PW; s += PPS) {
+      const TapsB t = shfl_taps(m, s + sub);
+      const int64_t gp = gp0 + s + sub;
+      if (gp >= total) continue;
+      const float* src = in + (int64_t)t.n_in * plane + cl;
+      float* d = out + gp * ostride + cl;
+      for (int c = 0; c < C - cl; c += LPPE * 4) {
+        const float4 a0 = ldg4(src + (t.o_nw + c)), a1 = ldg4(src + (t.o_ne + c));
+        const float4 a2 = ldg4(src + (t.o_sw + c)), a3 = ldg4(src + (t.o_se + c));
+        stcs4(d + c, blend4b(a0, a1, a2, a3, t));
       }
     }
   }

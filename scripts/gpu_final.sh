@@ -4,7 +4,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 |
 timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err; echo "bench rc=$? lines=$(wc -l < gpurun_out/final_bench_n1.json)"
 timeout 900 python bench.py --impl reference --gpus 1 --steps 10 --warmup 3 > gpurun_out/final_ref_n1.json 2> gpurun_out/final_ref_n1.err; echo "ref rc=$? lines=$(wc -l < gpurun_out/final_ref_n1.json)"
 timeout 600 python scripts/bench_kernels.py --stock > gpurun_out/final_kernels.jsonl 2>/dev/null
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'dual_warp|grid_sample_fwd|corr_' -o gpurun_out/final_prof_hot python scripts/profile_step.py --batch 64 > gpurun_out/final_ncu.log 2>&1
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'dual_warp|grid_sample_fwd|corr_|conv7x7|cat2|resize_bilinear_nhwc_kernel|flow_carry|subpixel' -o gpurun_out/final_prof_hot python scripts/profile_step.py --batch 64 > gpurun_out/final_ncu.log 2>&1
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv python scripts/profile_step.py --batch 64 > gpurun_out/final_ncu_launch.log 2>&1
 timeout 300 python scripts/graph_probe.py 1 2>&1 | tail -2
 python - <<'PY'
