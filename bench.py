@@ -298,10 +298,12 @@ def run_ours(args):
                 e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
         klist.append(e)
     ours_ms = sum(k["total_ms"] for k in kernels.values())
-    # roofline: the dominant kernel of the hot path proper; the fused
-    # elementwise helpers of the "next" rows are listed in kernels[] only
-    helpers = ("channel_affine", "occlusion_blend", "resize_bilinear")
-    hot = [k for k in klist if k["kernel"] not in helpers]
+    # roofline: the dominant kernel of the hot path proper; the kernels of the
+    # "next" rows 8(f) (fused elementwise helpers, small-channel convolution, cat) are listed in kernels[] only
+    hot_path = ("dual_warp_fwd", "grid_sample_fwd", "corr_volume", "corr_lookup_fwd", "corr_pack", "dense_motion_prior",
+                "tps_motion_prior", "tps_solve", "kp2gaussian", "coords_grid", "make_coordinate_grid", "prior_to_flow",
+                "avg_pool2x2")
+    hot = [k for k in klist if k["kernel"] in hot_path]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     traffic_tbl = json.load(open(tpath)) if os.path.exists(tpath) else {}
 
