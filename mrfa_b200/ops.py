@@ -690,7 +690,7 @@ def conv7x7_small_pack(weight: Tensor) -> Tensor:
 
 def conv7x7_small_ok(x: Tensor, Cin: int, Cout: int) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and (Cin, Cout) in ((2, 128), (3, 64))
-            and x.shape[1] == Cin and x.shape[3] % 128 == 0)
+            and x.shape[1] == Cin and x.shape[3] % 128 == 0 and x.shape[0] * x.shape[2] * x.shape[3] < 2 ** 31)
 
 
 @torch.library.custom_op("mrfa::conv7x7_small", mutates_args=(), device_types="cuda")
