@@ -233,6 +233,9 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* Backward of mrfa_avg_pool2x2_nhwc: grad_y (N,C,H/2,W/2) -> grad_x (N,C,H,W), both NHWC; H, W even, C % 4 == 0. */
+int mrfa_avg_pool2x2_nhwc_bwd(const float* grad_y, float* grad_x, int N, int C, int H, int W, mrfa_stream_t stream);
+
 /* cat([a, b], dim=1) of two NHWC maps over `pixels` = N*H*W pixels (raft.py:64 cat([cor, flo]), :82
  * cat([motion_feature, context])): a (.., Ca), b (.., Cb) -> y (.., Ca+Cb); Ca % 4 == Cb % 4 == 0, 16-byte aligned. */
 int mrfa_cat2_nhwc(const float* a, const float* b, float* y, int64_t pixels, int Ca, int Cb, mrfa_stream_t stream);

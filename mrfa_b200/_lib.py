@@ -53,6 +53,7 @@ SIGNATURES = {
     "mrfa_conv7x7_small_kpad": (c_int, [c_int]),
     "mrfa_conv7x7_small": (c_int, [c_void_p, GridStrides] + [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "mrfa_subpixel_shuffle_cat": (c_int, [c_void_p, c_void_p, GridStrides, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "mrfa_avg_pool2x2_nhwc_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_cat2_nhwc": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_void_p]),
     "mrfa_flow_carry": (c_int, [c_void_p, GridStrides] + [c_void_p] * 8 + [c_int] * 3 + [c_float, c_int, c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),

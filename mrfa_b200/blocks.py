@@ -117,7 +117,8 @@ class _ConvNormAct(nn.Module):
         else:
             x = F.relu(self.norm(self.conv(x)))
         if self.post_pool:
-            if (fast_path(self, x) and x.shape[1] % 4 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+            if (FAST_INFERENCE and x.is_cuda and x.dtype == torch.float32          # training too: the op has a backward
+                    and x.shape[1] % 4 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
                     and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()):
                 x = torch.ops.mrfa.avg_pool2x2_nhwc(x)
             else:

@@ -723,6 +723,36 @@ def _(x, w_packed, bias, relu):
     return x.new_empty((x.shape[0], w_packed.shape[0], x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
 
 
+@torch.library.custom_op("mrfa::avg_pool2x2_nhwc_bwd", mutates_args=(), device_types="cuda")
+def avg_pool2x2_nhwc_bwd(grad_y: Tensor, H: int, W: int) -> Tensor:
+    """Gradient of avg_pool2x2_nhwc w.r.t. its (N,C,H,W) channels_last input (H, W even)."""
+    if not grad_y.is_cuda or grad_y.dtype != torch.float32 or grad_y.dim() != 4:
+        raise RuntimeError("mrfa_b200: avg_pool2x2_nhwc_bwd expects a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    grad_y = grad_y.contiguous(memory_format=torch.channels_last)
+    N, C = grad_y.shape[:2]
+    gx = _empty_image((N, C, H, W), grad_y.device, True)
+    if gx.numel() == 0:
+        return gx
+    with torch.cuda.device(grad_y.device):
+        with _timed("avg_pool2x2_nhwc_bwd", 4 * (gx.numel() + grad_y.numel())):
+            check(lib.mrfa_avg_pool2x2_nhwc_bwd(_p(grad_y), _p(gx), N, C, H, W, _stream()), "mrfa_avg_pool2x2_nhwc_bwd")
+    return gx
+
+
+@avg_pool2x2_nhwc_bwd.register_fake
+def _(grad_y, H, W):
+    return grad_y.new_empty((grad_y.shape[0], grad_y.shape[1], H, W)).contiguous(memory_format=torch.channels_last)
+
+
+def _ap_setup(ctx, inputs, output):
+    ctx.hw = tuple(inputs[0].shape[2:])
+
+
+def _ap_backward(ctx, g):
+    return torch.ops.mrfa.avg_pool2x2_nhwc_bwd(g, ctx.hw[0], ctx.hw[1])
+
+
+
 @torch.library.custom_op("mrfa::cat2", mutates_args=(), device_types="cuda")
 def cat2(a: Tensor, b: Tensor) -> Tensor:
     """torch.cat([a, b], 1) for two channels_last maps with channel counts divisible by 4."""
@@ -953,3 +983,6 @@ def avg_pool2x2_nhwc(x: Tensor) -> Tensor:
 def _(x):
     y = x.new_empty((x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2))
     return y.contiguous(memory_format=torch.channels_last)
+
+
+avg_pool2x2_nhwc.register_autograd(_ap_backward, setup_context=_ap_setup)

@@ -26,6 +26,7 @@ ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--nchw", action="store_true", help="keep NCHW memory (default: channels_last)")
+ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark (algorithm autotuning)")
 ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch.profiler)")
 a = ap.parse_args()
 
@@ -34,6 +35,7 @@ rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 torch.cuda.set_device(local)
+torch.backends.cudnn.benchmark = bool(a.cudnn_benchmark)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)

@@ -766,3 +766,18 @@ def test_cat2_matches_torch_cat():
     assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, torch.cat([a, b], 1))
     with pytest.raises(RuntimeError):
         torch.ops.mrfa.cat2(a.contiguous(), b)
+
+
+def test_avg_pool2x2_nhwc_forward_backward():
+    torch.manual_seed(51)
+    x = torch.randn(2, 8, 6, 10, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    y = torch.ops.mrfa.avg_pool2x2_nhwc(x)
+    yr = F.avg_pool2d(xr, (2, 2))
+    close(y, yr, 1e-6)
+    g = torch.randn_like(yr)
+    y.backward(g)
+    yr.backward(g)
+    close(x.grad, xr.grad, 1e-7)
+    torch.library.opcheck(torch.ops.mrfa.avg_pool2x2_nhwc, (x.detach().requires_grad_(True),),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
