@@ -13,7 +13,8 @@
 //                          reads (bank-conflict-free: a warp store covers 8 rows x 4 words);
 //   MMA       (warp 12)    one thread issues K/8 tcgen05.mma per tile into a double-buffered
 //                          TMEM accumulator; weights stay resident in shared memory;
-//   epilogue  (warps 8-11) TMEM -> registers -> ReLU -> 32-byte vector stores, NHWC.  The bias rides
+//   epilogue  (warps 8-11) TMEM -> registers -> ReLU -> swizzled staging -> TMA bulk stores, NHWC
+//                          (tiles enumerate pixels in NHWC order: pixel = tile * 128 + row).  The bias rides
 //                          in two spare K columns (TF32 hi + lo against a column of ones).
 // HBM-bound on the output write: algorithmic bytes per pixel = 4 * (Cin + Cout).
 #include <stdlib.h>
@@ -44,10 +45,10 @@ template <int CIN, int COUT> struct ConvSmallCfg {
   static constexpr uint32_t kPatchBytes = (((kPatchElems + kTileM * CIN) * 4 + 15) / 16) * 16;   // + zero tail for K padding
   static_assert(kBiasK + 2 <= kKP, "no free K columns for the bias");
   static constexpr uint32_t kTmemCols = 2 * COUT;                             // power of two >= 32
-  // epilogue through TMA bulk stores (one 32 x 32 fp32 box per warp and 32-channel chunk) where the staging
-  // fits in shared memory; 32-byte vector stores from registers otherwise
-  static constexpr bool kTmaStore = COUT == 128;
-  static constexpr uint32_t kStageBytes = kTmaStore ? 4 * 4096 : 0;
+  // epilogue through TMA bulk stores: per warp and 32-channel chunk one (kStageRows pixels x 32 channels) fp32 box
+  static constexpr int kStageRows = COUT == 128 ? 32 : 16;                     // rows per staged box (what fits in smem)
+  static constexpr uint32_t kStageWarpBytes = kStageRows * 128;
+  static constexpr uint32_t kStageBytes = 4 * kStageWarpBytes;
   static constexpr uint32_t kSmemBytes = 1024 + 2 * kABytes + kBBytes + kStageBytes + kPatchBytes + kKP * 4 + 128;
 };
 
@@ -89,7 +90,7 @@ conv7x7_small_kernel(const ConvSmallParams prm, const __grid_constant__ CUtensor
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                                   // [2][kKBlocks][128 x 128 B]
   uint8_t* smem_b = smem + 2 * Cfg::kABytes;                // [kKBlocks][COUT x 128 B]
-  uint8_t* smem_st = smem_b + Cfg::kBBytes;                 // [4 warps][32 rows x 128 B] (TMA-store staging)
+  uint8_t* smem_st = smem_b + Cfg::kBBytes;                 // [4 warps][kStageRows x 128 B] (TMA-store staging)
   float* patch = reinterpret_cast<float*>(smem_st + Cfg::kStageBytes);
   int* koff = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(patch) + Cfg::kPatchBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(koff + Cfg::kKP);
@@ -263,7 +264,6 @@ conv7x7_small_kernel(const ConvSmallParams prm, const __grid_constant__ CUtensor
     uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < prm.tiles; t += gridDim.x, ++it) {
       const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
-      float* dst = prm.y + (t * kTileM + ew * 32 + lane) * COUT;      // tiles enumerate pixels in NHWC order
       mbar_wait(&t_full[s], ph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + s * COUT;
@@ -281,33 +281,31 @@ conv7x7_small_kernel(const ConvSmallParams prm, const __grid_constant__ CUtensor
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));   // bias came with the MMA
         }
-        if constexpr (Cfg::kTmaStore) {
-          // stage 32 pixels x 32 channels (128-byte rows, SWIZZLE_128B) and hand the box to the TMA engine
-          const uint32_t st = smem_u32(smem_st + ew * 4096);
-          if (lane == 0) tma_store_wait_read();          // the previous box has left shared memory
-          __syncwarp();
+        {
+          // stage kStageRows pixels x 32 channels (128-byte rows, SWIZZLE_128B) and hand the box to the TMA engine
+          const uint32_t st = smem_u32(smem_st + ew * Cfg::kStageWarpBytes);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(st + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
-                         v[4 * j + 3]);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(prm.debug & 1)) {
-            tma_store_3d(&map_y, smem_st + ew * 4096, ch * 32, (int)(t * kTileM + ew * 32), 0);
-            tma_store_commit();
-          }
-        } else {
+          for (int h = 0; h < 32; h += Cfg::kStageRows) {
+            if (lane == 0) tma_store_wait_read();        // the previous box has left shared memory
+            __syncwarp();
+            if (lane >= h && lane < h + Cfg::kStageRows) {
+              const uint32_t row = (uint32_t)(lane - h);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[q * 8 + j];
-            if (!(prm.debug & 1)) st_global_v8(dst + ch * 32 + q * 8, o);
+              for (int j = 0; j < 8; ++j)
+                st_shared_v4(st + row * 128u + (uint32_t)((j ^ (row & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
+                             v[4 * j + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(prm.debug & 1)) {
+              tma_store_3d(&map_y, smem_st + ew * Cfg::kStageWarpBytes, ch * 32, (int)(t * kTileM + ew * 32 + h), 0);
+              tma_store_commit();
+            }
           }
         }
       }
     }
-    if (Cfg::kTmaStore && lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -331,13 +329,13 @@ static int launch_conv_small(const ConvSmallParams& prm, int sm_count, cudaStrea
   const int64_t grid = prm.tiles < sm_count ? prm.tiles : sm_count;
   CUtensorMap map_y;
   memset(&map_y, 0, sizeof(map_y));
-  if (Cfg::kTmaStore) {
+  {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return MRFA_E_DRIVER;
     const cuuint64_t pixels = (cuuint64_t)prm.tiles * kTileM;
     cuuint64_t dims[3] = {(cuuint64_t)COUT, pixels, 1};
     cuuint64_t strides[2] = {(cuuint64_t)COUT * 4, pixels * COUT * 4};
-    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t box[3] = {32, (cuuint32_t)Cfg::kStageRows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, prm.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
