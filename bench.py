@@ -290,6 +290,7 @@ def run_ours(args):
         sec = k["total_ms"] / 1e3
         e = {"kernel": name, "launches": k["launches"], "total_ms": round(k["total_ms"], 4),
              "share_of_step": round(k["total_ms"] / dev_ms, 4), "avg_ms": round(k["total_ms"] / max(1, k["calls"]), 5)}
+        e["algorithmic_bytes_per_launch"] = round(k["bytes"] / max(1, k["calls"]))
         if sec > 0:
             e["hbm_gbs"] = round(k["bytes"] / sec / 1e9, 1)
             e["hbm_frac"] = round(k["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4)
@@ -305,16 +306,19 @@ def run_ours(args):
                 "avg_pool2x2")
     hot = [k for k in klist if k["kernel"] in hot_path]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    traffic_tbl = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    # the ncu capture was taken at the default workload; other shapes report traffic = null
+    traffic_tbl = json.load(open(tpath)) if (os.path.exists(tpath) and args.batch == 64 and args.size == 256) else {}
 
     def roof(entry):
         if entry is None:
             return None
         t = traffic_tbl.get(entry["kernel"])
-        per_step = entry["launches"] // max(1, args.steps)
+        per_step = max(1, entry["launches"] // max(1, args.steps))
         base = {"kernel": entry["kernel"], "launches_per_step": per_step, "avg_launch_ms": entry["avg_ms"],
-                "traffic": t, "traffic_scope": "ncu dram__bytes_read+write summed over this kernel's launches in one step "
-                                               "(B=64, 256x256; profiles/r1_hot_kernels_ncu.md)" if t else None}
+                "algorithmic_bytes_per_launch": entry["algorithmic_bytes_per_launch"],
+                "traffic": round(t / per_step) if t else None,
+                "traffic_scope": "average per launch: ncu dram__bytes_read+write summed over this kernel's launches in one step "
+                                 "(B=64, 256x256; profiles/r1_hot_kernels_ncu.md), divided by launches_per_step" if t else None}
         if entry["kernel"] == "corr_volume":
             base.update({"bound": "tensor", "achieved": entry["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": entry["tensor_frac"], "peak_source": pk["source"] + " (sustained bf16)",
