@@ -140,12 +140,8 @@ class UpBlock2d(_ConvNormAct):
                 and tuple(c.stride) == (1, 1) and c.groups == 1 and c.out_channels % 4 == 0
                 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
 
-    def forward_subpixel(self, x):
-        """relu(norm(conv(upsample_x2_nearest(x)))) as ONE 2x2 convolution on the padded low-res
-        input with 4*Cout phase-major outputs (B, 4*Cout, H+1, W+1): output parity (a,b) of pixel
-        (Y,X) lives at [Y//2 + a, X//2 + b, (2a+b)*Cout + c].  3x3 rows {0,1,2} over a nearest x2
-        map collapse to low-res rows {y-1, y, y} (a=0) or {y, y, y+1} (a=1): 16/36 of the FLOPs and
-        no upsampled tensor.  Consumed by mrfa::occlusion_blend_subpixel."""
+    def subpixel_weights(self):
+        """(4*Cout, Cin, 2, 2) weights and (4*Cout,) bias of the sub-pixel form (BatchNorm folded), cached."""
         c, n = self.conv, self.norm
         if not hasattr(self, "_sub"):
             self._sub = _Cache()
@@ -156,7 +152,15 @@ class UpBlock2d(_ConvNormAct):
             w2 = torch.cat([torch.einsum("pi,ocij,qj->ocpq", R[a], w, R[q]) for a in (0, 1) for q in (0, 1)], dim=0)
             return w2.contiguous(memory_format=torch.channels_last), b.repeat(4).contiguous()
 
-        w2, b2 = self._sub.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), build)
+        return self._sub.get((c.weight, c.bias, n.weight, n.bias, n.running_mean, n.running_var), build)
+
+    def forward_subpixel(self, x):
+        """relu(norm(conv(upsample_x2_nearest(x)))) as ONE 2x2 convolution on the padded low-res
+        input with 4*Cout phase-major outputs (B, 4*Cout, H+1, W+1): output parity (a,b) of pixel
+        (Y,X) lives at [Y//2 + a, X//2 + b, (2a+b)*Cout + c].  3x3 rows {0,1,2} over a nearest x2
+        map collapse to low-res rows {y-1, y, y} (a=0) or {y, y, y+1} (a=1): 16/36 of the FLOPs and
+        no upsampled tensor.  Consumed by mrfa::occlusion_blend_subpixel."""
+        w2, b2 = self.subpixel_weights()
         # 2x2 kernel with padding 1: (H, W) -> (H+1, W+1), the zero border supplied by the convolution itself
         return torch.cudnn_convolution_relu(x, w2, b2, (1, 1), (1, 1), (1, 1), 1)
 

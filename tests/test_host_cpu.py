@@ -141,3 +141,30 @@ print("PATCHED")
 """
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
     assert res.returncode == 0 and "PATCHED" in res.stdout, res.stderr[-1500:]
+
+
+def test_subpixel_and_space_to_depth_weight_transforms_cpu():
+    """Host-side algebra behind two inference rewrites, checked with stock CPU convolutions:
+    (1) UpBlock2d (util.py:160-177): conv3x3(nearest_x2(x)) == de-interleave(conv2x2_pad1(x)) with 4*Cout phase-major
+        outputs;  (2) the generator's final 7x7 convolution (generator.py:66) == pixel_shuffle(conv3x3(space_to_depth_4(x)))."""
+    import torch
+    import torch.nn.functional as F
+    from mrfa_b200 import blocks, synthetic as syn
+    torch.manual_seed(5)
+    up = syn.fill_state_dict_(blocks.UpBlock2d(6, 8, kernel_size=3, padding=1)).eval()
+    x = torch.randn(2, 6, 5, 7)
+    with torch.no_grad():
+        ref = up(x)                                                          # plain path on CPU
+        w2, b2 = up.subpixel_weights()
+        y2 = F.relu(F.conv2d(x, w2, b2, padding=1))                          # (2, 32, 6, 8)
+        C = 8
+        out = torch.empty_like(ref)
+        for a in (0, 1):
+            for b in (0, 1):
+                ph = y2[:, (2 * a + b) * C:(2 * a + b + 1) * C]
+                out[:, :, a::2, b::2] = ph[:, :, a:a + 5, b:b + 7]           # pixel (Y,X) <- [Y//2 + a, X//2 + b]
+        assert torch.allclose(out, ref, atol=1e-5)
+        gen = syn.fill_state_dict_(blocks.OcclusionAwareGenerator(3, 16, 64, 3)).eval()
+        z = torch.randn(2, 16, 12, 20)
+        zs = z.reshape(2, 16, 3, 4, 5, 4).permute(0, 3, 5, 1, 2, 4).reshape(2, 256, 3, 5)   # channel (iy*4+ix)*16 + c
+        assert torch.allclose(gen._final_s2d(zs), gen.final(z), atol=1e-5)
