@@ -28,6 +28,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# kernels of the hot path proper: timed inside the timed region, candidates for `roofline`
+HOT_PATH = ("dual_warp_fwd", "grid_sample_fwd", "corr_volume", "corr_lookup_fwd", "corr_pack", "dense_motion_prior",
+            "tps_motion_prior", "tps_solve", "kp2gaussian", "coords_grid", "make_coordinate_grid", "prior_to_flow",
+            "avg_pool2x2")
 METRIC = "frame-pairs/sec (refinement forward, 256x256)"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 
@@ -241,11 +245,14 @@ def run_ours(args):
             out = forward(resident)
         sync_all()
 
-        # ---- device-resident timing (value) + per-kernel roofline accounting ----
+        # ---- device-resident timing (value).  Inside the timed region only the hot-path kernels (SURVEY.md
+        #      8(a), ~30 launches per step) are bracketed by CUDA events -- that is what `roofline` reports;
+        #      every other launch of this library is counted, not timed, so the instrumentation does not
+        #      inflate the step.  A second, fully instrumented pass of the same K steps fills kernels[]. ----
         sampler = ClockSampler(local)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ops.KernelTimer() as timer:
+        with ops.KernelTimer(only=HOT_PATH) as timer:
             sync_all()
             e0.record()
             for _ in range(args.steps):
@@ -254,19 +261,57 @@ def run_ours(args):
             sync_all()
         dev_ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
-        kernels = timer.summary()
+        hot_kernels = timer.summary()
+        launch_counts = dict(timer.counts)
         l1 = (out - resident["drv"]).abs().sum().double()
+        e0b, e1b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ops.KernelTimer() as timer_all:
+            e0b.record()
+            for _ in range(args.steps):
+                forward(resident)
+            e1b.record()
+            sync_all()
+        instrumented_ms = e0b.elapsed_time(e1b)
+        kernels = timer_all.summary()
+        kernels.update(hot_kernels)                        # hot-path rows: the numbers of the timed region
 
-        # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the predicted frames ----
-        for _ in range(2):
-            d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "drv"}
-            out_h.copy_(forward(d), non_blocking=True)
+        # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the predicted frames, every step.
+        #      Three streams: the next step's inputs are uploaded and the previous step's frames downloaded
+        #      while the current step computes (double-buffered pinned output) ----
+        cur = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        out_hh = [out_h, torch.empty_like(out_h).pin_memory()]
+
+        def stage():
+            with torch.cuda.stream(s_in):
+                d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "drv"}
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            return d, ev
+
+        def e2e_loop(n):
+            d, ev = stage()
+            for i in range(n):
+                cur.wait_event(ev)
+                for t in d.values():
+                    t.record_stream(cur)
+                nxt = stage() if i + 1 < n else None        # overlaps with this step's compute
+                o = forward(d)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    out_hh[i & 1].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+                if nxt is not None:
+                    d, ev = nxt
+            cur.wait_stream(s_out)                          # the last download is inside the timed region
+
+        e2e_loop(2)
         sync_all()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for _ in range(args.steps):
-            d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "drv"}
-            out_h.copy_(forward(d), non_blocking=True)
+        e2e_loop(args.steps)
         e3.record()
         sync_all()
         e2e_ms = e2.elapsed_time(e3)
@@ -301,10 +346,7 @@ def run_ours(args):
     ours_ms = sum(k["total_ms"] for k in kernels.values())
     # roofline: the dominant kernel of the hot path proper; the kernels of the
     # "next" rows 8(f) (fused elementwise helpers, small-channel convolution, cat) are listed in kernels[] only
-    hot_path = ("dual_warp_fwd", "grid_sample_fwd", "corr_volume", "corr_lookup_fwd", "corr_pack", "dense_motion_prior",
-                "tps_motion_prior", "tps_solve", "kp2gaussian", "coords_grid", "make_coordinate_grid", "prior_to_flow",
-                "avg_pool2x2")
-    hot = [k for k in klist if k["kernel"] in hot_path]
+    hot = [k for k in klist if k["kernel"] in HOT_PATH]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     # the ncu capture was taken at the default workload; other shapes report traffic = null
     traffic_tbl = json.load(open(tpath)) if (os.path.exists(tpath) and args.batch == 64 and args.size == 256) else {}
@@ -337,8 +379,10 @@ def run_ours(args):
             "config": workload_config(args, B, world), "clocks": clocks,
             "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": sum(k["launches"] for k in kernels.values()),
+            "gpu_launches": sum(launch_counts.values()),
             "roofline": roofline, "roofline_corr": roofline_corr, "kernels": klist,
+            "kernels_note": "hot-path rows (SURVEY 8a) are timed inside the timed region; the other rows come from a "
+                            f"second, fully instrumented pass of the same {args.steps} steps ({instrumented_ms / args.steps:.2f} ms/step)",
             "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
             "recon_l1_mean": float(sums[0] / sums[1]), "peaks": pk}
     if not args.no_cpu_baseline:

@@ -79,8 +79,12 @@ class KernelTimer:
     While installed (``with KernelTimer() as t:``) every C-ABI launch is bracketed by two events
     recorded on the current stream and tagged with its algorithmic bytes / flops."""
 
-    def __init__(self):
+    def __init__(self, only=None):
+        """`only`: names to bracket with events; every other launch is merely counted (no events, so the
+        instrumentation does not perturb a timed region)."""
         self.records = {}
+        self.counts = {}
+        self.only = None if only is None else frozenset(only)
 
     def __enter__(self):
         global _TIMER
@@ -111,12 +115,15 @@ class _timed:
         self.name, self.nbytes, self.flops, self.launches = name, nbytes, flops, launches
 
     def __enter__(self):
+        self.start = None
         if _TIMER is not None:
-            self.start = torch.cuda.Event(enable_timing=True)
-            self.start.record()
+            _TIMER.counts[self.name] = _TIMER.counts.get(self.name, 0) + self.launches
+            if _TIMER.only is None or self.name in _TIMER.only:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record()
 
     def __exit__(self, *exc):
-        if _TIMER is not None and exc[0] is None:
+        if _TIMER is not None and self.start is not None and exc[0] is None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
             _TIMER.records.setdefault(self.name, []).append((self.start, end, self.nbytes, self.flops, self.launches))
