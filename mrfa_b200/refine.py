@@ -17,6 +17,7 @@ from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_
 from .corr import CorrPyramid
 
 
+SPLIT_K = os.environ.get("MRFA_SPLIT_K", "0") != "0"            # conv(cat([a, b])) as two accumulating convolutions
 CAT_SLICES = os.environ.get("MRFA_CAT_SLICES", "1") != "0"       # A/B switch: coarse warps written into the decoder's cat buffers
 FUSED_CARRY = os.environ.get("MRFA_FUSED_CARRY", "1") != "0"     # A/B switch for the fused level hand-over
 
@@ -26,6 +27,12 @@ def _resize(x, size):
     if x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
         return torch.ops.mrfa.resize_bilinear(x, int(size[0]), int(size[1]), 0)
     return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+
+
+def _like(t, ref):
+    """Contiguous copy of a weight slice in the memory format of `ref`."""
+    fmt = torch.channels_last if (ref.dim() == 4 and ref.is_contiguous(memory_format=torch.channels_last)) else torch.contiguous_format
+    return t.contiguous(memory_format=fmt)
 
 
 def _cat(module, a, b):
@@ -47,6 +54,21 @@ class BasicMotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 96, 128 - 2, 3, padding=1)
 
+    def _padded_conv(self):
+        """self.conv with two zero filters appended (126 -> 128 output channels), cached."""
+        if not hasattr(self, "_pad"):
+            self._pad = _Cache()
+        cv = self.conv
+
+        def build():
+            w = torch.cat([cv.weight, cv.weight.new_zeros((2,) + tuple(cv.weight.shape[1:]))], dim=0)
+            b = torch.cat([cv.bias, cv.bias.new_zeros(2)])
+            if cv.weight.is_contiguous(memory_format=torch.channels_last):
+                w = w.contiguous(memory_format=torch.channels_last)
+            return w, b
+
+        return self._pad.get((cv.weight, cv.bias), build)
+
     def forward(self, delta_flow, corr):
         if corr.shape[-2:] != delta_flow.shape[-2:]:
             # correlation features still at the basic resolution (levels above it, raft.py:241-243):
@@ -58,23 +80,26 @@ class BasicMotionEncoder(nn.Module):
         else:
             c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
         f = conv_relu(self.convf2, conv_relu(self.convf1, delta_flow))
+        if SPLIT_K and fast_path(self, c) and self.conv.out_channels + delta_flow.shape[1] == 128:
+            # conv(cat([c, f])) = conv(c; W[:, :96]) + conv(f; W[:, 96:]): the second convolution accumulates onto the
+            # first (cuDNN's fused add + bias + ReLU), so the cat pass disappears into two compute-bound kernels
+            w, b = self._padded_conv()
+            if not hasattr(self, "_split"):
+                self._split = _Cache()
+            nc = c.shape[1]
+            wa, wb = self._split.get((w,), lambda: (_like(w[:, :nc], w), _like(w[:, nc:], w)))
+            cv = self.conv
+            z = torch.cudnn_convolution(c, wa, cv.padding, cv.stride, cv.dilation, cv.groups, torch.backends.cudnn.benchmark, False, True)
+            y = torch.cudnn_convolution_add_relu(f, wb, z, 1.0, b, cv.stride, cv.padding, cv.dilation, cv.groups)
+            y[:, 126:128] = delta_flow
+            return y
         cf = _cat(self, c, f)
         if fast_path(self, cf) and self.conv.out_channels + delta_flow.shape[1] == 128:
             # 126 output channels force cuDNN through pad / un-pad copies of the whole map: run the
             # convolution with two zero filters appended (128 channels) and drop the flow into
             # those two channels -- same values as cat([relu(conv(.)), flow]) without the cat.
-            if not hasattr(self, "_pad"):
-                self._pad = _Cache()
             cv = self.conv
-
-            def build():
-                w = torch.cat([cv.weight, cv.weight.new_zeros((2,) + tuple(cv.weight.shape[1:]))], dim=0)
-                b = torch.cat([cv.bias, cv.bias.new_zeros(2)])
-                if cv.weight.is_contiguous(memory_format=torch.channels_last):
-                    w = w.contiguous(memory_format=torch.channels_last)
-                return w, b
-
-            w, b = self._pad.get((cv.weight, cv.bias), build)
+            w, b = self._padded_conv()
             y = torch.cudnn_convolution_relu(cf, w, b, cv.stride, cv.padding, cv.dilation, cv.groups)
             y[:, 126:128] = delta_flow
             return y
@@ -94,8 +119,10 @@ class RefineFlow(nn.Module):
         self.convo2 = nn.Conv2d(128, 1, 3, padding=1)
 
     def forward(self, m_f, warp_f):
-        inp = _cat(self, m_f, conv_relu(self.convc1, warp_f))
-        if fast_path(self, inp):
+        ctx = conv_relu(self.convc1, warp_f)
+        split = SPLIT_K and fast_path(self, ctx)
+        inp = None if split else _cat(self, m_f, ctx)
+        if fast_path(self, ctx):
             # conv1 | convo1 read the same 256-channel input: run them as one 256 -> 256 convolution
             # (one pass over `inp`), then conv2 / convo2 as one block-diagonal 256 -> 4 convolution
             # whose channels are [flow_x, flow_y, occlusion, 0] -- identical arithmetic per output.
@@ -117,7 +144,17 @@ class RefineFlow(nn.Module):
 
             w1, b1, w2, b2 = self._merged.get((self.conv1.weight, self.conv1.bias, self.convo1.weight, self.convo1.bias,
                                                self.conv2.weight, self.conv2.bias, self.convo2.weight, self.convo2.bias), build)
-            hdn = torch.cudnn_convolution_relu(inp, w1, b1, self.conv1.stride, self.conv1.padding, self.conv1.dilation, 1)
+            c1 = self.conv1
+            if split:
+                # (conv1 | convo1)(cat([m_f, ctx])) as two accumulating convolutions: no cat pass (see BasicMotionEncoder)
+                if not hasattr(self, "_split"):
+                    self._split = _Cache()
+                nm = m_f.shape[1]
+                wa, wb = self._split.get((w1,), lambda: (_like(w1[:, :nm], w1), _like(w1[:, nm:], w1)))
+                z = torch.cudnn_convolution(m_f, wa, c1.padding, c1.stride, c1.dilation, 1, torch.backends.cudnn.benchmark, False, True)
+                hdn = torch.cudnn_convolution_add_relu(ctx, wb, z, 1.0, b1, c1.stride, c1.padding, c1.dilation, 1)
+            else:
+                hdn = torch.cudnn_convolution_relu(inp, w1, b1, c1.stride, c1.padding, c1.dilation, 1)
             out = F.conv2d(hdn, w2, b2, self.conv2.stride, self.conv2.padding)
             return out[:, :3], inp
         flow = self.conv2(conv_relu(self.conv1, inp))
