@@ -17,7 +17,7 @@ from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_
 from .corr import CorrPyramid
 
 
-SPLIT_K = os.environ.get("MRFA_SPLIT_K", "0") != "0"            # conv(cat([a, b])) as two accumulating convolutions
+SPLIT_K = os.environ.get("MRFA_SPLIT_K", "1") != "0"            # conv(cat([a, b])) as two accumulating convolutions
 CAT_SLICES = os.environ.get("MRFA_CAT_SLICES", "1") != "0"       # A/B switch: coarse warps written into the decoder's cat buffers
 FUSED_CARRY = os.environ.get("MRFA_FUSED_CARRY", "1") != "0"     # A/B switch for the fused level hand-over
 
@@ -89,7 +89,7 @@ class BasicMotionEncoder(nn.Module):
             nc = c.shape[1]
             wa, wb = self._split.get((w,), lambda: (_like(w[:, :nc], w), _like(w[:, nc:], w)))
             cv = self.conv
-            z = torch.cudnn_convolution(c, wa, cv.padding, cv.stride, cv.dilation, cv.groups, torch.backends.cudnn.benchmark, False, True)
+            z = torch.cudnn_convolution(c, wa, cv.padding, cv.stride, cv.dilation, cv.groups, torch.backends.cudnn.benchmark, False, torch.backends.cudnn.allow_tf32)
             y = torch.cudnn_convolution_add_relu(f, wb, z, 1.0, b, cv.stride, cv.padding, cv.dilation, cv.groups)
             y[:, 126:128] = delta_flow
             return y
@@ -151,7 +151,7 @@ class RefineFlow(nn.Module):
                     self._split = _Cache()
                 nm = m_f.shape[1]
                 wa, wb = self._split.get((w1,), lambda: (_like(w1[:, :nm], w1), _like(w1[:, nm:], w1)))
-                z = torch.cudnn_convolution(m_f, wa, c1.padding, c1.stride, c1.dilation, 1, torch.backends.cudnn.benchmark, False, True)
+                z = torch.cudnn_convolution(m_f, wa, c1.padding, c1.stride, c1.dilation, 1, torch.backends.cudnn.benchmark, False, torch.backends.cudnn.allow_tf32)
                 hdn = torch.cudnn_convolution_add_relu(ctx, wb, z, 1.0, b1, c1.stride, c1.padding, c1.dilation, 1)
             else:
                 hdn = torch.cudnn_convolution_relu(inp, w1, b1, c1.stride, c1.padding, c1.dilation, 1)

@@ -15,6 +15,7 @@ SWITCHES = [
     ("MRFA_SMALL_CONV", "tcgen05 TF32 kernel for the 7x7 small-channel convolutions"),
     ("MRFA_S2D_FINAL", "final 7x7 convolution as 3x3 over a 4x4 space-to-depth layout"),
     ("MRFA_HG_SUBPIXEL", "hourglass up-blocks as sub-pixel convolutions + shuffle-cat kernel"),
+    ("MRFA_SPLIT_K", "update-block cat+conv pairs as two accumulating convolutions (no cat pass)"),
     ("MRFA_CAT_SLICES", "coarse warp / blend written into the decoder's cat buffers"),
     ("MRFA_FAST_CONV", "all conv-block fusions (BN folding, fused bias+ReLU, blends, ...)"),
 ]
