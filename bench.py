@@ -126,6 +126,16 @@ def cpu_forward(dm, rf, src, kp_s, kp_d, bg):
     return rf(kp_s["kp"], kp_d["kp"], dense, img=dm.down(src), img_full=src)[0]
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def time_cpu_oracle(cfg, size, batch, steps, warmup):
     """The reference's CPU path (oracle port, stock torch CPU ops = the reference's arithmetic)."""
     import torch
@@ -146,7 +156,7 @@ def time_cpu_oracle(cfg, size, batch, steps, warmup):
                 times.append(dt)
     total = sum(times)
     return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
-            "best_pairs_s": batch / min(times)}
+            "best_pairs_s": batch / min(times), "median_pairs_s": batch / sorted(times)[len(times) // 2], "cpu_model": cpu_model()}
 
 
 def run_reference(args):
@@ -169,7 +179,8 @@ def run_reference(args):
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args, args.batch, max(1, args.gpus)),
-            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                             "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"]},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -388,6 +399,7 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         r = time_cpu_oracle(cfg, S, 1, 3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                                "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"],
                                 "sample": f"1 pair per step, 3 timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step), "
                                           f"oracle torch-CPU port of the reference path, {r['cores']} threads"}
     print(json.dumps(line), flush=True)
