@@ -81,7 +81,7 @@ int mrfa_grid_sample_bwd(const float* grad_out, const float* in, const float* gr
  * and coarse/prior (normalised grid, align_corners=False, raft.py:271).  flow (B,2,Ho,Wo)
  * planar; prior_grid (B,Ho,Wo,2).  Reads `in` once from HBM.  coarse_pixel_stride (NHWC only; 0 = C): element
  * stride between pixels of out_coarse, so the coarse warp can be written straight into a channel slice of the
- * buffer the decoder would otherwise build with cat([y, warp_c]) (generator.py:58-59).                  */
+ * buffer the decoder would otherwise build with cat([y, warp_c]) (generator.py:51,60).                  */
 int mrfa_dual_warp_fwd(const float* in, const float* flow, const float* prior_grid,
                        float* out_refined, float* out_coarse,
                        int N, int C, int H, int W, int channels_last, int64_t coarse_pixel_stride,
@@ -219,7 +219,7 @@ int mrfa_occlusion_blend(const float* a, const float* b, const float* occ, float
  * b2 (N,4C,H+1,W+1) NHWC, phase (Y&1, X&1) of pixel (Y,X) at b2[n, Y/2+(Y&1), X/2+(X&1), (2(Y&1)+(X&1))*C+c];
  * occ (N,1,2H,2W).  C % 4 == 0.  out_block r = 1: y plain NHWC; r > 1 (dividing 2H and 2W): y in r x r
  * space-to-depth order, pixel (Y,X) at y[n, Y/r, X/r, ((Y%r)*r + X%r)*C + c] = an (N, r*r*C, 2H/r, 2W/r) NHWC
- * tensor -- the layout in which the generator's final 7x7 convolution (generator.py:66) is a 3x3 one.
+ * tensor -- the layout in which the generator's final 7x7 convolution (generator.py:32,61) is a 3x3 one.
  * out_pixel_stride (out_block 1 only; 0 = C): element stride between pixels of y (a channel slice of a wider
  * NHWC buffer, see mrfa_dual_warp_fwd).                                                         */
 int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* occ, float* y,
@@ -236,11 +236,11 @@ int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, i
 /* Backward of mrfa_avg_pool2x2_nhwc: grad_y (N,C,H/2,W/2) -> grad_x (N,C,H,W), both NHWC; H, W even, C % 4 == 0. */
 int mrfa_avg_pool2x2_nhwc_bwd(const float* grad_y, float* grad_x, int N, int C, int H, int W, mrfa_stream_t stream);
 
-/* cat([a, b], dim=1) of two NHWC maps over `pixels` = N*H*W pixels (raft.py:64 cat([cor, flo]), :82
+/* cat([a, b], dim=1) of two NHWC maps over `pixels` = N*H*W pixels (raft.py:66 cat([cor, flo]), :83
  * cat([motion_feature, context])): a (.., Ca), b (.., Cb) -> y (.., Ca+Cb); Ca % 4 == Cb % 4 == 0, 16-byte aligned. */
 int mrfa_cat2_nhwc(const float* a, const float* b, float* y, int64_t pixels, int Ca, int Cb, mrfa_stream_t stream);
 
-/* Hourglass decoder step `out = cat([up_block(out), skip], dim=1)` (util.py:246-278) with the up-block evaluated as
+/* Hourglass decoder step `out = cat([up_block(out), skip], dim=1)` (util.py:239-263) with the up-block evaluated as
  * the sub-pixel 2x2 convolution (see mrfa_occlusion_blend_subpixel): b2 (N,4C,H+1,W+1) NHWC phase-major;
  * skip (N,Cs,2H,2W) with element strides {sn, sy, sx, sc}; y (N,C+Cs,2H,2W) NHWC = [shuffle(b2), skip].         */
 int mrfa_subpixel_shuffle_cat(const float* b2, const float* skip, mrfa_grid_strides_t skip_strides, float* y,
@@ -248,7 +248,7 @@ int mrfa_subpixel_shuffle_cat(const float* b2, const float* skip, mrfa_grid_stri
 
 /* 7x7 / stride 1 / pad 3 convolution with 2-3 input channels, + bias (BatchNorm pre-folded by the caller) and
  * optional ReLU, as a TF32 implicit GEMM on the tcgen05 tensor cores: BasicMotionEncoder.convf1 (2 -> 128,
- * raft.py:57) and the generator's `first` block (3 -> 64, generator.py:23).  Supported (Cin, Cout): (2,128), (3,64);
+ * raft.py:56,63) and the generator's `first` block (3 -> 64, generator.py:13).  Supported (Cin, Cout): (2,128), (3,64);
  * W % 128 == 0.  x (B,Cin,H,W) with element strides xs {sn, sy, sx, sc}; w_packed (Cout, KP) with
  * KP = mrfa_conv7x7_small_kpad(Cin), element [o][(ky*7+kx)*Cin + c] = weight[o][c][ky][kx], zero padded;
  * bias (Cout) or NULL; y (B,H,W,Cout) NHWC, 32-byte aligned.  sm_count sizes the persistent grid.            */

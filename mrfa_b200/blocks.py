@@ -71,7 +71,7 @@ SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for m
 
 def _small7_ok(conv: nn.Conv2d, x: torch.Tensor) -> bool:
     """7x7 / pad 3 / stride 1 with 2-3 input channels: served by the tcgen05 TF32 kernel instead of cuDNN's
-    legacy indexed path (raft.py:57 convf1, generator.py:23 first)."""
+    legacy indexed path (raft.py:56,63 convf1, generator.py:13 first)."""
     return (SMALL_CONV and tuple(conv.kernel_size) == (7, 7) and tuple(conv.padding) == (3, 3)
             and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
             and ops.conv7x7_small_ok(x, conv.in_channels, conv.out_channels))

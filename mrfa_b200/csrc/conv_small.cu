@@ -1,7 +1,7 @@
 // 7x7 / stride 1 / pad 3 convolutions with 2-3 input channels, fused with bias (+ folded
-// BatchNorm) and ReLU: BasicMotionEncoder.convf1 (2 -> 128, raft.py:57, at every refinement
-// level up to 256x256) and the generator's `first` SameBlock2d (3 -> 64, generator.py:23 /
-// util.py:160-176).  These are callers on either side of the hot path: the
+// BatchNorm) and ReLU: BasicMotionEncoder.convf1 (2 -> 128, raft.py:56,63, at every refinement
+// level up to 256x256) and the generator's `first` SameBlock2d (3 -> 64, generator.py:13 /
+// util.py:199-214).  These are callers on either side of the hot path: the
 // library convolution serves them with a legacy indexed kernel (2.3 ms and 1.6 ms per batch of
 // 64 at 256x256, 3-10x their output-write time).
 //

@@ -305,7 +305,7 @@ antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ we
 // y = a * occ + b2_shuffled * (1 - occ);  a, y: (N, 2H, 2W, C) NHWC;  b2: (N, H+1, W+1, 4C) NHWC.
 // out_block r > 1 writes y in r x r space-to-depth order -- pixel (Y,X) at
 // [n, Y/r, X/r, ((Y%r)*r + X%r)*C + c], i.e. an (N, r*r*C, 2H/r, 2W/r) NHWC tensor -- so the generator's final
-// 7x7 convolution (generator.py:66) can run as a 3x3 convolution with r*r*3 outputs.
+// 7x7 convolution (generator.py:32,61) can run as a 3x3 convolution with r*r*3 outputs.
 __global__ void __launch_bounds__(256)
 occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ occ,
                                 float4* __restrict__ y, int64_t n4, int C, int H, int W, int r, int64_t ostride) {
@@ -333,7 +333,7 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
 }
 
 
-// Hourglass decoder step (util.py:246-278: out = cat([up_block(out), skip], 1)) with the up-block run as
+// Hourglass decoder step (util.py:239-263: out = cat([up_block(out), skip], 1)) with the up-block run as
 // the sub-pixel 2x2 convolution above: this kernel de-interleaves the four phases of b2 into
 // channels [0, C) of the full-resolution map and copies the skip connection into [C, C+Cs) --
 // the nearest-upsampled tensor, the 3x3 convolution on it and the separate cat pass disappear.
@@ -406,7 +406,7 @@ avg_pool2x2_nhwc_bwd_kernel(const float4* __restrict__ gy, float* __restrict__ g
 
 
 // cat([a, b], dim=1) of two NHWC maps (the update block's cat([cor, flo]) and cat([motion, context]),
-// raft.py:64, :82): one float4 per thread, every warp instruction a contiguous run of one pixel row.
+// raft.py:66, :83): one float4 per thread, every warp instruction a contiguous run of one pixel row.
 // (ATen's CatArrayBatchedCopy reaches ~4 TB/s on these 2-4 GB copies.)
 __global__ void __launch_bounds__(256)
 cat2_nhwc_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y, int64_t n4, int Ca,

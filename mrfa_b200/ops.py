@@ -228,7 +228,7 @@ def dual_warp(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Te
 @torch.library.custom_op("mrfa::dual_warp_cat", mutates_args=(), device_types="cuda")
 def dual_warp_cat(inp: Tensor, flow: Tensor, prior_grid: Tensor) -> Tuple[Tensor, Tensor]:
     """dual_warp whose coarse result is written into channels [C, 2C) of a fresh (N,2C,H,W) channels_last buffer --
-    the tensor the decoder would build with cat([y, warp_c], 1) (generator.py:58-59); channels [0, C) are left for
+    the tensor the decoder would build with cat([y, warp_c], 1) (generator.py:51,60); channels [0, C) are left for
     mrfa::occlusion_blend_subpixel_into.  channels_last input only (inference path)."""
     (inp, cl), flow, prior_grid = _req_image(inp, "input"), _req(flow, "flow"), _req(prior_grid, "prior_grid")
     N, C, H, W = inp.shape

@@ -647,7 +647,7 @@ def test_equivariance_transform_matches_reference_golden(golden):
 
 @pytest.mark.parametrize("cin,cout,layout", [(2, 128, "nhwc"), (2, 128, "nchw"), (3, 64, "nchw"), (3, 64, "nhwc")])
 def test_conv7x7_small_matches_fp32_convolution(cin, cout, layout):
-    """tcgen05 TF32 implicit-GEMM 7x7 convolution (raft.py:57 convf1, generator.py:23 first) vs F.conv2d in fp32 on
+    """tcgen05 TF32 implicit-GEMM 7x7 convolution (raft.py:56,63 convf1, generator.py:13 first) vs F.conv2d in fp32 on
     the CPU.  TF32 operands (10-bit mantissa, round-to-nearest) with fp32 accumulation: 5e-3 relative."""
     m = mb()
     torch.manual_seed(31 + cin)
@@ -720,7 +720,7 @@ def test_blend_subpixel_space_to_depth_output_and_final_conv():
 
 @pytest.mark.parametrize("C,Cs,skip_cl", [(8, 12, True), (8, 5, False), (6, 13, True), (16, 0, True)])
 def test_subpixel_shuffle_cat(C, Cs, skip_cl):
-    """Hourglass decoder step (util.py:246-278) as shuffle + cat in one pass; vector and scalar paths."""
+    """Hourglass decoder step (util.py:239-263) as shuffle + cat in one pass; vector and scalar paths."""
     torch.manual_seed(43)
     N, H, W = 2, 5, 7
     b2 = torch.randn(N, 4 * C, H + 1, W + 1, device=DEV).contiguous(memory_format=torch.channels_last)

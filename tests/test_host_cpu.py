@@ -146,7 +146,7 @@ print("PATCHED")
 def test_subpixel_and_space_to_depth_weight_transforms_cpu():
     """Host-side algebra behind two inference rewrites, checked with stock CPU convolutions:
     (1) UpBlock2d (util.py:160-177): conv3x3(nearest_x2(x)) == de-interleave(conv2x2_pad1(x)) with 4*Cout phase-major
-        outputs;  (2) the generator's final 7x7 convolution (generator.py:66) == pixel_shuffle(conv3x3(space_to_depth_4(x)))."""
+        outputs;  (2) the generator's final 7x7 convolution (generator.py:32,61) == pixel_shuffle(conv3x3(space_to_depth_4(x)))."""
     import torch
     import torch.nn.functional as F
     from mrfa_b200 import blocks, synthetic as syn
