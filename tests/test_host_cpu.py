@@ -168,3 +168,25 @@ def test_subpixel_and_space_to_depth_weight_transforms_cpu():
         z = torch.randn(2, 16, 12, 20)
         zs = z.reshape(2, 16, 3, 4, 5, 4).permute(0, 3, 5, 1, 2, 4).reshape(2, 256, 3, 5)   # channel (iy*4+ix)*16 + c
         assert torch.allclose(gen._final_s2d(zs), gen.final(z), atol=1e-5)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU oracle port, the one arm that runs without a GPU) prints one JSON line
+    carrying the keys of the bench contract; run at 128x128 with one pair so it finishes in seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "128", "--steps", "1",
+                          "--warmup", "1", "--ref-batch", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"] and cb["cpu_model"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
