@@ -12,7 +12,7 @@ N=1 workload: BASELINE.json configs[1] (batch 64, 256x256, one B200).  N>1: one 
 
 Prints ONE JSON line (rank 0).  `value` is timed with the inputs resident in HBM; `e2e` times
 the same call with pinned HOST inputs (H2D inside) and the predicted frames read back (D2H).
-`--impl reference` times the CPU oracle port of the reference path on the host cores.
+`--impl reference` times the unmodified reference (vendored into oracle/_ref by oracle/build_ref.py) on the host cores.
 """
 from __future__ import annotations
 
@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep the networks in NCHW memory (default: channels_last)")
     ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark (algorithm autotuning)")
     ap.add_argument("--ref-batch", type=int, default=0, help="pairs per step of the CPU reference arm (0 = auto)")
+    ap.add_argument("--other-configs", type=int, default=1,
+                    help="also run short measurements of BASELINE.json configs 3/4/5 (celebvhq, 512x512 sweep, training step)")
+    ap.add_argument("--parity-pairs", type=int, default=2, help="pairs of the timed batch compared with the CPU reference in the same run")
     return ap.parse_args()
 
 
@@ -112,18 +115,28 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------
-def build_cpu_oracle(cfg, size):
+# CPU arm: the UNMODIFIED reference vendored into oracle/_ref by oracle/build_ref.py (kind "reference");
+# only if that copy is absent, the oracle port oracle/torch_path.py (kind "port").  Neither imports mrfa_b200.
+def build_cpu_nets(cfg, size):
+    """-> (kind, forward(src, kp_s, kp_d, bg) -> predicted frames, modules dict for load_state_dict)."""
     import torch
-    from oracle import torch_path as TP
+    from oracle import reference_arm as RA
     torch.manual_seed(0)
+    if RA.available():
+        nets = RA.build_networks(cfg, size)
+        return "reference", (lambda src, kp_s, kp_d, bg: RA.forward(nets, src, kp_s, kp_d, bg)[0]), {"dm": nets[1], "rf": nets[2]}
+    from oracle import torch_path as TP
     dm = TP.DenseMotionOracle(**cfg["dense_motion"]).eval()
     rf = TP.RaftFlowOracle(**dict(cfg["raft_flow"], size=size)).eval()
-    return dm, rf
+
+    def fwd(src, kp_s, kp_d, bg):
+        dense = dm(src, kp_d, kp_s, bg_param=bg)
+        return rf(kp_s["kp"], kp_d["kp"], dense, img=dm.down(src), img_full=src)[0]
+    return "port", fwd, {"dm": dm, "rf": rf}
 
 
-def cpu_forward(dm, rf, src, kp_s, kp_d, bg):
-    dense = dm(src, kp_d, kp_s, bg_param=bg)
-    return rf(kp_s["kp"], kp_d["kp"], dense, img=dm.down(src), img_full=src)[0]
+CPU_KIND_TEXT = {"reference": "unmodified reference modules (oracle/_ref: DenseMotionNetwork + RaftFlow, demo.py:47-73 composition)",
+                 "port": "oracle torch-CPU port of the reference path (oracle/_ref not vendored)"}
 
 
 def cpu_model():
@@ -136,13 +149,13 @@ def cpu_model():
     return "unknown"
 
 
-def time_cpu_oracle(cfg, size, batch, steps, warmup):
-    """The reference's CPU path (oracle port, stock torch CPU ops = the reference's arithmetic)."""
+def time_cpu_path(cfg, size, batch, steps, warmup):
+    """The reference's CPU implementation of the path on all host threads."""
     import torch
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    dm, rf = build_cpu_oracle(cfg, size)
+    kind, fwd, _ = build_cpu_nets(cfg, size)
     src, _ = syn.frame_pairs(batch, size, seed=0)
     kp_s, kp_d = syn.keypoints(batch, cfg["raft_flow"]["num_kp"], seed=0)
     bg = syn.bg_affine(batch) if cfg["train_params"]["bg_start"] == 0 else None
@@ -150,36 +163,43 @@ def time_cpu_oracle(cfg, size, batch, steps, warmup):
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            cpu_forward(dm, rf, src, kp_s, kp_d, bg)
+            fwd(src, kp_s, kp_d, bg)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     total = sum(times)
-    return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+    return {"value": batch * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores, "kind": kind,
             "best_pairs_s": batch / min(times), "median_pairs_s": batch / sorted(times)[len(times) // 2], "cpu_model": cpu_model()}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle port -- the
-    Python reference cannot travel to the GPU box), all host threads, on a bounded sample of
-    the workload: each step processes `ref_batch` pairs, sized from a one-pair probe so that the
-    whole --steps/--warmup run stays within a few minutes."""
+    """Reference arm: the reference's own CPU implementation of the path (the vendored, unmodified
+    reference modules), all host threads, on a bounded sample of the workload: each step processes
+    `ref_batch` pairs, sized from a one-pair probe so that the whole --steps/--warmup run stays within
+    a few minutes.  Never imports mrfa_b200 (asserted below): no product code, no CUDA library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = load_cfg(args.config)
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    probe = time_cpu_oracle(cfg, args.size, 1, 1, 1)
+    probe = time_cpu_path(cfg, args.size, 1, 1, 1)
     t1 = probe["ms_per_step"] / 1e3
     ref_batch = args.ref_batch or int(max(1, min(8, 180.0 / ((steps + warmup) * t1))))
-    r = time_cpu_oracle(cfg, args.size, ref_batch, steps, warmup)
+    r = time_cpu_path(cfg, args.size, ref_batch, steps, warmup)
+    assert "mrfa_b200" not in sys.modules, "the reference arm must not load the product"
     sample = (f"{ref_batch} pair(s) per step (bounded sample of the {args.batch}-pair batch), {steps} timed steps after "
-              f"{warmup} warm-up, oracle torch-CPU port of the reference path, {r['cores']} threads")
+              f"{warmup} warm-up, {CPU_KIND_TEXT[r['kind']]}, {r['cores']} threads")
+    config = workload_config(args, args.batch, max(1, args.gpus))
+    config.update({"reference_arm": f"CPU, fp32 (stock torch CPU ops, MKL-DNN convolutions), {r['cores']} host threads, "
+                                    f"{ref_batch} pair(s) per step; same workload definition, bounded sample",
+                   "pairs_per_step_this_arm": ref_batch, "device": "cpu"})
+    config.pop("convs", None)
+    config.pop("l2", None)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": workload_config(args, args.batch, max(1, args.gpus)),
-            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample,
+            "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
                              "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"]},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -194,13 +214,189 @@ def workload_config(args, batch, n):
             "convs": "cuDNN, TF32 allowed (PyTorch default), " + ("NCHW" if args.nchw else "channels_last (NHWC) memory")}
 
 
+def same_run_parity(cfg, size, host, parity_in, P, use_bg):
+    """BASELINE.md section 3 "parity in the same run": the first P pairs of the batch the GPU just timed (bench
+    settings: TF32 convolutions, channels_last, cuDNN autotuning, full batch) against the CPU reference
+    (oracle/_ref, else the oracle port) carrying the SAME weights, on the same inputs."""
+    import torch
+    kind, fwd, mods = build_cpu_nets(cfg, size)
+    mods["dm"].load_state_dict(parity_in["sd_dm"])
+    mods["rf"].load_state_dict(parity_in["sd_rf"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    kp_s = {"kp": host["kp_s"][:P].clone(), "jacobian": host["jac_s"][:P].clone()}
+    kp_d = {"kp": host["kp_d"][:P].clone(), "jacobian": host["jac_d"][:P].clone()}
+    bg = host["bg"][:P].clone() if use_bg else None
+    with torch.no_grad():
+        ref = fwd(host["src"][:P].clone(), kp_s, kp_d, bg).double()
+    got = parity_in["out"].double()
+    err = (got - ref).abs()
+    rel_l2 = float((got - ref).norm() / ref.norm())
+    tol = 2e-2
+    return {"against": kind, "pairs": P, "max_abs_err": float(err.max()), "mean_abs_err": float(err.mean()), "rel_l2": rel_l2,
+            "ref_rms": float(ref.pow(2).mean().sqrt()), "tolerance_rel": tol,
+            "ok": bool(rel_l2 < tol and float(err.max()) < tol * (1.0 + float(ref.abs().max()))),
+            "settings": "same process, same weights (state_dict copied to the CPU modules), product under the timed settings"}
+
+
+def measure_other_configs(args, world, rank, local, dev):
+    """Short measurements (3 timed steps after 2 warm-up, CUDA events, max over ranks) of the BASELINE.json configs the
+    headline line does not cover, at the same N: config 3 celebvhq 256x256 B=64 (background-affine path on), config 4
+    the vox1 architecture at 512x512 swept over B, config 5 the vox1 training step B=16/GPU (fwd + bwd through the
+    correlation lookup and the warps, Adam; DistributedDataParallel + SyncBatchNorm + NCCL gradient all-reduce when
+    N > 1, train.py:37-48,64-77)."""
+    import torch
+    import torch.distributed as dist
+    import mrfa_b200
+    import synthetic_inputs as syn
+    steps, warm = 3, 2
+    res = {"steps": steps, "warmup": warm, "note": "device-resident inputs, ms = max over ranks"}
+
+    def tmax(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def fwd_bench(cfg_name, size, batch):
+        cfg = load_cfg(cfg_name)
+        torch.manual_seed(0)
+        dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).to(dev).eval().channels_last_()
+        rf = mrfa_b200.RaftFlow(**dict(cfg["raft_flow"], size=size)).to(dev).eval().channels_last_()
+        src = syn.frame_pairs(batch, size, seed=rank)[0].to(dev)
+        ks, kd = ({k: v.to(dev) for k, v in d.items()} for d in syn.keypoints(batch, cfg["raft_flow"]["num_kp"], seed=rank))
+        bg = syn.bg_affine(batch, seed=rank).to(dev) if cfg["train_params"]["bg_start"] == 0 else None
+
+        def f():
+            dense = dm(src, kd, ks, bg_param=bg)
+            return rf(ks["kp"], kd["kp"], dense, img=dm.down(src), img_full=src)[0]
+        with torch.no_grad():
+            for _ in range(warm):
+                f()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = f()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = tmax(e0.elapsed_time(e1) / steps)
+        finite = bool(torch.isfinite(o).all())
+        del dm, rf, o
+        torch.cuda.empty_cache()
+        return {"pairs_per_gpu": batch, "size": size, "ms_per_step": round(ms, 3), "pairs_per_s": round(batch * world / ms * 1e3, 1),
+                "finite": finite}
+
+    try:
+        res["celebvhq_256_b64"] = dict(fwd_bench("celebvhq", 256, 64), config="celebvhq.yaml refinement forward, bg_param path on (bg_start: 0)")
+    except Exception as e:                                   # keep the headline line even if a side config fails
+        res["celebvhq_256_b64"] = {"error": repr(e)[:200]}
+    sweep = []
+    for b in (4, 8, 16):
+        try:
+            sweep.append(fwd_bench("vox1", 512, b))
+        except Exception as e:
+            sweep.append({"pairs_per_gpu": b, "size": 512, "error": repr(e)[:200]})
+    res["vox1_512_sweep"] = sweep
+    try:
+        res["train_step_b16"] = train_step_bench(world, rank, local, dev, 16, 256, steps, warm)
+    except Exception as e:
+        res["train_step_b16"] = {"error": repr(e)[:200]}
+    return res
+
+
+def train_step_bench(world, rank, local, dev, batch, size, steps, warm):
+    """Config 5: vox1 training step through the drop-in modules (L1 reconstruction loss, Adam(0.5, 0.999) as train.py:21-25).
+    The perceptual (pretrained VGG19, needs the network) and equivariance losses of model.py:219-254 are outside the hot path."""
+    import torch
+    import torch.distributed as dist
+    import mrfa_b200
+    import synthetic_inputs as syn
+    cfg = load_cfg("vox1")
+    torch.manual_seed(0)
+
+    class Refiner(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense_motion = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"])
+            self.decoder = mrfa_b200.RaftFlow(**dict(cfg["raft_flow"], size=size))
+
+        def forward(self, src, kp_s, kp_d):
+            dense = self.dense_motion(src, kp_d, kp_s)
+            return self.decoder(kp_s["kp"], kp_d["kp"], dense, img=self.dense_motion.down(src), img_full=src)[0]
+
+    model = Refiner().to(dev).train()
+    model.dense_motion.channels_last_()
+    model.decoder.channels_last_()
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)                     # train.py:43
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)   # train.py:45-48
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    src, drv = (t.to(dev) for t in syn.frame_pairs(batch, size, seed=rank))
+    kp_s, kp_d = ({k: v.to(dev) for k, v in d.items()} for d in syn.keypoints(batch, 10, seed=rank))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = (model(src, kp_s, kp_d) - drv).abs().mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lt = loss.detach().clone()
+        dist.reduce(lt, dst=0)                                                            # train.py:74-77
+    ms = float(t[0])
+    out = {"pairs_per_gpu": batch, "size": size, "ms_per_step": round(ms, 3), "pairs_per_s": round(batch * world / ms * 1e3, 1),
+           "loss": float(loss.detach()), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+           "parallelism": f"DDP dp{world} + SyncBatchNorm, NCCL gradient all-reduce" if world > 1 else "single GPU (no collective)"}
+    # share of NCCL / this library's / cuDNN kernels in one step (torch.profiler, rank 0; an extra untimed step)
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        tot = nccl = ours = 0.0
+        for ev in prof.key_averages():
+            us = float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0))
+            tot += us
+            name = ev.key.lower()
+            if "nccl" in name:
+                nccl += us
+            elif "mrfa::" in name or name.startswith("void mrfa"):
+                ours += us
+        if tot > 0:
+            out.update({"kernel_time_ms": round(tot / 1e3, 3), "nccl_kernel_ms": round(nccl / 1e3, 3),
+                        "nccl_share_of_kernel_time": round(nccl / tot, 4), "mrfa_kernel_ms": round(ours / 1e3, 3),
+                        "limiting_collective": "ncclAllReduce of DDP gradient buckets (457 MB fp32 per step) + SyncBatchNorm all-gathers"
+                        if world > 1 else None})
+    except Exception as e:
+        out["profile_error"] = repr(e)[:120]
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import mrfa_b200
     from mrfa_b200 import ops
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -327,12 +523,24 @@ def run_ours(args):
         sync_all()
         e2e_ms = e2.elapsed_time(e3)
 
-    stats = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    sums = torch.tensor([float(l1), float(out.numel())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)       # max over ranks
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)        # reconstruction-L1 statistics
-    dev_ms, e2e_ms = float(stats[0]), float(stats[1])
+    # reconstruction-L1 / timing statistics: SUM of the L1 terms, MAX over ranks of the two elapsed times
+    from mrfa_b200.dist import reduce_stats
+    red = reduce_stats(float(l1), float(out.numel()), dev_ms, float(B * args.steps), device=dev, extra_max=(e2e_ms,))
+    dev_ms, e2e_ms = red["elapsed_s"], red["extra_max"][0]
+    recon_l1_mean = red["l1_mean"]
+
+    # material for the same-run parity check (rank 0, evaluated after the GPU work): the first pairs of the timed batch
+    P = max(0, min(args.parity_pairs, B))
+    parity_in = None
+    if rank == 0 and P > 0:
+        parity_in = {"out": out[:P].float().cpu(), "sd_dm": {k: v.detach().cpu() for k, v in dm.state_dict().items()},
+                     "sd_rf": {k: v.detach().cpu() for k, v in rf.state_dict().items()}}
+    del out, resident
+    others = None
+    if args.other_configs:
+        del dm, rf
+        torch.cuda.empty_cache()
+        others = measure_other_configs(args, world, rank, local, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -395,13 +603,18 @@ def run_ours(args):
             "kernels_note": "hot-path rows (SURVEY 8a) are timed inside the timed region; the other rows come from a "
                             f"second, fully instrumented pass of the same {args.steps} steps ({instrumented_ms / args.steps:.2f} ms/step)",
             "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
-            "recon_l1_mean": float(sums[0] / sums[1]), "peaks": pk}
+            "recon_l1_mean": recon_l1_mean, "peaks": pk}
+    if others is not None:
+        line["other_configs"] = others
+    if parity_in is not None:
+        line["parity"] = same_run_parity(cfg, S, host, parity_in, P, use_bg)
+        line["parity_max_err"], line["parity_rel_l2"] = line["parity"]["max_abs_err"], line["parity"]["rel_l2"]
     if not args.no_cpu_baseline:
-        r = time_cpu_oracle(cfg, S, 1, 3, 1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+        r = time_cpu_path(cfg, S, 1, 3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
                                 "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"],
                                 "sample": f"1 pair per step, 3 timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step), "
-                                          f"oracle torch-CPU port of the reference path, {r['cores']} threads"}
+                                          f"{CPU_KIND_TEXT[r['kind']]}, {r['cores']} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,14 +35,17 @@ def shard_range(total_pairs: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def reduce_stats(l1_sum: float, n_elements: float, elapsed_s: float, n_pairs: float, device=None) -> dict:
-    """All-reduce {sum|out - driving|, element count, pair count} (SUM) and elapsed seconds (MAX)."""
+def reduce_stats(l1_sum: float, n_elements: float, elapsed_s: float, n_pairs: float, device=None,
+                 extra_max=()) -> dict:
+    """All-reduce {sum|out - driving|, element count, pair count} (SUM) and elapsed seconds (MAX);
+    `extra_max`: further per-rank timings reduced with MAX alongside `elapsed_s`."""
     device = device or ("cuda" if (dist.is_initialized() and dist.get_backend() == "nccl") else "cpu")
     sums = torch.tensor([l1_sum, n_elements, n_pairs], dtype=torch.float64, device=device)
-    tmax = torch.tensor([elapsed_s], dtype=torch.float64, device=device)
+    tmax = torch.tensor([elapsed_s, *extra_max], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     l1, n, pairs = (float(x) for x in sums)
     t = float(tmax[0])
-    return {"l1_mean": l1 / max(n, 1.0), "pairs": pairs, "elapsed_s": t, "pairs_per_s": pairs / t if t > 0 else 0.0}
+    return {"l1_mean": l1 / max(n, 1.0), "pairs": pairs, "elapsed_s": t, "pairs_per_s": pairs / t if t > 0 else 0.0,
+            "extra_max": [float(x) for x in tmax[1:]]}

@@ -9,8 +9,8 @@ It is a restatement, not a copy: the reference control flow (modules/raft.py:141
 modules/dense_motion.py:104-146 and :262-312) is re-derived as an explicit per-level schedule.
 Pinned against the unmodified reference run in the build container with identical weights
 and inputs (tests/golden/make_golden.py -> tests/golden/*.npz; tests/test_oracle_golden.py).
-The dense-convolution blocks are shared with the product (``mrfa_b200.blocks``, plain
-nn.Conv2d/BatchNorm2d, out of the hot path) and are covered by the same golden vectors.
+The dense-convolution blocks are the oracle's own plain nn.Conv2d / BatchNorm2d restatement
+(oracle/conv_blocks.py): importing the oracle never loads the product package or its CUDA library.
 """
 from __future__ import annotations
 
@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from mrfa_b200.blocks import AntiAliasInterpolation2d, Hourglass, OcclusionAwareGenerator
+from .conv_blocks import AntiAliasInterpolation2d, Hourglass, OcclusionAwareGenerator
 
 
 # ------------------------------------------------------------------ primitives (util.py)

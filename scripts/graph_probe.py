@@ -4,7 +4,7 @@ import torch, yaml
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mrfa_b200
-from mrfa_b200 import synthetic as syn
+import synthetic_inputs as syn
 cfg = yaml.safe_load(open(os.path.join(ROOT, "tests", "golden", "vox1.yaml")))
 dev = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True

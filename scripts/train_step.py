@@ -18,7 +18,7 @@ import yaml
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mrfa_b200                                    # noqa: E402
-from mrfa_b200 import synthetic as syn             # noqa: E402
+import synthetic_inputs as syn             # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)

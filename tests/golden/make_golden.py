@@ -41,7 +41,7 @@ def npy(t):
 
 
 def main():
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     util, raft, dm = import_reference()
     torch.set_grad_enabled(False)
     torch.manual_seed(0)
@@ -177,7 +177,7 @@ def main():
 def equivariance():
     """Training-only random warps: model.py:26-77 `Transform` and util.py TPS mode 'random'.
     Written to its own file so the other fixtures stay byte-identical:  python make_golden.py equivariance"""
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     util, _, _ = import_reference()
     from modules.model import Transform
     T = syn.tensor
@@ -213,5 +213,6 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["equivariance"]:
         equivariance()
     else:
-        main()
+        main()                                   # main() disables grad globally;
+        torch.set_grad_enabled(True)             # Transform.jacobian (model.py:72-77) needs autograd
         equivariance()

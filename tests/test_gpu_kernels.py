@@ -334,7 +334,7 @@ def test_corr_lookup_backward():
 
 # ------------------------------------------------------------------ prior dense motion
 def _prior_inputs():
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     src, _ = syn.frame_pairs(2, 64, seed=1)
     kp_s, kp_d = syn.keypoints(2, 10, seed=1)
     return src, kp_s, kp_d, syn.bg_affine(2, seed=1)
@@ -351,7 +351,7 @@ def _cfg():
 
 
 def test_dense_motion_prior_kernels(golden):
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     m, d = mb(), golden("prior_motion")
     _, kp_s, kp_d, bg = _prior_inputs()
     cfg = _cfg()
@@ -371,7 +371,7 @@ def test_dense_motion_prior_kernels(golden):
 
 def test_tps_kernels(golden):
     m, d = mb(), golden("prior_motion")
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     bg = syn.bg_affine(2, seed=1).to(DEV)
     kp_d, kp_s = cu(d["tps_kp_d"]), cu(d["tps_kp_s"])
     tps = m.TPS(mode="kp", bs=2, kp_1=kp_d.view(2, -1, 5, 2), kp_2=kp_s.view(2, -1, 5, 2))
@@ -379,19 +379,21 @@ def test_tps_kernels(golden):
     th, cp, cw = O.tps_params(d["tps_kp_d"].reshape(2, -1, 5, 2), d["tps_kp_s"].reshape(2, -1, 5, 2))
     close(tps.theta, th, 1e-5, 1e-5)
     close(tps.control_params, cw, 1e-5, 1e-5)
-    # ... and with the reference (fp32 LU inverse) to that inverse's own round-off
-    close(tps.theta, d["tps_theta"], 2e-3, 2e-3)
+    # ... and with the reference's own parameters: its fp32 inverse sits within 2e-6 of the fp64 solve on these inputs
+    # (tests/test_reference_vendored.py::test_tps_reference_solve_agrees_with_fp64), so no loosened bound is needed
+    close(tps.theta, d["tps_theta"], 3e-5, 1e-5)
+    close(tps.control_params, d["tps_control_params"], 3e-5, 1e-5)
     cfg = _cfg()
     net = m.TPSDenseMotionNetwork(**dict(cfg["tpsm_dense_motion"], block_expansion=16, max_features=64, num_blocks=3)).to(DEV)
     small = cu(d["source_small"])
     got = net.create_transformations(small, {"kp": kp_d}, {"kp": kp_s}, bg)
     close(got, O.tps_transformations(d["tps_kp_d"], d["tps_kp_s"], 16, 16, bg.cpu().numpy()), 2e-5)
-    close(got, d["tps_transformations_bg"], 5e-3)
+    close(got, d["tps_transformations_bg"], 3e-5)
     close(tps.transform_frame(small), O.tps_transformations(d["tps_kp_d"], d["tps_kp_s"], 16, 16)[:, 1:], 2e-5)
 
 
 def test_dense_motion_networks_forward(golden):
-    from mrfa_b200 import synthetic as syn
+    import synthetic_inputs as syn
     m, d = mb(), golden("prior_motion")
     src, kp_s, kp_d, bg = _prior_inputs()
     cfg = _cfg()
@@ -407,7 +409,7 @@ def test_dense_motion_networks_forward(golden):
                                                                    max_features=64, num_blocks=3))).to(DEV).eval()
         out = tnet(src.to(DEV), {"kp": cu(d["tps_kp_d"])}, {"kp": cu(d["tps_kp_s"])}, bg_param=bg.to(DEV))
         for k in ("deformed_source", "contribution_maps", "deformation", "occlusion"):
-            close(out[k], d["tps_fwd_" + k], 5e-3)
+            close(out[k], d["tps_fwd_" + k], 2e-4)
 
 
 # ------------------------------------------------------------------ channels-last (NHWC) paths
@@ -499,7 +501,8 @@ def test_channel_affine_and_blend(cl):
 
 def test_fast_inference_blocks_match_plain():
     """BN folding / fused conv-bias-ReLU / fused blends are a re-association, not new numerics."""
-    from mrfa_b200 import blocks, synthetic as syn
+    from mrfa_b200 import blocks
+    import synthetic_inputs as syn
     torch.manual_seed(12)
     gen = syn.fill_state_dict_(blocks.OcclusionAwareGenerator(3, 16, 64, 3)).to(DEV).eval()
     hg = syn.fill_state_dict_(blocks.Hourglass(8, 5, 3, 32)).to(DEV).eval()
@@ -695,7 +698,8 @@ def test_small_conv_blocks_match_cudnn_path():
 def test_blend_subpixel_space_to_depth_output_and_final_conv():
     """The r x r space-to-depth output of the last blend is a pure re-layout, and the generator's final 7x7
     convolution evaluated on it as a 3x3 convolution (blocks._final_s2d) equals the direct one."""
-    from mrfa_b200 import blocks, synthetic as syn
+    from mrfa_b200 import blocks
+    import synthetic_inputs as syn
     torch.manual_seed(41)
     N, C, H, W = 2, 8, 6, 10
     a = torch.randn(N, C, 2 * H, 2 * W, device=DEV).contiguous(memory_format=torch.channels_last)

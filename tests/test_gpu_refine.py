@@ -9,7 +9,7 @@ import yaml
 
 pytestmark = pytest.mark.gpu
 
-from mrfa_b200 import synthetic as syn               # noqa: E402
+import synthetic_inputs as syn               # noqa: E402
 from oracle import torch_path as TP                   # noqa: E402
 
 DEV = "cuda"

@@ -149,7 +149,8 @@ def test_subpixel_and_space_to_depth_weight_transforms_cpu():
         outputs;  (2) the generator's final 7x7 convolution (generator.py:32,61) == pixel_shuffle(conv3x3(space_to_depth_4(x)))."""
     import torch
     import torch.nn.functional as F
-    from mrfa_b200 import blocks, synthetic as syn
+    from mrfa_b200 import blocks
+    import synthetic_inputs as syn
     torch.manual_seed(5)
     up = syn.fill_state_dict_(blocks.UpBlock2d(6, 8, kernel_size=3, padding=1)).eval()
     x = torch.randn(2, 6, 5, 7)
@@ -171,7 +172,7 @@ def test_subpixel_and_space_to_depth_weight_transforms_cpu():
 
 
 def test_bench_reference_arm_json_contract():
-    """`bench.py --impl reference` (the CPU oracle port, the one arm that runs without a GPU) prints one JSON line
+    """`bench.py --impl reference` (the vendored reference on the CPU, the one arm that runs without a GPU) prints one JSON line
     carrying the keys of the bench contract; run at 128x128 with one pair so it finishes in seconds."""
     import json
     import subprocess
@@ -187,6 +188,8 @@ def test_bench_reference_arm_json_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["device"] == "cpu" and d["config"]["pairs_per_step_this_arm"] == 1 and "cuDNN" not in json.dumps(d["config"])
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"] and cb["cpu_model"]
+    from oracle import reference_arm
+    assert cb["kind"] == ("reference" if reference_arm.available() else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"] and cb["cpu_model"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

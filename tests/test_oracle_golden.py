@@ -5,7 +5,7 @@ import pytest
 import torch
 import yaml
 
-from mrfa_b200 import synthetic as syn
+import synthetic_inputs as syn
 from oracle import np_ops as O
 from oracle import torch_path as TP
 
