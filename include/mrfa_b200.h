@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 5
+#define MRFA_B200_ABI_VERSION 6
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -150,9 +150,25 @@ int mrfa_prior_to_flow(const float* deformation, float* flow, int B, int h, int 
 int64_t mrfa_corr_rows_total(int h, int w);
 int64_t mrfa_corr_row_offset(int h, int w, int pool_log2);
 
+/* Map layouts: where element (y, x) of one query's H x W source map sits inside its volume row.
+ *   MRFA_MAP_ROWMAJOR  y*W + x  -- the reference's (B*Q,1,H,W) `corr` (raft.py:208) and every fp32 map.
+ *   MRFA_MAP_TILED     bf16 pyramid maps only: 64-byte tiles of 4 rows x 8 columns, so the (2r+2)^2 lookup
+ *                      footprint (raft.py:23-48) touches 4-6 DRAM granules instead of 8 scattered row pieces.
+ *        level 0 (H x W, H % 8 == 0, W % 16 == 0): 2 x 2 tiles form a 16 x 8-pixel super-tile
+ *            off0(y,x) = ((y>>3)*(W>>4) + (x>>4))*128 + ((y>>2)&1)*64 + ((x>>3)&1)*32 + (y&3)*8 + (x&7)
+ *        level 1 (H/2 x W/2): plain tiles, tile t of level 1 = the 2x2 pool of super-tile t of level 0
+ *            off1(y,x) = ((y>>2)*((W/2)>>3) + (x>>3))*32 + (y&3)*8 + (x&7)
+ * mrfa_corr_map_layout(h, w) is the layout mrfa_corr_pack / mrfa_corr_volume produce for an h x w plane
+ * (TILED for w in {64, 128}: the 256x256 and 512x512 configurations; ROWMAJOR for the small shapes).   */
+enum { MRFA_MAP_ROWMAJOR = 0, MRFA_MAP_TILED = 1 };
+int     mrfa_corr_map_layout(int h, int w);
+int64_t mrfa_corr_map_offset(int map_layout, int level, int y, int x, int W_level);
+
 /* fp32 NCHW features -> bf16 K-major GEMM operands (fuses the rearranges raft.py:183-184, the
  * fp32->bf16 cast and the driving-side average pooling raft.py:219).
- *   q_d, k_s (B,C,h,w) fp32;  a_op (B, rows_total, C) bf16;  b_op (B, h*w, C) bf16.
+ *   q_d, k_s (B,C,h,w) fp32;  a_op (B, rows_total, C) bf16;  b_op (B, h*w, C) bf16: source pixel (y,x)
+ *   is row mrfa_corr_map_offset(mrfa_corr_map_layout(h,w), 0, y, x, w) -- permuting the B-operand rows is what
+ *   makes the GEMM write every volume row directly in the map layout.
  * C % 64 == 0, h and w multiples of 8.  channels_last != 0: q_d / k_s are NHWC in memory (then
  * the rearrange is the identity and the kernel is a vectorised cast + pool).                 */
 int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op,
@@ -181,21 +197,22 @@ int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_
  *   the map of query (b,q) is level0 + (b*map_batch_stride + row_offset + q) * H*W, i.e.
  *   reference `corr` (B*Q,1,H,W) has map_batch_stride = Q, row_offset = 0; a pyramid volume
  *   from mrfa_corr_volume has map_batch_stride = rows_total, row_offset = pooled-level offset.
- *   level1 is the 2x2-pooled map (H/2 x W/2) with the same indexing.
+ *   level1 is the 2x2-pooled map (H/2 x W/2) with the same indexing.  map_layout: MRFA_MAP_* of both levels
+ *   (TILED needs bf16 maps, H % 8 == 0, W % 16 == 0, 16-byte aligned levels).
  *   elem_bf16: 0 -> fp32 maps, 1 -> bf16 maps.   out (B, 2*(2r+1)^2, Q) fp32, or (B, Q, 2*(2r+1)^2)
  *   in memory when out_channels_last != 0 (feeds the 1x1 convc1 without a layout change).
  *   radius <= 4.                                                                              */
 int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16,
                          const float* coords, float* out,
                          int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
-                         int radius, int out_channels_last, mrfa_stream_t stream);
+                         int radius, int map_layout, int out_channels_last, mrfa_stream_t stream);
 
 /* Backward: grad_level0/1 (fp32, same indexing as the maps, ZERO-FILLED by the caller, may be
  * NULL) receive the scatter-add; grad_coords (B,2,Q) is written.                             */
 int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* level1, int elem_bf16,
                          const float* coords, float* grad_level0, float* grad_level1, float* grad_coords,
                          int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
-                         int radius, mrfa_stream_t stream);
+                         int radius, int map_layout, mrfa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused elementwise passes between the warps and the cuDNN convolutions

@@ -12,10 +12,11 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
 TPS_L1, TPS_L2SQ = 0, 1
+MAP_ROWMAJOR, MAP_TILED = 0, 1
 
 
 class GridStrides(ctypes.Structure):
@@ -39,11 +40,13 @@ SIGNATURES = {
     "mrfa_prior_to_flow": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "mrfa_corr_rows_total": (c_int64, [c_int, c_int]),
     "mrfa_corr_row_offset": (c_int64, [c_int, c_int, c_int]),
+    "mrfa_corr_map_layout": (c_int, [c_int, c_int]),
+    "mrfa_corr_map_offset": (c_int64, [c_int] * 5),
     "mrfa_corr_pack": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_corr_volume": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "mrfa_avg_pool2x2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 4
-                             + [c_int64, c_int64, c_int, c_int, c_void_p]),
+                             + [c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "mrfa_channel_affine": (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mrfa_occlusion_blend_subpixel": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_int64, c_void_p]),
     "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
@@ -58,7 +61,7 @@ SIGNATURES = {
     "mrfa_flow_carry": (c_int, [c_void_p, GridStrides] + [c_void_p] * 8 + [c_int] * 3 + [c_float, c_int, c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4
-                             + [c_int64, c_int64, c_int, c_void_p]),
+                             + [c_int64, c_int64, c_int, c_int, c_void_p]),
 }
 
 

@@ -36,14 +36,19 @@ class _CorrPyramidFn(torch.autograd.Function):
         N = h * w
         if holder is None:
             return torch.zeros_like(q_d), torch.zeros_like(k_s), None, None
-        # level-1 gradients: each pooled source cell feeds its 2x2 block with weight 1/4
-        g = holder.g0
-        g1 = holder.g1.view(B, -1, h // 2, w // 2)
-        g = g + (g1 * 0.25).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3).reshape(B, -1, N)
+        # level-1 gradients: each pooled source cell feeds its 2x2 block with weight 1/4.  Both gradient buffers are in the
+        # map layout of the volume (tiled for w = 64 / 128), so the spread is a gather through a cached index
+        layout = ops.corr_map_layout(h, w)
+        perm0 = ops.corr_map_permutation(layout, 0, h, w, q_d.device)               # (y, x) -> stored position, level 0
+        perm1 = ops.corr_map_permutation(layout, 1, h // 2, w // 2, q_d.device)
+        yy, xx = torch.meshgrid(torch.arange(h, device=q_d.device), torch.arange(w, device=q_d.device), indexing="ij")
+        l1_of_l0 = torch.empty(N, dtype=torch.int64, device=q_d.device)
+        l1_of_l0[perm0] = perm1[((yy // 2) * (w // 2) + xx // 2).reshape(-1)]
+        g = holder.g0 + 0.25 * holder.g1.index_select(2, l1_of_l0)
         a_op, b_op = ops.corr_pack_debug(q_d.detach(), k_s.detach())
         gb = (g * ctx.scale).to(torch.bfloat16)
         d_a = torch.bmm(gb, b_op).float()                          # (B, rows_total, C)
-        d_b = torch.bmm(gb.transpose(1, 2), a_op).float()          # (B, N, C)
+        d_b = torch.bmm(gb.transpose(1, 2), a_op).float()          # (B, N, C), rows in stored (map layout) order
         # driving operand rows: level 0 plus the average-pooled levels (pool backward = spread / k^2)
         d_q = d_a[:, :N].transpose(1, 2).reshape(B, C, h, w)
         off = N
@@ -53,23 +58,23 @@ class _CorrPyramidFn(torch.autograd.Function):
             part = d_a[:, off:off + n_l].transpose(1, 2).reshape(B, C, h // k, w // k) / (k * k)
             d_q = d_q + part.repeat_interleave(k, dim=2).repeat_interleave(k, dim=3)
             off += n_l
-        d_k = d_b.transpose(1, 2).reshape(B, C, h, w)
+        d_k = d_b.index_select(1, perm0).transpose(1, 2).reshape(B, C, h, w)
         ctx.holder_box[0] = None
         return d_q.contiguous(), d_k.contiguous(), None, None
 
 
 class _PyramidLookupFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coords, vol0, vol1, holder_box, H, W, stride, offset, radius, channels_last):
-        out = torch.ops.mrfa.corr_lookup(vol0, vol1, coords, H, W, stride, offset, radius, channels_last)
+    def forward(ctx, coords, vol0, vol1, holder_box, H, W, stride, offset, radius, layout, channels_last):
+        out = torch.ops.mrfa.corr_lookup(vol0, vol1, coords, H, W, stride, offset, radius, layout, channels_last)
         ctx.save_for_backward(coords, vol0, vol1)
-        ctx.cfg, ctx.holder_box = (H, W, stride, offset, radius), holder_box
+        ctx.cfg, ctx.holder_box = (H, W, stride, offset, radius, layout), holder_box
         return out
 
     @staticmethod
     def backward(ctx, g):
         coords, vol0, vol1 = ctx.saved_tensors
-        H, W, stride, offset, radius = ctx.cfg
+        H, W, stride, offset, radius, layout = ctx.cfg
         holder = ctx.holder_box[0]
         if holder is None:
             holder = ctx.holder_box[0] = _GradHolder(vol0, vol1)
@@ -80,8 +85,8 @@ class _PyramidLookupFn(torch.autograd.Function):
         with torch.cuda.device(coords.device):
             ops.check(ops.lib.mrfa_corr_lookup_bwd(ops._p(g), ops._p(vol0), ops._p(vol1), 1, ops._p(coords), ops._p(holder.g0),
                                                    ops._p(holder.g1), ops._p(gc), B, h1 * w1, H, W, stride, offset, radius,
-                                                   ops._stream()), "mrfa_corr_lookup_bwd")
-        return gc, None, None, None, None, None, None, None, None, None
+                                                   layout, ops._stream()), "mrfa_corr_lookup_bwd")
+        return gc, None, None, None, None, None, None, None, None, None, None
 
 
 class CorrPyramid:
@@ -102,16 +107,22 @@ class CorrPyramid:
         else:
             self.volume0, self.volume1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, float(scale))
         self.rows_total = self.volume0.shape[1]
+        self.layout = ops.corr_map_layout(self.h, self.w)      # _lib.MAP_TILED for w = 64 / 128, else row-major
 
     def block(self, pool_log2: int = 0, radius: int = 3) -> "CorrBlock":
         """CorrBlock over the driving plane pooled by 2^pool_log2 (0 = basic resolution)."""
         return CorrBlock.from_pyramid(self, pool_log2, radius)
 
-    def dense(self, pool_log2: int = 0) -> torch.Tensor:
-        """fp32 copy of one driving level as the reference's (B*Q,1,h,w) ``corr`` (tests)."""
+    def dense(self, pool_log2: int = 0, level: int = 0) -> torch.Tensor:
+        """fp32 row-major copy of one driving level as the reference's (B*Q,1,H,W) ``corr`` (level 0) or its 2x2 source
+        pool (level 1, raft.py:20), whatever the stored map layout (tests / debugging)."""
         off = ops.corr_row_offset(self.h, self.w, pool_log2)
         q = (self.h >> pool_log2) * (self.w >> pool_log2)
-        return self.volume0[:, off:off + q].float().reshape(self.B * q, 1, self.h, self.w)
+        H, W = self.h >> level, self.w >> level
+        rows = (self.volume1 if level else self.volume0)[:, off:off + q].float()
+        if self.layout != _lib.MAP_ROWMAJOR:
+            rows = rows.index_select(2, ops.corr_map_permutation(self.layout, level, H, W, rows.device))
+        return rows.reshape(self.B * q, 1, H, W)
 
 
 class CorrBlock:
@@ -136,6 +147,7 @@ class CorrBlock:
         self._H, self._W = corr.shape[-2:]
         self._stride = None          # maps per sample = queries per sample (set at call time)
         self._offset = 0
+        self._layout = _lib.MAP_ROWMAJOR
         self._holder_box = None
 
     @classmethod
@@ -146,6 +158,7 @@ class CorrBlock:
         self._H, self._W = pyr.h, pyr.w
         self._stride = pyr.rows_total
         self._offset = ops.corr_row_offset(pyr.h, pyr.w, pool_log2)
+        self._layout = pyr.layout
         self._holder_box = pyr._holder_box
         return self
 
@@ -158,6 +171,6 @@ class CorrBlock:
         if self._holder_box is not None and torch.is_grad_enabled() and \
                 (coords.requires_grad or self.corr_pyramid[0].requires_grad):
             return _PyramidLookupFn.apply(coords, self.corr_pyramid[0], self.corr_pyramid[1], self._holder_box, self._H,
-                                          self._W, stride, self._offset, self.radius, channels_last)
+                                          self._W, stride, self._offset, self.radius, self._layout, channels_last)
         return torch.ops.mrfa.corr_lookup(self.corr_pyramid[0], self.corr_pyramid[1], coords, self._H, self._W,
-                                          stride, self._offset, self.radius, channels_last)
+                                          stride, self._offset, self.radius, self._layout, channels_last)

@@ -100,6 +100,19 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
   return t;
 }
 
+// Element offset of (y, x) inside one H x W map (include/mrfa_b200.h, "Map layouts").
+//   ROWMAJOR: y * W + x.
+//   TILED   : 64-byte tiles of 4 rows x 8 columns (bf16), so an (2r+2)^2 footprint touches 4-6 DRAM granules
+//             instead of 8 separate rows.  Level 0 groups 2 x 2 tiles into a 16 x 8-pixel super-tile (the unit
+//             one level-1 tile is pooled from in the GEMM epilogue); level 1 orders plain tiles row-major.
+template <bool TILED>
+__host__ __device__ __forceinline__ int64_t map_offset(int lvl, int y, int x, int Wl) {
+  if (!TILED) return (int64_t)y * Wl + x;
+  if (lvl == 0)
+    return (int64_t)((y >> 3) * (Wl >> 4) + (x >> 4)) * 128 + ((y >> 2) & 1) * 64 + ((x >> 3) & 1) * 32 + (y & 3) * 8 + (x & 7);
+  return (int64_t)((y >> 2) * (Wl >> 3) + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

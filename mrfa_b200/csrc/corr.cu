@@ -38,7 +38,7 @@ __device__ __forceinline__ int64_t level_row_offset(int hw, int lvl) {
 // grid: (tiles_y * tiles_x, 2 * C/32, B); blockIdx.y < C/32 -> q_d (all levels), else k_s
 __global__ void __launch_bounds__(kPackThreads)
 corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, __nv_bfloat16* __restrict__ a_op,
-                 __nv_bfloat16* __restrict__ b_op, int C, int h, int w, int tile_w, int64_t rows_total) {
+                 __nv_bfloat16* __restrict__ b_op, int C, int h, int w, int tile_w, int64_t rows_total, int tiled) {
   extern __shared__ float tile[];                      // [kPackCh][kPackRows * tile_w + 1]
   const int cblocks = C / kPackCh;
   const bool is_q = blockIdx.y < cblocks;
@@ -66,7 +66,8 @@ corr_pack_kernel(const float* __restrict__ q_d, const float* __restrict__ k_s, _
   const int npix = kPackRows * tile_w;
   for (int p = warp; p < npix; p += kPackThreads / 32) {
     const int y = p / tile_w, x = p - y * tile_w;
-    const int64_t row = (int64_t)(y0 + y) * w + x0 + x;
+    // source operand rows follow the map layout of the volume (tiled: the GEMM then writes tiled maps)
+    const int64_t row = (!is_q && tiled) ? map_offset<true>(0, y0 + y, x0 + x, w) : (int64_t)(y0 + y) * w + x0 + x;
     dst[row * C + c0 + lane] = __float2bfloat16_rn(tile[lane * cs + p]);
   }
   if (!is_q) return;
@@ -149,6 +150,20 @@ __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = pack_bf16x4(__ldg(x + i));
+}
+
+// Source operand for the tiled map layout: the same cast with the pixel rows written in tile order
+// (whole C-channel rows move, so loads and stores stay contiguous 4*C / 2*C-byte runs)
+__global__ void __launch_bounds__(256)
+cast_bf16_tiled_rows_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t pixels, int hw, int w, int cq) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels * cq; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / cq;
+    const int c = (int)(i - pix * cq);
+    const int64_t b = pix / hw;
+    const int p = (int)(pix - b * hw);
+    const int py = p / w, px = p - py * w;
+    y[(b * hw + map_offset<true>(0, py, px, w)) * cq + c] = pack_bf16x4(__ldg(x + i));
+  }
 }
 
 // ============================================================================================
@@ -448,17 +463,73 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 constexpr uint32_t kStageWarpBytes = 4096 + 4096 + 2048;   // two 32x64 bf16 boxes + one 32x32 box
 
+// One 128-column step of the tiled epilogue (MRFA_MAP_TILED, include/mrfa_b200.h).  The B-operand rows were packed in
+// tile order, so 128 consecutive accumulator columns are one level-0 super-tile of 16 x 8 source pixels: four 32-column
+// tiles (ty, tx) of 4 rows x 8 columns.  Thread = TMEM lane = volume row.  Per `sub` (= ty) the thread reads tiles (ty,0)
+// and (ty,1) -- 64 contiguous columns -- scales, packs to bf16 into the 64-column staging box `sub`, and 2x2-pools them
+// into rows 2*ty, 2*ty+1 of the level-1 tile (16 contiguous level-1 values); the pooled sum keeps the order of
+// F.avg_pool2d ((a + b) + (c + d), then * 1/4).
+__device__ __forceinline__ void stage_supertile(uint32_t taddr, float scale, float scale4, uint32_t box0, uint32_t box1,
+                                                uint32_t boxl, uint32_t row128, uint32_t row64, uint32_t sw128,
+                                                uint32_t sw64) {
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32(taddr + sub * 64, v0);
+    tmem_ld_32x32(taddr + sub * 64 + 32, v1);
+    tmem_ld_wait();
+    uint32_t p0[16], p1[16], pl[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      p0[j] = pack_bf16(__uint_as_float(v0[2 * j]) * scale, __uint_as_float(v0[2 * j + 1]) * scale);
+      p1[j] = pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
+    }
+    // tile element (row r, column c) = v[r * 8 + c]; pooled (r2, c2) = rows 2*r2, 2*r2+1 x columns 2*c2, 2*c2+1
+    float a[8], b[8];
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        const int i0 = r2 * 16 + 2 * c2, i1 = i0 + 8;
+        a[r2 * 4 + c2] = ((__uint_as_float(v0[i0]) + __uint_as_float(v0[i0 + 1])) +
+                          (__uint_as_float(v0[i1]) + __uint_as_float(v0[i1 + 1]))) * scale4;
+        b[r2 * 4 + c2] = ((__uint_as_float(v1[i0]) + __uint_as_float(v1[i0 + 1])) +
+                          (__uint_as_float(v1[i1]) + __uint_as_float(v1[i1 + 1]))) * scale4;
+      }
+    // level-1 tile rows 2*sub + r2: [a(r2, 0..3), b(r2, 0..3)]
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      pl[r2 * 4 + 0] = pack_bf16(a[r2 * 4 + 0], a[r2 * 4 + 1]);
+      pl[r2 * 4 + 1] = pack_bf16(a[r2 * 4 + 2], a[r2 * 4 + 3]);
+      pl[r2 * 4 + 2] = pack_bf16(b[r2 * 4 + 0], b[r2 * 4 + 1]);
+      pl[r2 * 4 + 3] = pack_bf16(b[r2 * 4 + 2], b[r2 * 4 + 3]);
+    }
+    const uint32_t box = sub ? box1 : box0;
+    // 16-byte chunk j of a 128-byte row lands at chunk (j ^ (row & 7))  [SWIZZLE_128B]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      st_shared_v4(box + row128 + (((uint32_t)j) ^ sw128) * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+      st_shared_v4(box + row128 + (((uint32_t)(4 + j)) ^ sw128) * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+    }
+    // 64-byte rows: chunk j lands at chunk (j ^ ((row >> 1) & 3))            [SWIZZLE_64B]
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t ch = (uint32_t)(sub * 2 + j) ^ sw64;
+      st_shared_v4(boxl + row64 + ch * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+    }
+  }
+}
+
 template <int kW, int kBlockN_, int kMTiles> struct Gemm2Cfg {
-  static_assert(kW == 64 || kW == 128, "TMA-store epilogue is specialised for w = 64 / 128");
-  static_assert(kBlockN_ % (2 * kW) == 0 && kBlockN_ <= 256, "a tile holds whole source row pairs");
+  static_assert(kW == 64 || kW == 128, "TMA-store epilogue is specialised for w = 64 / 128 (tiled map layout)");
+  static_assert(kBlockN_ % 128 == 0 && kBlockN_ <= 256, "a tile holds whole 16 x 8-pixel super-tiles");
   static constexpr int kBlockN = kBlockN_;
-  static constexpr int kGroups = kBlockN / (2 * kW);                     // source row pairs per tile
+  static constexpr int kSuper = kBlockN / 128;                            // super-tiles (epilogue steps) per tile
   static constexpr int kUnitRows = kBlockM * kMTiles;
   static constexpr uint32_t kBStageBytes = kBlockN * kBlockK * 2;
   static constexpr uint32_t kAKBytes = kUnitRows * kBlockK * 2;          // one K block of the A unit
   static constexpr int kTmemCols = 2 * kMTiles * kBlockN;               // double-buffered accumulators
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
-  static constexpr int kSteps = kW / 64;                                  // 64-column pairs per tile
 };
 
 struct Gemm2Params {
@@ -626,47 +697,12 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * kMTiles + half) * kBlockN;
           const int row0 = m_blk * Cfg::kUnitRows + half * kBlockM + ew * 32;
 #pragma unroll 1
-          for (int gs = 0; gs < Cfg::kGroups * Cfg::kSteps; ++gs) {
-            const int g = gs / Cfg::kSteps, s = gs - g * Cfg::kSteps;
+          for (int gs = 0; gs < Cfg::kSuper; ++gs) {
             // the staging boxes are free once the previous bulk stores have read them
             if (prm.store_mode == 0 && lane == 0 && !(prm.debug & 4)) tma_store_wait_read();
             __syncwarp();
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              if (prm.debug & 2) break;
-              const int c0 = g * 2 * kW + s * 64 + sub * 32;  // source row p   : tile cols [c0, c0+32)
-              const int c1 = c0 + kW;                         // source row p+1 : tile cols [c1, c1+32)
-              uint32_t v0[32], v1[32];
-              tmem_ld_32x32(taddr + c0, v0);
-              tmem_ld_32x32(taddr + c1, v1);
-              tmem_ld_wait();
-              uint32_t p0[16], p1[16], pl[8];
-              float pooled[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
-                const float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
-                p0[j] = pack_bf16(a0 * scale, a1 * scale);
-                p1[j] = pack_bf16(b0 * scale, b1 * scale);
-                pooled[j] = ((a0 + a1) + (b0 + b1)) * scale4;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
-              // 16-byte chunk j of a 128-byte row lands at chunk (j ^ (row & 7))  [SWIZZLE_128B]
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t ch = (uint32_t)(sub * 4 + j) ^ sw128;
-                st_shared_v4(box0 + row128 + ch * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
-                st_shared_v4(box1 + row128 + ch * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
-              }
-              // 64-byte rows: chunk j lands at chunk (j ^ ((row >> 1) & 3))            [SWIZZLE_64B]
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint32_t ch = (uint32_t)(sub * 2 + j) ^ sw64;
-                st_shared_v4(boxl + row64 + ch * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-              }
-            }
-            if (half == kMTiles - 1 && gs == Cfg::kGroups * Cfg::kSteps - 1) {
+            if (!(prm.debug & 2)) stage_supertile(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
+            if (half == kMTiles - 1 && gs == Cfg::kSuper - 1) {
               // every TMEM read of this accumulator stage is done: hand it back to the MMA warp
               tcgen05_fence_before();
               __syncwarp();
@@ -677,10 +713,10 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               fence_async_smem();
               __syncwarp();
               if (lane == 0 && !(prm.debug & 1)) {
-                const int col = nt * kBlockN + g * 2 * kW + s * 64;
-                const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+                const int col = nt * kBlockN + gs * 128;
+                const int colp = nt * (kBlockN / 4) + gs * 32;
                 tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes, col, row0, b);
-                tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + kW, row0, b);
+                tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + 64, row0, b);
                 tma_store_3d(&map_v1, smem_st + (size_t)ew * kStageWarpBytes + 8192, colp, row0, b);
                 tma_store_commit();
               }
@@ -689,8 +725,8 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               //      every warp instruction writes 4 (or 8) whole rows = full 128-byte lines ----
               __syncwarp();
               if (!(prm.debug & 1)) {
-                const int col = nt * kBlockN + g * 2 * kW + s * 64;
-                const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+                const int col = nt * kBlockN + gs * 128;
+                const int colp = nt * (kBlockN / 4) + gs * 32;
                 const int64_t rbase = (int64_t)b * prm.rows_total + row0;
                 const int rows_ok = (int)min((int64_t)32, prm.rows_total - row0);     // may be <= 0
                 {
@@ -705,7 +741,7 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     if (r < rows_ok) {
                       __nv_bfloat16* o = prm.vol0 + (rbase + r) * prm.N + col + ch * 8;
                       st_global_v4(o, x0.x, x0.y, x0.z, x0.w);
-                      st_global_v4(o + kW, x1.x, x1.y, x1.z, x1.w);
+                      st_global_v4(o + 64, x1.x, x1.y, x1.z, x1.w);
                     }
                   }
                 }
@@ -916,43 +952,11 @@ corr_volume_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kBlockN;
 #pragma unroll 1
-        for (int gs = 0; gs < Cfg::kGroups * Cfg::kSteps; ++gs) {
-          const int g = gs / Cfg::kSteps, s = gs - g * Cfg::kSteps;
+        for (int gs = 0; gs < Cfg::kSuper; ++gs) {
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int c0 = g * 2 * kW + s * 64 + sub * 32;
-            const int c1 = c0 + kW;
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(taddr + c0, v0);
-            tmem_ld_32x32(taddr + c1, v1);
-            tmem_ld_wait();
-            uint32_t p0[16], p1[16], pl[8];
-            float pooled[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
-              const float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
-              p0[j] = pack_bf16(a0 * scale, a1 * scale);
-              p1[j] = pack_bf16(b0 * scale, b1 * scale);
-              pooled[j] = ((a0 + a1) + (b0 + b1)) * scale4;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pl[j] = pack_bf16(pooled[2 * j], pooled[2 * j + 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t ch = (uint32_t)(sub * 4 + j) ^ sw128;
-              st_shared_v4(box0 + row128 + ch * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
-              st_shared_v4(box1 + row128 + ch * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t ch = (uint32_t)(sub * 2 + j) ^ sw64;
-              st_shared_v4(boxl + row64 + ch * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-            }
-          }
-          if (gs == Cfg::kGroups * Cfg::kSteps - 1) {
+          stage_supertile(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
+          if (gs == Cfg::kSuper - 1) {
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&t_empty[acc]);       // the leader's MMA warp owns the wait
@@ -960,10 +964,10 @@ corr_volume_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            const int col = nt * kBlockN + g * 2 * kW + s * 64;
-            const int colp = nt * (kBlockN / 4) + g * (kW / 2) + s * 32;
+            const int col = nt * kBlockN + gs * 128;
+            const int colp = nt * (kBlockN / 4) + gs * 32;
             tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes, col, row0, b);
-            tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + kW, row0, b);
+            tma_store_3d(&map_v0, smem_st + (size_t)ew * kStageWarpBytes + 4096, col + 64, row0, b);
             tma_store_3d(&map_v1, smem_st + (size_t)ew * kStageWarpBytes + 8192, colp, row0, b);
             tma_store_commit();
           }
@@ -1182,12 +1186,22 @@ extern "C" int64_t mrfa_corr_row_offset(int h, int w, int pool_log2) {
   return off;
 }
 
+extern "C" int mrfa_corr_map_layout(int h, int w) {
+  // the TMA-store GEMM kernels (w = 64 / 128: 256x256 and 512x512 frames) write tiled maps; the small-shape kernel keeps row-major
+  return ((w == 64 || w == 128) && h % 8 == 0) ? MRFA_MAP_TILED : MRFA_MAP_ROWMAJOR;
+}
+
+extern "C" int64_t mrfa_corr_map_offset(int map_layout, int level, int y, int x, int W_level) {
+  return map_layout == MRFA_MAP_TILED ? map_offset<true>(level, y, x, W_level) : map_offset<false>(level, y, x, W_level);
+}
+
 extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op, int B, int C, int h, int w,
                               int channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(q_d && k_s && a_op && b_op && B >= 0 && C > 0 && h > 0 && w > 0);
   MRFA_CHECK_SHAPE(C % kPackCh == 0 && h % 8 == 0 && w % 8 == 0 && B <= 65535);
   MRFA_CHECK_SHAPE(w <= 32 || w % 32 == 0);
   if (B == 0) return 0;
+  const int tiled = mrfa_corr_map_layout(h, w) == MRFA_MAP_TILED;
   if (channels_last) {
     if (((reinterpret_cast<uintptr_t>(q_d) | reinterpret_cast<uintptr_t>(k_s)) & 15) != 0) return MRFA_E_ALIGN;
     const int64_t rows_total = mrfa_corr_rows_total(h, w);
@@ -1202,8 +1216,12 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
     const int64_t n4 = (int64_t)B * h * w * C / 4;
     int64_t cblocks = cdiv64(n4, 256);
     if (cblocks > 148 * 32) cblocks = 148 * 32;
-    cast_bf16_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(k_s),
-                                                                      static_cast<uint2*>(b_op), n4);
+    if (tiled)
+      cast_bf16_tiled_rows_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(k_s), static_cast<uint2*>(b_op), (int64_t)B * h * w, h * w, w, C / 4);
+    else
+      cast_bf16_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(k_s),
+                                                                        static_cast<uint2*>(b_op), n4);
     return MRFA_LAUNCH_RESULT();
   }
   const int tile_w = w < 32 ? w : 32;
@@ -1211,17 +1229,8 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
   const size_t smem = (size_t)kPackCh * (kPackRows * tile_w + 1) * sizeof(float);
   corr_pack_kernel<<<grid, kPackThreads, smem, as_stream(stream)>>>(
       q_d, k_s, static_cast<__nv_bfloat16*>(a_op), static_cast<__nv_bfloat16*>(b_op), C, h, w, tile_w,
-      mrfa_corr_rows_total(h, w));
+      mrfa_corr_rows_total(h, w), tiled);
   return MRFA_LAUNCH_RESULT();
-}
-
-// MRFA_CORR_EPILOGUE=direct selects the v1 register-store epilogue (A/B measurements only)
-static bool use_direct_epilogue() {
-  static const bool v = []() {
-    const char* e = getenv("MRFA_CORR_EPILOGUE");
-    return e != nullptr && e[0] == 'd';
-  }();
-  return v;
 }
 
 // MRFA_CORR_VARIANT (A/B measurements only): 1 = 256-row units x 128-wide tiles, 4 = 2-CTA cluster with
@@ -1251,7 +1260,6 @@ extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume
     case 32: MRFA_CHECK_SHAPE(N % 128 == 0); return launch_corr_volume<32>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 64:
       MRFA_CHECK_SHAPE(N % 128 == 0);
-      if (use_direct_epilogue()) return launch_corr_volume<64>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       // 128-row units, 256-wide tiles (two source row pairs): every B tile (32 KiB per K block) feeds
       // 128x256 outputs and ~96 KiB of B stay in flight; deeper K falls back to 128-wide tiles
       if (corr_variant() == 1) return launch_corr_volume_tma<64, 128, 2, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
@@ -1261,7 +1269,6 @@ extern "C" int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume
       return launch_corr_volume_tma<64, 128, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
     case 128:
       MRFA_CHECK_SHAPE(N % 256 == 0);
-      if (use_direct_epilogue()) return launch_corr_volume<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       if (corr_variant() == 5) return launch_corr_volume_2sm<128>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       if (corr_variant() == 4) return launch_corr_volume_tma<128, 256, 1, 2>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);
       return launch_corr_volume_tma<128, 256, 1, 1>(a_op, b_op, volume0, volume1, B, C, h, w, scale, num_sms, st);

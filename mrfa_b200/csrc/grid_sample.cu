@@ -332,6 +332,129 @@ dual_warp_fwd_nhwc_kernel(const float* __restrict__ in, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Run-walk forward kernels (the production path for >= 100k output pixels).
+//
+// The plain NHWC kernels above pull 4 taps x C floats through L1 for every output pixel: 5 units of L1 / LSU traffic
+// (4 loads + 1 store) per unit of output, which at C = 64, R = 256 is more than the 128 B/clk/SM L1 data path delivers
+// in the time HBM needs for the algorithmic bytes -- the kernels were L1-bound at ~0.55 of the HBM roofline.
+// Motion fields are smooth: along a row the sample position advances by ~1 source pixel per output pixel, so the right
+// taps (ne, se) of pixel x are the left taps (nw, sw) of pixel x + 1.  Each lane group (the lanes that cover the C channels
+// of one pixel) therefore walks a RUN of consecutive pixels and keeps the previous right column in registers: when the
+// tap offsets chain (checked per pixel, exact -- any flow is still handled, it just reloads) a pixel costs 2 loads + 1
+// store.  V = floats per lane access: 8 -> 256-bit LDG.E.ENL2.256 / STG.E.ENL2.256 (sm_100), 4 -> 128-bit.
+// ---------------------------------------------------------------------------------------------
+template <int V> struct VecF { float v[V]; };
+
+template <int V> __device__ __forceinline__ VecF<V> ldgv(const float* p);
+template <> __device__ __forceinline__ VecF<4> ldgv<4>(const float* p) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  VecF<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+template <> __device__ __forceinline__ VecF<8> ldgv<8>(const float* p) {
+  VecF<8> r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+template <int V> __device__ __forceinline__ void stv(float* p, const VecF<V>& r);
+template <> __device__ __forceinline__ void stv<4>(float* p, const VecF<4>& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+template <> __device__ __forceinline__ void stv<8>(float* p, const VecF<8>& r) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+               "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]) : "memory");
+}
+template <int V>
+__device__ __forceinline__ VecF<V> blendv(const VecF<V>& a, const VecF<V>& b, const VecF<V>& c, const VecF<V>& d, const TapsB& t) {
+  VecF<V> r;     // same evaluation order as ATen / blend4b: nw, ne, sw, se
+#pragma unroll
+  for (int i = 0; i < V; ++i) r.v[i] = fmaf(d.v[i], t.w_se, fmaf(c.v[i], t.w_sw, fmaf(b.v[i], t.w_ne, a.v[i] * t.w_nw)));
+  return r;
+}
+
+// One pass of a warp over its 32 pixels: lane l holds the taps of pixel gp0 + l in `mine`; group `grp` (LPPE lanes) walks
+// pixels [grp * RUN, (grp + 1) * RUN) of the warp, channel chunk by channel chunk.
+template <int V, int LPPE>
+__device__ __forceinline__ void run_walk(const TapsB& mine, const float* __restrict__ in, float* __restrict__ out,
+                                         int64_t gp0, int64_t total, int C, int64_t plane, int64_t ostride, int lane) {
+  constexpr int G = 32 / LPPE;            // lane groups per warp
+  constexpr int RUN = 32 / G;             // consecutive pixels per group
+  const int grp = lane / LPPE, cl = (lane % LPPE) * V;
+  for (int c0 = 0; c0 < C; c0 += LPPE * V) {                     // warp-uniform trip count: the shuffles below need every lane
+    const int c = c0 + cl;
+    const bool act = c < C;
+    VecF<V> pr_ne, pr_se;
+    int po_ne = -1, po_se = -1, pn = -1;
+#pragma unroll 4
+    for (int i = 0; i < RUN; ++i) {
+      const TapsB t = shfl_taps(mine, grp * RUN + i);
+      const int64_t gp = gp0 + grp * RUN + i;
+      if (gp >= total || !act) continue;
+      const float* src = in + (int64_t)t.n_in * plane + c;
+      const bool chain = (t.o_nw == po_ne) & (t.o_sw == po_se) & (t.n_in == pn);
+      VecF<V> a, d;
+      if (chain) { a = pr_ne; d = pr_se; }
+      else { a = ldgv<V>(src + t.o_nw); d = ldgv<V>(src + t.o_sw); }
+      const VecF<V> b = ldgv<V>(src + t.o_ne), e = ldgv<V>(src + t.o_se);
+      stv<V>(out + gp * ostride + c, blendv<V>(a, b, d, e, t));
+      pr_ne = b; pr_se = e; po_ne = t.o_ne; po_se = t.o_se; pn = t.n_in;
+    }
+  }
+}
+
+template <int MODE, int PAD, bool ADD_ID, int V, int LPPE>
+__global__ void __launch_bounds__(kThreads)
+grid_sample_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
+                                float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div) {
+  const int HoWo = Ho * Wo;
+  const int lane = threadIdx.x % 32;
+  const int64_t total = (int64_t)N * HoWo;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 32;
+  if (gp0 >= total) return;
+  TapsB mine;
+  {
+    const int64_t gp = min(gp0 + lane, total - 1);
+    const int n = (int)(gp / HoWo);
+    const int p = (int)(gp - (int64_t)n * HoWo);
+    const int y = p / Wo, x = p - y * Wo;
+    float ix, iy, mx, my;
+    load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
+    mine = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div, C);
+  }
+  run_walk<V, LPPE>(mine, in, out, gp0, total, C, (int64_t)H * W * C, C, lane);
+}
+
+template <int V, int LPPE>
+__global__ void __launch_bounds__(kThreads)
+dual_warp_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
+                              float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W,
+                              int64_t cstride) {
+  const int HW = H * W;
+  const int lane = threadIdx.x % 32;
+  const int64_t total = (int64_t)N * HW;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 32;
+  if (gp0 >= total) return;
+  const int64_t gp = min(gp0 + lane, total - 1);
+  const int n = (int)(gp / HW);
+  const int p = (int)(gp - (int64_t)n * HW);
+  const int64_t plane = (int64_t)HW * C;
+  {   // refined warp: pixel flow + identity (raft.py:247)
+    const int y = p / W, x = p - y * W;
+    const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
+    const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
+    const TapsB m = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n, C);
+    run_walk<V, LPPE>(m, in, out_r, gp0, total, C, plane, C, lane);
+  }
+  {   // coarse warp: normalised prior grid, align_corners=False (raft.py:271); may land in a channel slice of a wider buffer
+    const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
+    const TapsB m = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n, C);
+    run_walk<V, LPPE>(m, in, out_c, gp0, total, C, plane, cstride, lane);
+  }
+}
+
 // NHWC backward: one thread group (16 lanes) per output pixel; the grad_input scatter is a
 // vector red.global.add.v4.f32 per tap and channel quad; the coordinate gradient is reduced over
 // the channel axis with shuffles inside the 16-lane group.
@@ -401,11 +524,49 @@ static inline int lanes_per_pixel(int C) {
 
 constexpr int64_t kSmallPixels = 100000;     // below this, 4 pixels per warp keep the SMs busy
 
+// run-walk configuration: lanes per pixel for V floats per lane (power of two, <= 32)
+static inline int lanes_per_pixel_v(int C, int V) {
+  int l = 1;
+  while (l < 32 && l * 2 * V <= C) l *= 2;
+  return l;
+}
+// MRFA_WARP_RUN=0 selects the plain (4 loads per pixel) kernels, MRFA_WARP_VEC=4 the 128-bit run-walk (A/B measurements only)
+static int warp_run_mode() {
+  static const int v = []() { const char* e = getenv("MRFA_WARP_RUN"); return e ? atoi(e) : 1; }();
+  return v;
+}
+static int warp_vec_pref() {
+  static const int v = []() { const char* e = getenv("MRFA_WARP_VEC"); return e ? atoi(e) : 8; }();
+  return v;
+}
+static inline int pick_vec(int C, const void* a, const void* b, const void* c, int64_t ostride) {
+  const bool al32 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 31) == 0;
+  return (warp_vec_pref() == 8 && C % 8 == 0 && ostride % 8 == 0 && al32) ? 8 : 4;
+}
+
+template <int MODE, int PAD, bool ADD_ID>
+static int launch_fwd_nhwc_run(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C,
+                               int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
+  const int64_t pixels = (int64_t)N * Ho * Wo;
+  dim3 g((unsigned)cdiv64(cdiv64(pixels, 32), kThreads / 32));
+  const int V = pick_vec(C, in, out, out, C);
+#define MRFA_GSR_CASE(VV, L)                                                                                          \
+  case L: grid_sample_fwd_nhwc_run_kernel<MODE, PAD, ADD_ID, VV, L><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); break;
+  if (V == 8) {
+    switch (lanes_per_pixel_v(C, 8)) { MRFA_GSR_CASE(8, 1) MRFA_GSR_CASE(8, 2) MRFA_GSR_CASE(8, 4) MRFA_GSR_CASE(8, 8) MRFA_GSR_CASE(8, 16) MRFA_GSR_CASE(8, 32) }
+  } else {
+    switch (lanes_per_pixel_v(C, 4)) { MRFA_GSR_CASE(4, 1) MRFA_GSR_CASE(4, 2) MRFA_GSR_CASE(4, 4) MRFA_GSR_CASE(4, 8) MRFA_GSR_CASE(4, 16) MRFA_GSR_CASE(4, 32) }
+  }
+#undef MRFA_GSR_CASE
+  return MRFA_LAUNCH_RESULT();
+}
+
 template <int MODE, int PAD, bool ADD_ID>
 static int launch_fwd_nhwc_lpp(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C,
                                int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
   const int64_t pixels = (int64_t)N * Ho * Wo;
   const bool small = pixels < kSmallPixels;
+  if (!small && warp_run_mode()) return launch_fwd_nhwc_run<MODE, PAD, ADD_ID>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
   static const int unroll = []() { const char* e = getenv("MRFA_WARP_UNROLL"); return e ? atoi(e) : 2; }();
   dim3 g((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
 #define MRFA_GS_CASE(L)                                                                                            \
@@ -530,6 +691,19 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
     dim3 gn((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
     cudaStream_t st = as_stream(stream);
     const int64_t cs = coarse_pixel_stride > 0 ? coarse_pixel_stride : C;
+    if (!small && warp_run_mode()) {
+      dim3 gr((unsigned)cdiv64(cdiv64(pixels, 32), kThreads / 32));
+      const int V = pick_vec(C, in, out_refined, out_coarse, cs);
+#define MRFA_DWR_CASE(VV, L)                                                                                         \
+  case L: dual_warp_fwd_nhwc_run_kernel<VV, L><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs); break;
+      if (V == 8) {
+        switch (lanes_per_pixel_v(C, 8)) { MRFA_DWR_CASE(8, 1) MRFA_DWR_CASE(8, 2) MRFA_DWR_CASE(8, 4) MRFA_DWR_CASE(8, 8) MRFA_DWR_CASE(8, 16) MRFA_DWR_CASE(8, 32) }
+      } else {
+        switch (lanes_per_pixel_v(C, 4)) { MRFA_DWR_CASE(4, 1) MRFA_DWR_CASE(4, 2) MRFA_DWR_CASE(4, 4) MRFA_DWR_CASE(4, 8) MRFA_DWR_CASE(4, 16) MRFA_DWR_CASE(4, 32) }
+      }
+#undef MRFA_DWR_CASE
+      return MRFA_LAUNCH_RESULT();
+    }
 #define MRFA_DW_CASE(L)                                                                                              \
   case L:                                                                                                            \
     if (small) dual_warp_fwd_nhwc_kernel<L, 4><<<gn, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs); \

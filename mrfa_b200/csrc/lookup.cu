@@ -42,7 +42,7 @@ __device__ __forceinline__ QueryGeom query_geom(float cx, float cy, int lvl, int
   return g;
 }
 
-template <typename T, int R>
+template <typename T, int R, bool TILED>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level1, const float* __restrict__ coords,
                        float* __restrict__ out, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
@@ -103,7 +103,7 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
           const int fy_ = e / F, fx_ = e - fy_ * F;
           const int yy = gy0 + fy_, xx = gx0 + fx_;
           float t = 0.f;
-          if (live && e < FF && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) t = ld_elem<T>(base + yy * Wl + xx);
+          if (live && e < FF && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) t = ld_elem<T>(base + map_offset<TILED>(lvl, yy, xx, Wl));
           v[g][lvl][it] = t;
         }
       }
@@ -165,11 +165,137 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tiled bf16 pyramid maps (the volume written by mrfa_corr_volume for w = 64 / 128), r <= 3.
+// One warp instruction fetches BOTH footprints of a query: lane = (level, footprint row, tile
+// column) loads one 16-byte tile row -- 8 rows x 2 tile columns x 2 levels = 32 lanes -- so a
+// query costs 4-6 64-byte granules per level instead of 8 scattered 16-byte row pieces, and
+// kGroupT queries per lane are in flight before the first shared-memory store.
+// Shared memory keeps the 8 x 16 bf16 patches; phase 2 evaluates from them (fp32 arithmetic).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPatchWords = 2 * 8 * 16 / 2;          // two levels x 8 rows x 16 columns of bf16, in 32-bit words
+constexpr int kPatchStride = kPatchWords + 1;        // odd -> lane-per-query reads spread over the banks
+
+__device__ __forceinline__ float bf16_at(const uint32_t* patch, int e) {      // element e of a patch held as packed words
+  const uint32_t wv = patch[e >> 1];
+  return __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+}
+
+template <int R>
+__global__ void __launch_bounds__(kLookupThreads)
+corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __nv_bfloat16* __restrict__ level1,
+                             const float* __restrict__ coords, float* __restrict__ out, int Q, int H, int W,
+                             int64_t map_batch_stride, int64_t row_offset, int out_channels_last) {
+  constexpr int n = 2 * R + 1, F = n + 1;
+  static_assert(F <= 8, "the footprint must fit the 8 x 16 patch");
+  __shared__ uint32_t patch[kQPB * kPatchStride];
+  __shared__ float frac[kQPB][4];
+  __shared__ int org[kQPB][4];
+
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * kQPB;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int H1 = H / 2, W1 = W / 2;
+
+  if (warp == 0) {                                    // phase 0: lane = query, IEEE coordinate round trip once per query
+    const int q = q0 + lane;
+    if (q < Q) {
+      const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
+      const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
+#pragma unroll
+      for (int lvl = 0; lvl < 2; ++lvl) {
+        const QueryGeom g = query_geom(cx, cy, lvl, lvl ? H1 : H, lvl ? W1 : W, R);
+        frac[lane][2 * lvl] = g.fx; frac[lane][2 * lvl + 1] = g.fy;
+        org[lane][2 * lvl] = g.x0; org[lane][2 * lvl + 1] = g.y0;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: lane = (level, row, tile column); kGroupT queries per round
+  constexpr int kWarps = kLookupThreads / 32;
+  constexpr int kPerWarp = kQPB / kWarps;
+  constexpr int kGroupT = 8;
+  static_assert(kPerWarp % kGroupT == 0, "query grouping");
+  const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
+  const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
+  const __nv_bfloat16* lbase = lvl ? level1 : level0;
+  const int64_t map_elems = (int64_t)Hl * Wl;
+#pragma unroll 1
+  for (int g0 = 0; g0 < kPerWarp; g0 += kGroupT) {
+    uint4 v[kGroupT];
+#pragma unroll
+    for (int g = 0; g < kGroupT; ++g) {
+      const int qi = warp + (g0 + g) * kWarps;
+      const int x0 = org[qi][2 * lvl], y0 = org[qi][2 * lvl + 1];
+      const int y = y0 + r, tx = (x0 >> 3) + half;          // arithmetic shift: floor for negative origins
+      // the second tile column is only needed when the footprint crosses an 8-column boundary
+      const bool ok = (q0 + qi < Q) && r < F && y >= 0 && y < Hl && tx >= 0 && tx < (Wl >> 3) &&
+                      (half == 0 || (x0 & 7) + F > 8);
+      v[g] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) {
+        const int64_t map = (int64_t)b * map_batch_stride + row_offset + q0 + qi;
+        v[g] = __ldg(reinterpret_cast<const uint4*>(lbase + map * map_elems + map_offset<true>(lvl, y, tx * 8, Wl)));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroupT; ++g) {
+      const int qi = warp + (g0 + g) * kWarps;
+      uint32_t* d = patch + qi * kPatchStride + lane * 4;    // word (lvl*64 + r*8 + half*4) == lane*4
+      d[0] = v[g].x; d[1] = v[g].y; d[2] = v[g].z; d[3] = v[g].w;
+    }
+  }
+  __syncthreads();
+
+  if (out_channels_last) {
+    // ---- phase 2 (NHWC output): warp per query, lanes along the 2*(2r+1)^2 contiguous channels
+    for (int qi = warp; qi < kQPB; qi += kWarps) {
+      const int q = q0 + qi;
+      if (q >= Q) break;
+      const uint32_t* pq = patch + qi * kPatchStride;
+      float* dst = out + ((int64_t)b * Q + q) * (2 * n * n);
+      for (int k = lane; k < 2 * n * n; k += 32) {
+        const int l = k / (n * n), kk = k - l * n * n;
+        const int a = kk / n, bb = kk - a * n;
+        const float fx = frac[qi][2 * l], fy = frac[qi][2 * l + 1];
+        const int e = l * 128 + bb * 16 + (org[qi][2 * l] & 7) + a;
+        float acc = bf16_at(pq, e) * ((1.f - fx) * (1.f - fy));
+        acc = fmaf(bf16_at(pq, e + 1), fx * (1.f - fy), acc);
+        acc = fmaf(bf16_at(pq, e + 16), (1.f - fx) * fy, acc);
+        acc = fmaf(bf16_at(pq, e + 17), fx * fy, acc);
+        dst[k] = acc;
+      }
+    }
+    return;
+  }
+  // ---- phase 2 (NCHW output): lane = query, warps stride over the channels
+  const int q = q0 + lane;
+  if (q >= Q) return;
+  const uint32_t* pq = patch + lane * kPatchStride;
+  float* dst = out + (int64_t)b * (2 * n * n) * Q + q;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const float fx = frac[lane][2 * l], fy = frac[lane][2 * l + 1];
+    const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
+    const int e0 = l * 128 + (org[lane][2 * l] & 7);
+    for (int k = warp; k < n * n; k += kWarps) {
+      const int a = k / n, bb = k - a * n;
+      const int e = e0 + bb * 16 + a;
+      float acc = bf16_at(pq, e) * w_nw;
+      acc = fmaf(bf16_at(pq, e + 1), w_ne, acc);
+      acc = fmaf(bf16_at(pq, e + 16), w_sw, acc);
+      acc = fmaf(bf16_at(pq, e + 17), w_se, acc);
+      *(dst + (int64_t)(l * n * n + k) * Q) = acc;
+    }
+  }
+}
+
 // Backward: footprint-cell gradients are assembled by a gather over the (at most four) window
 // taps that touch a cell -- the overlapping-tap pre-reduction -- and leave the block as one
 // red.global per in-image cell (128 instead of 392 atomics per query); coordinate gradients
 // are reduced over the channel axis with warp shuffles.
-template <typename T, int R>
+template <typename T, int R, bool TILED>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_bwd_kernel(const float* __restrict__ grad_out, const T* __restrict__ level0,
                        const T* __restrict__ level1, const float* __restrict__ coords,
@@ -223,10 +349,10 @@ corr_lookup_bwd_kernel(const float* __restrict__ grad_out, const T* __restrict__
           if (fy_ < n && fx_ >= 1) acc = fmaf(gq[lvl * NN + (fx_ - 1) * n + fy_], w_ne, acc);
           if (fy_ >= 1 && fx_ < n) acc = fmaf(gq[lvl * NN + fx_ * n + (fy_ - 1)], w_sw, acc);
           if (fy_ >= 1 && fx_ >= 1) acc = fmaf(gq[lvl * NN + (fx_ - 1) * n + (fy_ - 1)], w_se, acc);
-          if (acc != 0.f) atomicAdd(gl + map * ((int64_t)Hl * Wl) + (int64_t)yy * Wl + xx, acc);
+          if (acc != 0.f) atomicAdd(gl + map * ((int64_t)Hl * Wl) + map_offset<TILED>(lvl, yy, xx, Wl), acc);
         }
         // (2) stage the map values for the coordinate gradient (zero outside the image)
-        if (grad_coords != nullptr) foot[warp][e] = inside ? ld_elem<T>(base + (int64_t)yy * Wl + xx) : 0.f;
+        if (grad_coords != nullptr) foot[warp][e] = inside ? ld_elem<T>(base + map_offset<TILED>(lvl, yy, xx, Wl)) : 0.f;
       }
       if (grad_coords != nullptr) {
         __syncwarp();
@@ -272,23 +398,38 @@ avg_pool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_
 
 using namespace mrfa;
 
-template <typename T>
+template <typename T, bool TILED>
 static int launch_lookup_fwd(const void* l0, const void* l1, const float* coords, float* out, int B, int Q, int H,
                              int W, int64_t mbs, int64_t ro, int radius, int ocl, cudaStream_t st) {
   dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
   const T* a = static_cast<const T*>(l0);
   const T* b = static_cast<const T*>(l1);
   switch (radius) {
-    case 1: corr_lookup_fwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
-    case 2: corr_lookup_fwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
-    case 3: corr_lookup_fwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
-    case 4: corr_lookup_fwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 1: corr_lookup_fwd_kernel<T, 1, TILED><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 2: corr_lookup_fwd_kernel<T, 2, TILED><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 3: corr_lookup_fwd_kernel<T, 3, TILED><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 4: corr_lookup_fwd_kernel<T, 4, TILED><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
     default: return MRFA_E_SHAPE;
   }
   return MRFA_LAUNCH_RESULT();
 }
 
-template <typename T>
+// bf16 tiled maps, radius <= 3: the vectorised tile walk
+static int launch_lookup_fwd_tiled(const void* l0, const void* l1, const float* coords, float* out, int B, int Q, int H,
+                                   int W, int64_t mbs, int64_t ro, int radius, int ocl, cudaStream_t st) {
+  dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(l0);
+  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(l1);
+  switch (radius) {
+    case 1: corr_lookup_fwd_tiled_kernel<1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 2: corr_lookup_fwd_tiled_kernel<2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 3: corr_lookup_fwd_tiled_kernel<3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    default: return launch_lookup_fwd<__nv_bfloat16, true>(l0, l1, coords, out, B, Q, H, W, mbs, ro, radius, ocl, st);
+  }
+  return MRFA_LAUNCH_RESULT();
+}
+
+template <typename T, bool TILED>
 static int launch_lookup_bwd(const float* go, const void* l0, const void* l1, const float* coords, float* g0,
                              float* g1, float* gc, int B, int Q, int H, int W, int64_t mbs, int64_t ro, int radius,
                              cudaStream_t st) {
@@ -296,40 +437,58 @@ static int launch_lookup_bwd(const float* go, const void* l0, const void* l1, co
   const T* a = static_cast<const T*>(l0);
   const T* b = static_cast<const T*>(l1);
   switch (radius) {
-    case 1: corr_lookup_bwd_kernel<T, 1><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
-    case 2: corr_lookup_bwd_kernel<T, 2><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
-    case 3: corr_lookup_bwd_kernel<T, 3><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
-    case 4: corr_lookup_bwd_kernel<T, 4><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 1: corr_lookup_bwd_kernel<T, 1, TILED><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 2: corr_lookup_bwd_kernel<T, 2, TILED><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 3: corr_lookup_bwd_kernel<T, 3, TILED><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
+    case 4: corr_lookup_bwd_kernel<T, 4, TILED><<<g, kLookupThreads, 0, st>>>(go, a, b, coords, g0, g1, gc, Q, H, W, mbs, ro); break;
     default: return MRFA_E_SHAPE;
   }
   return MRFA_LAUNCH_RESULT();
 }
 
+static bool tiled_ok(int elem_bf16, int H, int W) {      // the tiled layout exists for bf16 maps with whole super-tiles only
+  return elem_bf16 && H % 8 == 0 && W % 16 == 0;
+}
+
 extern "C" int mrfa_corr_lookup_fwd(const void* level0, const void* level1, int elem_bf16, const float* coords,
                                     float* out, int B, int Q, int H, int W, int64_t map_batch_stride,
-                                    int64_t row_offset, int radius, int out_channels_last, mrfa_stream_t stream) {
+                                    int64_t row_offset, int radius, int map_layout, int out_channels_last,
+                                    mrfa_stream_t stream) {
   MRFA_CHECK_ARG(level0 && level1 && coords && out);
   MRFA_CHECK_ARG(B >= 0 && Q > 0 && H >= 2 && W >= 2 && map_batch_stride >= 0 && row_offset >= 0);
+  MRFA_CHECK_ARG(map_layout == MRFA_MAP_ROWMAJOR || map_layout == MRFA_MAP_TILED);
   MRFA_CHECK_SHAPE(radius >= 1 && radius <= kMaxR && B <= 65535);
   if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (map_layout == MRFA_MAP_TILED) {
+    MRFA_CHECK_SHAPE(tiled_ok(elem_bf16, H, W));
+    if (((reinterpret_cast<uintptr_t>(level0) | reinterpret_cast<uintptr_t>(level1)) & 15) != 0) return MRFA_E_ALIGN;
+    return launch_lookup_fwd_tiled(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, st);
+  }
   if (elem_bf16)
-    return launch_lookup_fwd<__nv_bfloat16>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, as_stream(stream));
-  return launch_lookup_fwd<float>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, as_stream(stream));
+    return launch_lookup_fwd<__nv_bfloat16, false>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, st);
+  return launch_lookup_fwd<float, false>(level0, level1, coords, out, B, Q, H, W, map_batch_stride, row_offset, radius, out_channels_last, st);
 }
 
 extern "C" int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* level1, int elem_bf16,
                                     const float* coords, float* grad_level0, float* grad_level1, float* grad_coords,
                                     int B, int Q, int H, int W, int64_t map_batch_stride, int64_t row_offset,
-                                    int radius, mrfa_stream_t stream) {
+                                    int radius, int map_layout, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(grad_out && level0 && level1 && coords);
   MRFA_CHECK_ARG((grad_level0 == nullptr) == (grad_level1 == nullptr));
   MRFA_CHECK_ARG(grad_level0 || grad_coords);
   MRFA_CHECK_ARG(B >= 0 && Q > 0 && H >= 2 && W >= 2 && map_batch_stride >= 0 && row_offset >= 0);
+  MRFA_CHECK_ARG(map_layout == MRFA_MAP_ROWMAJOR || map_layout == MRFA_MAP_TILED);
   MRFA_CHECK_SHAPE(radius >= 1 && radius <= kMaxR && B <= 65535);
   if (B == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (map_layout == MRFA_MAP_TILED) {
+    MRFA_CHECK_SHAPE(tiled_ok(elem_bf16, H, W));
+    return launch_lookup_bwd<__nv_bfloat16, true>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, st);
+  }
   if (elem_bf16)
-    return launch_lookup_bwd<__nv_bfloat16>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
-  return launch_lookup_bwd<float>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, as_stream(stream));
+    return launch_lookup_bwd<__nv_bfloat16, false>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, st);
+  return launch_lookup_bwd<float, false>(grad_out, level0, level1, coords, grad_level0, grad_level1, grad_coords, B, Q, H, W, map_batch_stride, row_offset, radius, st);
 }
 
 extern "C" int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_stream_t stream) {

@@ -461,6 +461,24 @@ def corr_row_offset(h: int, w: int, pool_log2: int) -> int:
     return int(lib.mrfa_corr_row_offset(h, w, pool_log2))
 
 
+def corr_map_layout(h: int, w: int) -> int:
+    """Layout of the maps mrfa_corr_volume writes for an h x w plane (_lib.MAP_ROWMAJOR / _lib.MAP_TILED)."""
+    return int(lib.mrfa_corr_map_layout(h, w))
+
+
+_MAP_PERM = {}
+
+
+def corr_map_permutation(layout: int, level: int, H: int, W: int, device) -> Tensor:
+    """index[y * W + x] = position of element (y, x) inside a map stored in `layout` (int64, cached per device);
+    ``map.index_select(-1, index)`` turns a stored map back into row-major order."""
+    key = (layout, level, H, W, str(device))
+    if key not in _MAP_PERM:
+        idx = [int(lib.mrfa_corr_map_offset(layout, level, y, x, W)) for y in range(H) for x in range(W)]
+        _MAP_PERM[key] = torch.tensor(idx, dtype=torch.int64, device=device)
+    return _MAP_PERM[key]
+
+
 @torch.library.custom_op("mrfa::corr_pyramid", mutates_args=(), device_types="cuda")
 def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
     """(B,C,h,w) x2 -> volume0 (B, rows_total, h*w) bf16, volume1 (B, rows_total, h*w/4) bf16."""
@@ -541,8 +559,8 @@ avg_pool2x2.register_autograd(_ap_backward, setup_context=_ap_setup)
 
 @torch.library.custom_op("mrfa::corr_lookup", mutates_args=(), device_types="cuda")
 def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, map_batch_stride: int,
-                row_offset: int, radius: int, channels_last: bool) -> Tensor:
-    """coords (B,2,h1,w1) -> (B, 2*(2r+1)^2, h1, w1).  level maps fp32 or bf16 (see the header)."""
+                row_offset: int, radius: int, map_layout: int, channels_last: bool) -> Tensor:
+    """coords (B,2,h1,w1) -> (B, 2*(2r+1)^2, h1, w1).  level maps fp32 or bf16, row-major or tiled (see the header)."""
     coords = _req(coords, "coords")
     if level0.dtype != level1.dtype or level0.dtype not in (torch.float32, torch.bfloat16):
         raise RuntimeError("mrfa_b200: correlation levels must both be float32 or both bfloat16")
@@ -554,13 +572,13 @@ def corr_lookup(level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int, 
     with torch.cuda.device(coords.device):
         with _timed("corr_lookup_fwd", B * h1 * w1 * (2 * (2 * radius + 2) ** 2 * level0.element_size() + 8 + 4 * 2 * n * n)):
             check(lib.mrfa_corr_lookup_fwd(_p(level0), _p(level1), int(level0.dtype == torch.bfloat16), _p(coords), _p(out),
-                                           B, h1 * w1, H, W, map_batch_stride, row_offset, radius, int(channels_last),
-                                           _stream()), "mrfa_corr_lookup_fwd")
+                                           B, h1 * w1, H, W, map_batch_stride, row_offset, radius, map_layout,
+                                           int(channels_last), _stream()), "mrfa_corr_lookup_fwd")
     return out
 
 
 @corr_lookup.register_fake
-def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius, channels_last):
+def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius, map_layout, channels_last):
     B, _, h1, w1 = coords.shape
     out = coords.new_empty((B, 2 * (2 * radius + 1) ** 2, h1, w1))
     return out.contiguous(memory_format=torch.channels_last) if channels_last else out
@@ -568,7 +586,7 @@ def _(level0, level1, coords, H, W, map_batch_stride, row_offset, radius, channe
 
 @torch.library.custom_op("mrfa::corr_lookup_bwd", mutates_args=(), device_types="cuda")
 def corr_lookup_bwd(grad_out: Tensor, level0: Tensor, level1: Tensor, coords: Tensor, H: int, W: int,
-                    map_batch_stride: int, row_offset: int, radius: int, need_levels: bool,
+                    map_batch_stride: int, row_offset: int, radius: int, map_layout: int, need_levels: bool,
                     need_coords: bool) -> Tuple[Tensor, Tensor, Tensor]:
     grad_out, coords = _req(grad_out, "grad_out"), _req(coords, "coords")
     B, _, h1, w1 = coords.shape
@@ -581,20 +599,20 @@ def corr_lookup_bwd(grad_out: Tensor, level0: Tensor, level1: Tensor, coords: Te
             check(lib.mrfa_corr_lookup_bwd(_p(grad_out), _p(level0), _p(level1), int(level0.dtype == torch.bfloat16),
                                            _p(coords), _p(g0) if need_levels else None, _p(g1) if need_levels else None,
                                            _p(gc) if need_coords else None, B, h1 * w1, H, W, map_batch_stride,
-                                           row_offset, radius, _stream()), "mrfa_corr_lookup_bwd")
+                                           row_offset, radius, map_layout, _stream()), "mrfa_corr_lookup_bwd")
     return g0, g1, gc
 
 
 @corr_lookup_bwd.register_fake
-def _(grad_out, level0, level1, coords, H, W, map_batch_stride, row_offset, radius, need_levels, need_coords):
+def _(grad_out, level0, level1, coords, H, W, map_batch_stride, row_offset, radius, map_layout, need_levels, need_coords):
     f = lambda t: coords.new_empty(tuple(t.shape)) if need_levels else coords.new_empty(0)
     return f(level0), f(level1), torch.empty_like(coords) if need_coords else coords.new_empty(0)
 
 
 def _cl_setup(ctx, inputs, output):
-    level0, level1, coords, H, W, mbs, ro, radius, _cl = inputs
+    level0, level1, coords, H, W, mbs, ro, radius, layout, _cl = inputs
     ctx.save_for_backward(level0, level1, coords)
-    ctx.cfg = (H, W, mbs, ro, radius)
+    ctx.cfg = (H, W, mbs, ro, radius, layout)
 
 
 def _cl_backward(ctx, g):
@@ -604,7 +622,7 @@ def _cl_backward(ctx, g):
     g0, g1, gc = torch.ops.mrfa.corr_lookup_bwd(g, level0, level1, coords, *ctx.cfg, need_levels, need_coords)
     return (g0.to(level0.dtype) if ctx.needs_input_grad[0] else None,
             g1.to(level1.dtype) if ctx.needs_input_grad[1] else None,
-            gc if need_coords else None, None, None, None, None, None, None)
+            gc if need_coords else None, None, None, None, None, None, None, None)
 
 
 corr_lookup.register_autograd(_cl_backward, setup_context=_cl_setup)

@@ -25,6 +25,8 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--only", default="")
 ap.add_argument("--C", type=int, default=256)
 ap.add_argument("--stock", action="store_true", help="also time the stock PyTorch op on the same shapes")
+ap.add_argument("--flow", default="smooth", choices=["smooth", "random"],
+                help="warp benchmarks: smooth = low-resolution random motion upsampled (what RaftFlow produces); random = i.i.d. per pixel")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -89,6 +91,7 @@ with torch.no_grad():
         v0 = torch.empty((B, rows, N), device=dev, dtype=torch.bfloat16)
         v1 = torch.empty((B, rows, N // 4), device=dev, dtype=torch.bfloat16)
         st = lambda: ops._stream()
+        layout = ops.corr_map_layout(h, w)
         pack = lambda: ops.check(ops.lib.mrfa_corr_pack(ops._p(q), ops._p(k), ops._p(a_op), ops._p(b_op), B, C, h, w, 0, st()))
         qcl, kcl = q.contiguous(memory_format=torch.channels_last), k.contiguous(memory_format=torch.channels_last)
         pack_cl = lambda: ops.check(ops.lib.mrfa_corr_pack(ops._p(qcl), ops._p(kcl), ops._p(a_op), ops._p(b_op), B, C, h, w, 1, st()))
@@ -125,9 +128,32 @@ with torch.no_grad():
             coords = (torch.rand(B, 2, Rq, Rq, device=dev) * (h + 4) - 2)
             off = ops.corr_row_offset(h, w, lvl)
             for cl in (False, True):
-                fn = lambda: torch.ops.mrfa.corr_lookup(v0, v1, coords, h, w, rows, off, 3, cl)
+                fn = lambda: torch.ops.mrfa.corr_lookup(v0, v1, coords, h, w, rows, off, 3, layout, cl)
                 ms = timeit(fn)
-                report(f"corr_lookup_fwd[Q={Rq}x{Rq} {'nhwc' if cl else 'nchw'}]", ms, B * Rq * Rq * (2 * 64 * 2 + 8 + 98 * 4))
+                report(f"corr_lookup_fwd[Q={Rq}x{Rq} {'nhwc' if cl else 'nchw'}]", ms, B * Rq * Rq * (2 * 64 * 2 + 8 + 98 * 4),
+                       layout="tiled" if layout else "rowmajor")
+            if a.stock and Rq == h:
+                # the reference's CorrBlock on the same GPU: fp32 volume rows -> avg_pool2d level 1 -> two F.grid_sample calls
+                # (raft.py:12-48), timed on a few pairs and scaled
+                nb = min(B, 4)
+                corr32 = v0[:nb, off:off + Rq * Rq].float().reshape(nb * Rq * Rq, 1, h, w)
+                cc = coords[:nb]
+
+                def stock_block():
+                    lv1 = F.avg_pool2d(corr32, 2, stride=2)
+                    d = torch.linspace(-3, 3, 7, device=dev)
+                    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, 7, 7, 2)
+                    cen = cc.permute(0, 2, 3, 1).reshape(-1, 1, 1, 2)
+                    outs = []
+                    for lv, mp in enumerate((corr32, lv1)):
+                        pts = cen / 2 ** lv + delta
+                        Hm, Wm = mp.shape[-2:]
+                        g = torch.cat([2 * pts[..., :1] / (Wm - 1) - 1, 2 * pts[..., 1:] / (Hm - 1) - 1], -1)
+                        outs.append(F.grid_sample(mp, g, align_corners=True).view(nb, Rq, Rq, 49))
+                    return torch.cat(outs, -1).permute(0, 3, 1, 2).contiguous()
+                ms = timeit(stock_block)
+                report(f"stock_CorrBlock[Q={Rq}x{Rq}] (avg_pool2d + 2x grid_sample, fp32 volume)", ms * B / nb,
+                       B * Rq * Rq * (2 * 64 * 2 + 8 + 98 * 4), note=f"timed on {nb} pairs, scaled; same algorithmic bytes as ours")
         del v0, v1, a_op, b_op
 
     if want("warp"):
@@ -135,17 +161,24 @@ with torch.no_grad():
         for i, R in enumerate([S // 32 * 2 ** j for j in range(6)]):
             Cc = chans[i]
             feat = torch.randn(B, Cc, R, R, device=dev)
-            flow = torch.randn(B, 2, R, R, device=dev) * 2.0
-            prior = (mrfa_b200.make_coordinate_grid((R, R), "torch.cuda.FloatTensor")[None] +
-                     torch.randn(B, R, R, 2, device=dev) * 0.05).contiguous()
+            if a.flow == "random":                                     # per-pixel random displacements (no tap reuse)
+                flow = torch.randn(B, 2, R, R, device=dev) * 2.0
+                prior = (mrfa_b200.make_coordinate_grid((R, R), "torch.cuda.FloatTensor")[None] +
+                         torch.randn(B, R, R, 2, device=dev) * 0.05).contiguous()
+            else:                                                      # motion fields as the path produces them: low-res, upsampled
+                lo = max(2, R // 8)
+                flow = F.interpolate(torch.randn(B, 2, lo, lo, device=dev) * 3.0, size=(R, R), mode="bilinear", align_corners=True)
+                prior = (mrfa_b200.make_coordinate_grid((R, R), "torch.cuda.FloatTensor")[None] +
+                         F.interpolate(torch.randn(B, 2, lo, lo, device=dev) * 0.05, size=(R, R), mode="bilinear",
+                                       align_corners=True).permute(0, 2, 3, 1)).contiguous()
             elems = B * Cc * R * R
             for fmt in ("nchw", "nhwc"):
                 f_ = feat if fmt == "nchw" else feat.contiguous(memory_format=torch.channels_last)
                 try:
                     ms = timeit(lambda: mrfa_b200.warp_by_flow(f_, flow))
-                    report(f"grid_sample_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R))
+                    report(f"grid_sample_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R), flow=a.flow)
                     ms = timeit(lambda: torch.ops.mrfa.dual_warp(f_, flow, prior))
-                    report(f"dual_warp_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (3 * elems + 4 * B * R * R))
+                    report(f"dual_warp_fwd[{fmt} C={Cc} R={R}]", ms, 4 * (3 * elems + 4 * B * R * R), flow=a.flow)
                 except Exception as e:  # layout not supported yet
                     print(json.dumps({"kernel": f"warp[{fmt} C={Cc} R={R}]", "error": str(e)[:120]}))
             if a.stock:

@@ -229,11 +229,13 @@ def test_corr_volume_sizes(h, w, C, B):
         kk = 2 ** lvl
         qp = F.avg_pool2d(q.double(), kk) if kk > 1 else q.double()
         r = torch.einsum("bic,bjc->bij", qp.flatten(2).transpose(1, 2), kd) * C ** -0.5
-        rel_close(pyr.volume0[:, off:off + r.shape[1]], r)
+        # dense(): row-major view of the stored maps ((64, 64) is stored tiled, the small shapes row-major)
+        rel_close(pyr.dense(lvl).view(B, -1, h * w), r)
         l1 = F.avg_pool2d(r.view(B, -1, h, w), 2).flatten(2)
-        rel_close(pyr.volume1[:, off:off + r.shape[1]], l1)
+        rel_close(pyr.dense(lvl, 1).view(B, -1, h * w // 4), l1)
         off += r.shape[1]
     assert off == pyr.rows_total
+    assert pyr.layout == (m._lib.MAP_TILED if w in (64, 128) else m._lib.MAP_ROWMAJOR)
 
 
 def test_corr_shape_errors():
@@ -257,8 +259,11 @@ def test_corr_volume_512_tile_geometry():
     qd = q.flatten(2).transpose(1, 2)[:, idx].double()
     kd = k.flatten(2).transpose(1, 2).double()
     ref = torch.einsum("bic,bjc->bij", qd, kd) * C ** -0.5
-    rel_close(pyr.volume0[:, idx], ref)
-    rel_close(pyr.volume1[:, idx], F.avg_pool2d(ref.view(B, -1, h, h), 2).flatten(2))
+    assert pyr.layout == m._lib.MAP_TILED
+    p0 = m.ops.corr_map_permutation(pyr.layout, 0, h, h, DEV)
+    p1 = m.ops.corr_map_permutation(pyr.layout, 1, h // 2, h // 2, DEV)
+    rel_close(pyr.volume0[:, idx].float().index_select(2, p0), ref)
+    rel_close(pyr.volume1[:, idx].float().index_select(2, p1), F.avg_pool2d(ref.view(B, -1, h, h), 2).flatten(2))
 
 
 def test_corr_lookup_golden(golden):
@@ -288,6 +293,67 @@ def test_corr_lookup_from_bf16_pyramid(golden):
         l1 = pyr.volume1[:, off:off + Q].float().reshape(B * Q, 1, h // 2, w // 2).cpu().numpy()
         close(got, O.corr_lookup([l0, l1], c[f"coords_k{kk}"]))
         rel_close(got, c[f"lookup_k{kk}"])                                    # and 2e-2 of the fp32 reference
+
+
+@pytest.mark.parametrize("h,w,C", [(64, 64, 64), (16, 128, 64)])
+def test_corr_lookup_from_tiled_pyramid(h, w, C):
+    """w = 64 / 128: the volume is stored in 4 x 8 tiles (include/mrfa_b200.h "Map layouts") and the lookup walks tiles with
+    16-byte loads.  Every driving level, both output layouts, windows hanging over every border, against the oracle lookup
+    evaluated on the very bf16 maps the kernel read (un-tiled by CorrPyramid.dense)."""
+    m = mb()
+    torch.manual_seed(h + w)
+    B = 2
+    q = torch.randn(B, C, h, w, device=DEV)
+    k = torch.randn(B, C, h, w, device=DEV)
+    pyr = m.CorrPyramid(q.contiguous(memory_format=torch.channels_last), k.contiguous(memory_format=torch.channels_last), C ** -0.5)
+    ref = m.CorrPyramid(q, k, C ** -0.5)                                    # NCHW pack path
+    assert pyr.layout == m._lib.MAP_TILED and ref.layout == m._lib.MAP_TILED
+    assert torch.equal(pyr.volume0[:, :h * w], ref.volume0[:, :h * w]) and torch.equal(pyr.volume1[:, :h * w], ref.volume1[:, :h * w])
+    for lvl in range(4):
+        kk = 2 ** lvl
+        hq, wq = h // kk, w // kk
+        coords = torch.rand(B, 2, hq, wq) * torch.tensor([w + 10.0, h + 10.0]).view(1, 2, 1, 1) - 5.0
+        coords[0, :, 0, 0] = torch.tensor([0.0, 0.0])
+        coords[0, :, 0, 1] = torch.tensor([w - 1.0, h - 1.0])
+        coords[1, :, 0, 0] = torch.tensor([-40.0, 3.5])                      # window entirely outside
+        coords[1, :, 0, 1] = torch.tensor([8.0, 4.0])                        # footprint aligned to a tile boundary
+        l0 = pyr.dense(lvl).cpu().numpy()
+        l1 = pyr.dense(lvl, 1).cpu().numpy()
+        exp = O.corr_lookup([l0, l1], coords.numpy())
+        close(pyr.block(lvl)(coords.to(DEV)), exp)
+        got_cl = pyr.block(lvl)(coords.to(DEV), True)
+        assert got_cl.is_contiguous(memory_format=torch.channels_last)
+        close(got_cl, exp)
+    # radius 1 and 2 share the tile walk (smaller footprints), radius 4 falls back to the per-element kernel
+    coords = torch.rand(B, 2, h, w) * torch.tensor([w + 6.0, h + 6.0]).view(1, 2, 1, 1) - 3.0
+    l0, l1 = pyr.dense(0).cpu().numpy(), pyr.dense(0, 1).cpu().numpy()
+    for r in (1, 2, 4):
+        close(pyr.block(0, radius=r)(coords.to(DEV)), O.corr_lookup([l0, l1], coords.numpy(), radius=r))
+
+
+def test_corr_lookup_backward_tiled_pyramid():
+    """Gradients through lookups on a tiled pyramid (w = 64): d/d(coords) and d/d(q_d, k_s) against fp64 autograd on the
+    dense reference formulation (einsum volume -> avg-pool pyramid -> bilinear windows)."""
+    m = mb()
+    torch.manual_seed(21)
+    B, C, h, w = 1, 64, 8, 64
+    q = torch.randn(B, C, h, w, dtype=torch.float64)
+    k = torch.randn(B, C, h, w, dtype=torch.float64)
+    coords = torch.rand(B, 2, h, w, dtype=torch.float64) * torch.tensor([w + 2.0, h + 2.0]).view(1, 2, 1, 1) - 1.0
+    go = torch.randn(B, 98, h, w, dtype=torch.float64)
+    q64, k64, x64 = q.clone().requires_grad_(), k.clone().requires_grad_(), coords.clone().requires_grad_()
+    vol = torch.einsum("bic,bjc->bij", q64.flatten(2).transpose(1, 2), k64.flatten(2).transpose(1, 2)) * C ** -0.5
+    TP.corr_lookup(vol.reshape(B * h * w, 1, h, w), x64).backward(go)
+    q32 = q.float().to(DEV).requires_grad_()
+    k32 = k.float().to(DEV).requires_grad_()
+    x32 = coords.float().to(DEV).requires_grad_()
+    pyr = m.CorrPyramid(q32, k32, C ** -0.5)
+    assert pyr.layout == m._lib.MAP_TILED
+    pyr.block(0)(x32).backward(go.float().to(DEV))
+    for name, g, r in (("q_d", q32.grad, q64.grad), ("k_s", k32.grad, k64.grad), ("coords", x32.grad, x64.grad)):
+        a, b = g.double().cpu().flatten(), r.flatten()
+        rel = float((a - b).norm() / b.norm())
+        assert rel < 3e-2, (name, rel)                                        # bf16 volume and bf16 gradient GEMM operands
 
 
 def test_corr_lookup_edge_cases():
@@ -330,6 +396,41 @@ def test_corr_lookup_backward():
     out.backward(go.float().to(DEV))
     close(c32.grad, c64.grad, 5e-5)
     close(x32.grad, x64.grad, 5e-4, 1e-4)
+
+
+def test_corr_lookup_batched_sampler_branch():
+    """h1 = w1 = 128 with batch 2: the reference switches to batch_bilinear_sampler (raft.py:39-40, util.py:40-51), one
+    sample per chunk.  The chunking is a memory workaround -- the kernel's single launch must give the same values."""
+    m = mb()
+    torch.manual_seed(12)
+    B, h1, H = 2, 128, 16
+    corr = torch.randn(B * h1 * h1, 1, H, H)
+    coords = torch.rand(B, 2, h1, h1) * (H + 4) - 2
+    ref = TP.corr_lookup(corr, coords)                  # takes the `B > 1 and h1 >= 128` branch
+    close(m.CorrBlock(corr.to(DEV))(coords.to(DEV)), ref)
+    # and the drop-in batch_bilinear_sampler itself with one sample per chunk (the dropped-remainder case is in the goldens)
+    img = torch.randn(B * 9, 1, H, H)
+    pts = torch.rand(B * 9, 7, 7, 2) * (H + 2) - 1
+    got = m.batch_bilinear_sampler(img.to(DEV), pts.to(DEV), "bilinear", False, 3, 3, 1)
+    ref = torch.cat([TP.bilinear_sampler(img[i * 9:(i + 1) * 9], pts[i * 9:(i + 1) * 9]) for i in range(B)], 0)
+    close(got, ref)
+
+
+def test_prior_to_flow_direct():
+    """raft.py:189-190: init_flow = (self.h - 1) * (deformation + 1) / 2 - coords_grid, with self.h used for BOTH axes
+    (checked on a non-square map), forward at 1e-5 and the backward factor (h - 1) / 2."""
+    m = mb()
+    torch.manual_seed(13)
+    for (B, h, w, hm1) in ((2, 64, 64, 63.0), (3, 6, 10, 5.0), (1, 128, 128, 127.0)):
+        d = (torch.rand(B, h, w, 2) * 2.4 - 1.2)
+        ref = hm1 * (d.permute(0, 3, 1, 2) + 1) / 2.0 - TP.coords_grid(B, h, w)
+        x = d.to(DEV).requires_grad_()
+        got = torch.ops.mrfa.prior_to_flow(x, hm1)
+        assert got.shape == (B, 2, h, w)
+        close(got, ref, 1e-5)
+        go = torch.randn(B, 2, h, w)
+        got.backward(go.to(DEV))
+        close(x.grad, go.permute(0, 2, 3, 1) * (hm1 / 2.0), 1e-6)
 
 
 # ------------------------------------------------------------------ prior dense motion
@@ -435,6 +536,43 @@ def test_feature_warp_channels_last(C, R):
     assert a.is_contiguous(memory_format=torch.channels_last)
     close(a, ref)
     close(b, F.grid_sample(feat, grid, align_corners=False))
+
+
+@pytest.mark.parametrize("C,R,B,flow_kind", [(64, 128, 7, "smooth"), (64, 128, 7, "wild"), (128, 64, 26, "smooth"),
+                                             (512, 32, 100, "smooth"), (12, 200, 3, "smooth"), (64, 192, 3, "edges")])
+def test_run_walk_warps(C, R, B, flow_kind):
+    """>= 100k output pixels: the NHWC warps switch to the run-walk kernels, which keep the right-hand taps of a pixel in
+    registers for its neighbour when the sample positions chain (smooth motion) and reload otherwise.  Smooth flows (chains
+    hold), per-pixel random flows (chains break everywhere), flows leaving the image, and a channel count that is not a
+    multiple of 8 (128-bit path) must all give the plain result to 1e-5 -- refined, coarse and cat-slice outputs."""
+    m = mb()
+    torch.manual_seed(C + R)
+    assert B * R * R >= 100000
+    feat = torch.randn(B, C, R, R)
+    if flow_kind == "smooth":
+        flow = F.interpolate(torch.randn(B, 2, R // 8, R // 8) * 3.0, size=(R, R), mode="bilinear", align_corners=True)
+        noise = 0.002
+    elif flow_kind == "edges":
+        flow = F.interpolate(torch.randn(B, 2, 4, 4) * 0.4 * R, size=(R, R), mode="bilinear", align_corners=True)   # leaves the image
+        noise = 0.3
+    else:
+        flow = torch.randn(B, 2, R, R) * 4.0
+        noise = 0.3
+    grid = TP.make_coordinate_grid((R, R))[None].repeat(B, 1, 1, 1) + \
+        F.interpolate(torch.randn(B, 2, 8, 8) * noise * 10, size=(R, R), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ident = TP.coords_grid(B, R, R)
+    ref_r = TP.bilinear_sampler(feat, (flow + ident).permute(0, 2, 3, 1))
+    ref_c = F.grid_sample(feat, grid, align_corners=False)
+    fcl = feat.to(DEV).contiguous(memory_format=torch.channels_last)
+    close(m.warp_by_flow(fcl, flow.to(DEV)), ref_r)
+    close(m.grid_sample(fcl, grid.to(DEV)), ref_c)
+    a, b = torch.ops.mrfa.dual_warp(fcl, flow.to(DEV), grid.to(DEV))
+    close(a, ref_r)
+    close(b, ref_c)
+    if C % 4 == 0:
+        a2, buf = torch.ops.mrfa.dual_warp_cat(fcl, flow.to(DEV), grid.to(DEV))
+        close(a2, ref_r)
+        close(buf[:, C:], ref_c)
 
 
 @pytest.mark.parametrize("mode", ["pixel", "acF"])

@@ -224,8 +224,84 @@ def test_custom_op_schemas_and_fake_impls():
     opcheck(torch.ops.mrfa.grid_sample.default, (feat.contiguous(memory_format=torch.channels_last), grid, 2, 0, True, 1), test_utils=tests)
     opcheck(torch.ops.mrfa.dual_warp.default, (feat, torch.randn(2, 2, 6, 7, device=DEV), torch.rand(2, 6, 7, 2, device=DEV)), test_utils=tests)
     corr = torch.randn(2 * 9, 1, 8, 8, device=DEV)
-    opcheck(torch.ops.mrfa.corr_lookup.default, (corr, torch.ops.mrfa.avg_pool2x2(corr), torch.rand(2, 2, 3, 3, device=DEV) * 8, 8, 8, 9, 0, 3, False), test_utils=tests)
+    opcheck(torch.ops.mrfa.corr_lookup.default, (corr, torch.ops.mrfa.avg_pool2x2(corr), torch.rand(2, 2, 3, 3, device=DEV) * 8, 8, 8, 9, 0, 3, 0, False), test_utils=tests)
     opcheck(torch.ops.mrfa.corr_pyramid.default, (torch.randn(1, 64, 16, 16, device=DEV), torch.randn(1, 64, 16, 16, device=DEV), 0.125), test_utils=tests)
     opcheck(torch.ops.mrfa.kp2gaussian.default, (torch.rand(2, 10, 2, device=DEV), None, 8, 8, 0.1), test_utils=tests)
     opcheck(torch.ops.mrfa.resize_bilinear.default, (feat, 12, 9, 1), test_utils=tests)
     opcheck(torch.ops.mrfa.channel_affine.default, (feat, torch.rand(8, device=DEV), None, None, 1), test_utils=tests)
+
+
+def test_bench_settings_full_size_vs_oracle():
+    """The numerics bench.py times are the numerics tested: TF32 convolutions allowed (PyTorch default), cuDNN autotuning on,
+    channels_last, every MRFA_* fast path at its default, batch 4 of full-width vox1 256x256 pairs -- against the CPU oracle at
+    the north_star tolerance for bf16/TF32 end-to-end frames (2e-2 relative)."""
+    import mrfa_b200
+    cfg = _cfg()
+    B = 4
+    src, drv = syn.frame_pairs(B, 256, seed=7)
+    kp_s, kp_d = syn.keypoints(B, 10, seed=7)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            o_dm = syn.fill_state_dict_(TP.DenseMotionOracle(**cfg["dense_motion"])).eval()
+            o_rf = syn.fill_state_dict_(TP.RaftFlowOracle(**cfg["raft_flow"])).eval()
+            dense = o_dm(src, kp_d, kp_s)
+            ref_out, ref_warp, ref_occ = o_rf(kp_s["kp"], kp_d["kp"], dense, img=o_dm.down(src), img_full=src)
+            dm = mrfa_b200.DenseMotionNetwork(**cfg["dense_motion"]).eval()
+            rf = mrfa_b200.RaftFlow(**cfg["raft_flow"]).eval()
+            dm.load_state_dict(o_dm.state_dict())
+            rf.load_state_dict(o_rf.state_dict())
+            dm, rf = dm.to(DEV).channels_last_(), rf.to(DEV).channels_last_()      # what bench.py does
+            c = lambda d: {k: v.to(DEV) for k, v in d.items()}
+            for _ in range(2):                                                      # second pass: autotuned algorithms, warm caches
+                got = dm(src.to(DEV), c(kp_d), c(kp_s))
+                out, warp_img, occ = rf(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), got, img=dm.down(src.to(DEV)), img_full=src.to(DEV))
+        for name, a, b in (("out", out, ref_out), ("warp_img", warp_img, ref_warp), ("occlusion", occ, ref_occ)):
+            a, b = a.double().cpu(), b.double()
+            rel_l2 = float((a - b).norm() / b.norm())
+            max_abs = float((a - b).abs().max())
+            print(f"bench settings (TF32, NHWC, B={B}) {name}: rel-L2 {rel_l2:.3e}, max|err| {max_abs:.3e}")
+            assert rel_l2 < 2e-2, (name, rel_l2)
+            assert max_abs < 2e-2 * (1.0 + float(b.abs().max())), (name, max_abs)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+
+
+def test_chain_512_vs_oracle():
+    """BASELINE.json configs[3]: 512x512 (h = w = 128, N = 16384), B = 2 so the oracle takes the reference's
+    batch_bilinear_sampler branch (raft.py:39-40: batch > 1 and h1 >= 128) at the three finest levels.  DenseMotionNetwork ->
+    RaftFlow on the GPU (bf16 pyramid 4x the 256x256 one, lookups at H = W = 128) vs the CPU oracle; the structure encoders and
+    the dense-motion hourglass are narrowed (the generator keeps its width: raft.py:105-113 hard-codes the pyramid channels)."""
+    import mrfa_b200
+    cfg = _cfg()
+    dmc = dict(cfg["dense_motion"], block_expansion=16, max_features=64, num_blocks=3)
+    rfc = _rf_cfg(512)
+    src, _ = syn.frame_pairs(2, 512, seed=9)
+    kp_s, kp_d = syn.keypoints(2, 10, seed=9)
+    with torch.no_grad():
+        o_dm = syn.fill_state_dict_(TP.DenseMotionOracle(**dmc)).eval()
+        o_rf = syn.fill_state_dict_(TP.RaftFlowOracle(**rfc)).eval()
+        dense = o_dm(src, kp_d, kp_s)
+        ref_out, ref_warp, ref_occ, trace = o_rf(kp_s["kp"], kp_d["kp"], dense, img=o_dm.down(src), img_full=src, return_trace=True)
+        dm = syn.fill_state_dict_(mrfa_b200.DenseMotionNetwork(**dmc)).to(DEV).eval()
+        rf = syn.fill_state_dict_(mrfa_b200.RaftFlow(**rfc)).to(DEV).eval()
+        c = lambda d: {k: v.to(DEV) for k, v in d.items()}
+        got = dm(src.to(DEV), c(kp_d), c(kp_s))
+        np.testing.assert_allclose(got["deformation"].cpu().numpy(), dense["deformation"].numpy(), atol=2e-4)
+        # the lookup at H = W = 128 in isolation: same fp32 coordinates as the oracle's basic-resolution iteration (i = 3)
+        q_d, k_s = rf.structure_features(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), dm.down(src.to(DEV)))
+        pyr = mrfa_b200.CorrPyramid(q_d, k_s, rf.scale)
+        coords = trace["flow3"] + TP.coords_grid(2, 128, 128)
+        lk = pyr.block(0)(coords.to(DEV))
+        _rel(lk, trace["corr3"], 2e-2)
+        out, warp_img, occ = rf(kp_s["kp"].to(DEV), kp_d["kp"].to(DEV), got, img=dm.down(src.to(DEV)), img_full=src.to(DEV))
+    for name, a, b in (("out", out, ref_out), ("warp_img", warp_img, ref_warp), ("occlusion", occ, ref_occ)):
+        a, b = a.double().cpu(), b.double()
+        rel_l2 = float((a - b).norm() / b.norm())
+        max_abs = float((a - b).abs().max())
+        print(f"512x512 chain {name}: rel-L2 {rel_l2:.3e}, max|err| {max_abs:.3e}")
+        assert rel_l2 < 2e-2, (name, rel_l2)
+        assert max_abs < 2e-2 * (1.0 + float(b.abs().max())), (name, max_abs)
