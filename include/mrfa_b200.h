@@ -184,6 +184,28 @@ int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op,
 int mrfa_corr_volume(const void* a_op, const void* b_op, void* volume0, void* volume1,
                      int B, int C, int h, int w, float scale, int num_sms, mrfa_stream_t stream);
 
+/* Backward of mrfa_corr_pack + mrfa_corr_volume (the two GEMMs autograd derives from the einsum at raft.py:185, plus the
+ * avg_pool2d backward of raft.py:20 and :219), for the training-step configuration.
+ *   g0 (B, rows_total, hw) / g1 (B, rows_total, hw/4): fp32 gradients w.r.t. volume0 / volume1 in their map layout
+ *   (what mrfa_corr_lookup_bwd scatter-adds).  With G = scale * (g0 + unpool(g1)/4):
+ *     mrfa_corr_bwd_pack    G  (B, rows_total, hw) bf16 and GT (B, hw, rows_pad) bf16 = G transposed, rows_pad =
+ *                           mrfa_corr_bwd_rows_pad(h, w) (pitch rounded up to 64; the pad columns are never read)
+ *     mrfa_transpose_bf16   out[b, c, r] = in[b, r, c], out row pitch `out_pitch` >= rows  (operand transposes)
+ *     mrfa_corr_bwd_gemm    D[b,m,n] = sum_k X[b,m,k] * Y[b,n,k]; X (B, M, ldx), Y (B, Nn, ldy) bf16 with K contiguous,
+ *                           D (B, M, Nn) fp32; tcgen05.mma kind::f16, TMA operands, TMEM accumulators.
+ *                           Nn % 64 == 0 and (Nn <= 256 or Nn % 256 == 0); ldx, ldy multiples of 8; X, Y 16-byte aligned.
+ *                           dA = gemm(G, Bm^T) (M = rows_total, K = hw), dB = gemm(GT, A^T) (M = hw, K = rows_total).
+ *     mrfa_corr_bwd_unpack  d_q[b,y,x,c] = dA[b, y*w+x, c] + sum_l dA[b, off_l + pooled(y,x), c] / 4^l ;
+ *                           d_k[b,y,x,c] = dB[b, map_offset(y,x), c]; both (B, h, w, C) fp32 (NHWC memory).       */
+int64_t mrfa_corr_bwd_rows_pad(int h, int w);
+int mrfa_corr_bwd_pack(const float* g0, const float* g1, void* G, void* GT, int B, int h, int w, float scale,
+                       mrfa_stream_t stream);
+int mrfa_transpose_bf16(const void* in, void* out, int B, int rows, int cols, int out_pitch, mrfa_stream_t stream);
+int mrfa_corr_bwd_gemm(const void* X, const void* Y, float* D, int B, int M, int Nn, int K, int64_t ldx, int64_t ldy,
+                       int num_sms, mrfa_stream_t stream);
+int mrfa_corr_bwd_unpack(const float* dA, const float* dB, float* d_q, float* d_k, int B, int C, int h, int w,
+                         mrfa_stream_t stream);
+
 /* Generic CorrBlock.__init__ level build for the drop-in API (raft.py:19-21):
  * out (P,1,H/2,W/2) = avg_pool2d(in (P,1,H,W), 2, 2), fp32.                                  */
 int mrfa_avg_pool2x2(const float* in, float* out, int64_t P, int H, int W, mrfa_stream_t stream);

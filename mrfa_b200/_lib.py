@@ -44,6 +44,11 @@ SIGNATURES = {
     "mrfa_corr_map_offset": (c_int64, [c_int] * 5),
     "mrfa_corr_pack": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_corr_volume": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "mrfa_corr_bwd_rows_pad": (c_int64, [c_int, c_int]),
+    "mrfa_corr_bwd_pack": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_void_p]),
+    "mrfa_transpose_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "mrfa_corr_bwd_gemm": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_int64, c_int64, c_int, c_void_p]),
+    "mrfa_corr_bwd_unpack": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "mrfa_avg_pool2x2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 4
                              + [c_int64, c_int64, c_int, c_int, c_int, c_void_p]),

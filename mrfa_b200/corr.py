@@ -32,35 +32,13 @@ class _CorrPyramidFn(torch.autograd.Function):
         # the volume gradients arrive through the holder (see _PyramidLookupFn), not through autograd
         q_d, k_s = ctx.saved_tensors
         holder = ctx.holder_box[0]
-        B, C, h, w = q_d.shape
-        N = h * w
         if holder is None:
             return torch.zeros_like(q_d), torch.zeros_like(k_s), None, None
-        # level-1 gradients: each pooled source cell feeds its 2x2 block with weight 1/4.  Both gradient buffers are in the
-        # map layout of the volume (tiled for w = 64 / 128), so the spread is a gather through a cached index
-        layout = ops.corr_map_layout(h, w)
-        perm0 = ops.corr_map_permutation(layout, 0, h, w, q_d.device)               # (y, x) -> stored position, level 0
-        perm1 = ops.corr_map_permutation(layout, 1, h // 2, w // 2, q_d.device)
-        yy, xx = torch.meshgrid(torch.arange(h, device=q_d.device), torch.arange(w, device=q_d.device), indexing="ij")
-        l1_of_l0 = torch.empty(N, dtype=torch.int64, device=q_d.device)
-        l1_of_l0[perm0] = perm1[((yy // 2) * (w // 2) + xx // 2).reshape(-1)]
-        g = holder.g0 + 0.25 * holder.g1.index_select(2, l1_of_l0)
-        a_op, b_op = ops.corr_pack_debug(q_d.detach(), k_s.detach())
-        gb = (g * ctx.scale).to(torch.bfloat16)
-        d_a = torch.bmm(gb, b_op).float()                          # (B, rows_total, C)
-        d_b = torch.bmm(gb.transpose(1, 2), a_op).float()          # (B, N, C), rows in stored (map layout) order
-        # driving operand rows: level 0 plus the average-pooled levels (pool backward = spread / k^2)
-        d_q = d_a[:, :N].transpose(1, 2).reshape(B, C, h, w)
-        off = N
-        for lvl in (1, 2, 3):
-            k = 1 << lvl
-            n_l = N >> (2 * lvl)
-            part = d_a[:, off:off + n_l].transpose(1, 2).reshape(B, C, h // k, w // k) / (k * k)
-            d_q = d_q + part.repeat_interleave(k, dim=2).repeat_interleave(k, dim=3)
-            off += n_l
-        d_k = d_b.index_select(1, perm0).transpose(1, 2).reshape(B, C, h, w)
+        # G = scale * (g0 + unpool(g1) / 4) -> dA = G Bm, dB = G^T A on tcgen05, then the avg-pool backward of the pooled
+        # driving rows and the un-permutation of the source rows (csrc/corr_bwd.cu)
+        d_q, d_k = torch.ops.mrfa.corr_pyramid_bwd(holder.g0, holder.g1, q_d.detach(), k_s.detach(), ctx.scale)
         ctx.holder_box[0] = None
-        return d_q.contiguous(), d_k.contiguous(), None, None
+        return d_q, d_k, None, None
 
 
 class _PyramidLookupFn(torch.autograd.Function):

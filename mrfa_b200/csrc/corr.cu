@@ -520,6 +520,52 @@ __device__ __forceinline__ void stage_supertile(uint32_t taddr, float scale, flo
   }
 }
 
+// Half a super-tile (64 accumulator columns = tiles (ty,0), (ty,1)) into ONE staging half-buffer: a 32 x 64 level-0 box
+// (SWIZZLE_128B) and a 32 x 16 level-1 box (32-byte rows, SWIZZLE_32B).  Two half-buffers per warp alternate, so the TMA
+// engine drains one while the warp fills the other (store mode 2).
+__device__ __forceinline__ void stage_half(uint32_t taddr, float scale, float scale4, uint32_t box, uint32_t boxl,
+                                           uint32_t row128, uint32_t row32, uint32_t sw128, uint32_t sw32) {
+  uint32_t v0[32], v1[32];
+  tmem_ld_32x32(taddr, v0);
+  tmem_ld_32x32(taddr + 32, v1);
+  tmem_ld_wait();
+  uint32_t p0[16], p1[16], pl[8];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    p0[j] = pack_bf16(__uint_as_float(v0[2 * j]) * scale, __uint_as_float(v0[2 * j + 1]) * scale);
+    p1[j] = pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
+  }
+  float a[8], b[8];
+#pragma unroll
+  for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+    for (int c2 = 0; c2 < 4; ++c2) {
+      const int i0 = r2 * 16 + 2 * c2, i1 = i0 + 8;
+      a[r2 * 4 + c2] = ((__uint_as_float(v0[i0]) + __uint_as_float(v0[i0 + 1])) +
+                        (__uint_as_float(v0[i1]) + __uint_as_float(v0[i1 + 1]))) * scale4;
+      b[r2 * 4 + c2] = ((__uint_as_float(v1[i0]) + __uint_as_float(v1[i0 + 1])) +
+                        (__uint_as_float(v1[i1]) + __uint_as_float(v1[i1 + 1]))) * scale4;
+    }
+#pragma unroll
+  for (int r2 = 0; r2 < 2; ++r2) {
+    pl[r2 * 4 + 0] = pack_bf16(a[r2 * 4 + 0], a[r2 * 4 + 1]);
+    pl[r2 * 4 + 1] = pack_bf16(a[r2 * 4 + 2], a[r2 * 4 + 3]);
+    pl[r2 * 4 + 2] = pack_bf16(b[r2 * 4 + 0], b[r2 * 4 + 1]);
+    pl[r2 * 4 + 3] = pack_bf16(b[r2 * 4 + 2], b[r2 * 4 + 3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    st_shared_v4(box + row128 + (((uint32_t)j) ^ sw128) * 16, p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+    st_shared_v4(box + row128 + (((uint32_t)(4 + j)) ^ sw128) * 16, p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+  }
+  // 32-byte rows: 16-byte chunk j lands at chunk (j ^ ((row >> 2) & 1))          [SWIZZLE_32B]
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    st_shared_v4(boxl + row32 + (((uint32_t)j) ^ sw32) * 16, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+}
+
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <int kW, int kBlockN_, int kMTiles> struct Gemm2Cfg {
   static_assert(kW == 64 || kW == 128, "TMA-store epilogue is specialised for w = 64 / 128 (tiled map layout)");
   static_assert(kBlockN_ % 128 == 0 && kBlockN_ <= 256, "a tile holds whole 16 x 8-pixel super-tiles");
@@ -535,7 +581,8 @@ template <int kW, int kBlockN_, int kMTiles> struct Gemm2Cfg {
 struct Gemm2Params {
   int B, kblocks, m_blocks, n_tiles, n_split, b_stages;
   float scale;
-  int store_mode;            // 0 = TMA bulk tensor stores, 1 = coalesced LSU stores from the staged boxes
+  int store_mode;            // 0 = TMA bulk tensor stores from one staging buffer per warp, 1 = coalesced LSU stores from the
+                             // staged boxes, 2 (default) = TMA stores from two alternating half-buffers per warp
   int N;                     // hw
   int64_t rows_total;
   __nv_bfloat16 *vol0, *vol1;
@@ -547,7 +594,7 @@ template <int kW, int kBlockN_, int kMTiles, int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1,
-                       const Gemm2Params prm) {
+                       const __grid_constant__ CUtensorMap map_v1h, const Gemm2Params prm) {
   using Cfg = Gemm2Cfg<kW, kBlockN_, kMTiles>;
   constexpr int kBlockN = Cfg::kBlockN;
   extern __shared__ uint8_t smem_raw[];
@@ -578,6 +625,7 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v1h) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 8; ++i) {
@@ -682,7 +730,7 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t box0 = st_base, box1 = st_base + 4096, boxl = st_base + 8192;
     const uint32_t row128 = (uint32_t)lane * 128, row64 = (uint32_t)lane * 64;
     const uint32_t sw128 = (uint32_t)(lane & 7), sw64 = (uint32_t)((lane >> 1) & 3);
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, hcount = 0;
     for (int64_t u = cid; u < units; u += ncl) {
       const int split = (int)(u % prm.n_split);
       const int m_blk = (int)((u / prm.n_split) % prm.m_blocks) * kCluster + (int)crank;
@@ -698,10 +746,33 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           const int row0 = m_blk * Cfg::kUnitRows + half * kBlockM + ew * 32;
 #pragma unroll 1
           for (int gs = 0; gs < Cfg::kSuper; ++gs) {
+            if (prm.store_mode == 2) {
+              // ---- (c) two half-buffers per warp: fill one while the TMA engine drains the other ----
+#pragma unroll 1
+              for (int sub = 0; sub < 2; ++sub, ++hcount) {
+                const uint32_t hb = st_base + (hcount & 1u) * (kStageWarpBytes / 2);
+                if (lane == 0) tma_store_wait_read1();           // the group that last used this half-buffer has been read
+                __syncwarp();
+                stage_half(taddr + gs * 128 + sub * 64, scale, scale4, hb, hb + 4096, row128, (uint32_t)lane * 32, sw128,
+                           (uint32_t)((lane >> 2) & 1));
+                if (half == kMTiles - 1 && gs == Cfg::kSuper - 1 && sub == 1) {
+                  tcgen05_fence_before();                        // every TMEM read of this accumulator stage is done
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&t_empty[acc]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  const uint8_t* hp = smem_st + (size_t)ew * kStageWarpBytes + (size_t)(hcount & 1u) * (kStageWarpBytes / 2);
+                  tma_store_3d(&map_v0, hp, nt * kBlockN + gs * 128 + sub * 64, row0, b);
+                  tma_store_3d(&map_v1h, hp + 4096, nt * (kBlockN / 4) + gs * 32 + sub * 16, row0, b);
+                  tma_store_commit();
+                }
+              }
+              continue;
+            }
             // the staging boxes are free once the previous bulk stores have read them
             if (prm.store_mode == 0 && lane == 0 && !(prm.debug & 4)) tma_store_wait_read();
-            __syncwarp();
-            if (!(prm.debug & 2)) stage_supertile(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
             if (half == kMTiles - 1 && gs == Cfg::kSuper - 1) {
               // every TMEM read of this accumulator stage is done: hand it back to the MMA warp
               tcgen05_fence_before();
@@ -1036,7 +1107,7 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
     const char* e = getenv("MRFA_CORR_DEBUG");
     prm.debug = e ? atoi(e) : 0;
     const char* m = getenv("MRFA_CORR_STORE");
-    prm.store_mode = m ? atoi(m) : 0;
+    prm.store_mode = m ? atoi(m) : 2;
   }
   prm.N = N;
   prm.rows_total = rows_total;
@@ -1051,6 +1122,9 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
   rc = make_bf16_map(&map_v0, v0, N, rows_total, B, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_bf16_map(&map_v1, v1, N / 4, rows_total, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  CUtensorMap map_v1h;
+  rc = make_bf16_map(&map_v1h, v1, N / 4, rows_total, B, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
 
   auto kern = corr_volume_tma_kernel<kW, kBlockN_, kMTiles, kCluster>;
@@ -1071,7 +1145,7 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_v0, map_v1, prm);
+  e = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_v0, map_v1, map_v1h, prm);
   return (int)e;
 }
 

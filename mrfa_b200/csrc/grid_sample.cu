@@ -375,13 +375,14 @@ __device__ __forceinline__ VecF<V> blendv(const VecF<V>& a, const VecF<V>& b, co
   return r;
 }
 
-// One pass of a warp over its 32 pixels: lane l holds the taps of pixel gp0 + l in `mine`; group `grp` (LPPE lanes) walks
-// pixels [grp * RUN, (grp + 1) * RUN) of the warp, channel chunk by channel chunk.
+// One pass of a warp over its `pw` consecutive pixels (pw a power of two, G <= pw <= 32): lane l holds the taps of pixel
+// gp0 + (l & (pw - 1)) in `mine`; group `grp` (LPPE lanes, G = 32 / LPPE groups) walks pixels [grp * run, (grp + 1) * run),
+// run = pw / G, channel chunk by channel chunk.  Fewer pixels per warp = more warps for the mid-sized levels.
 template <int V, int LPPE>
 __device__ __forceinline__ void run_walk(const TapsB& mine, const float* __restrict__ in, float* __restrict__ out,
-                                         int64_t gp0, int64_t total, int C, int64_t plane, int64_t ostride, int lane) {
-  constexpr int G = 32 / LPPE;            // lane groups per warp
-  constexpr int RUN = 32 / G;             // consecutive pixels per group
+                                         int64_t gp0, int64_t total, int C, int64_t plane, int64_t ostride, int lane, int pw) {
+  constexpr int G = 32 / LPPE;
+  const int run = pw / G;
   const int grp = lane / LPPE, cl = (lane % LPPE) * V;
   for (int c0 = 0; c0 < C; c0 += LPPE * V) {                     // warp-uniform trip count: the shuffles below need every lane
     const int c = c0 + cl;
@@ -389,9 +390,9 @@ __device__ __forceinline__ void run_walk(const TapsB& mine, const float* __restr
     VecF<V> pr_ne, pr_se;
     int po_ne = -1, po_se = -1, pn = -1;
 #pragma unroll 4
-    for (int i = 0; i < RUN; ++i) {
-      const TapsB t = shfl_taps(mine, grp * RUN + i);
-      const int64_t gp = gp0 + grp * RUN + i;
+    for (int i = 0; i < run; ++i) {
+      const TapsB t = shfl_taps(mine, grp * run + i);
+      const int64_t gp = gp0 + grp * run + i;
       if (gp >= total || !act) continue;
       const float* src = in + (int64_t)t.n_in * plane + c;
       const bool chain = (t.o_nw == po_ne) & (t.o_sw == po_se) & (t.n_in == pn);
@@ -408,15 +409,15 @@ __device__ __forceinline__ void run_walk(const TapsB& mine, const float* __restr
 template <int MODE, int PAD, bool ADD_ID, int V, int LPPE>
 __global__ void __launch_bounds__(kThreads)
 grid_sample_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
-                                float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div) {
+                                float* __restrict__ out, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div, int pw) {
   const int HoWo = Ho * Wo;
   const int lane = threadIdx.x % 32;
   const int64_t total = (int64_t)N * HoWo;
-  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 32;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * pw;
   if (gp0 >= total) return;
   TapsB mine;
   {
-    const int64_t gp = min(gp0 + lane, total - 1);
+    const int64_t gp = min(gp0 + (lane & (pw - 1)), total - 1);
     const int n = (int)(gp / HoWo);
     const int p = (int)(gp - (int64_t)n * HoWo);
     const int y = p / Wo, x = p - y * Wo;
@@ -424,20 +425,20 @@ grid_sample_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __res
     load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
     mine = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div, C);
   }
-  run_walk<V, LPPE>(mine, in, out, gp0, total, C, (int64_t)H * W * C, C, lane);
+  run_walk<V, LPPE>(mine, in, out, gp0, total, C, (int64_t)H * W * C, C, lane, pw);
 }
 
 template <int V, int LPPE>
 __global__ void __launch_bounds__(kThreads)
 dual_warp_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
                               float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W,
-                              int64_t cstride) {
+                              int64_t cstride, int pw) {
   const int HW = H * W;
   const int lane = threadIdx.x % 32;
   const int64_t total = (int64_t)N * HW;
-  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 32;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * pw;
   if (gp0 >= total) return;
-  const int64_t gp = min(gp0 + lane, total - 1);
+  const int64_t gp = min(gp0 + (lane & (pw - 1)), total - 1);
   const int n = (int)(gp / HW);
   const int p = (int)(gp - (int64_t)n * HW);
   const int64_t plane = (int64_t)HW * C;
@@ -446,12 +447,12 @@ dual_warp_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restr
     const float fx = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 0) * HW + p), (float)x);
     const float fy = __fadd_rn(__ldg(flow + ((int64_t)n * 2 + 1) * HW + p), (float)y);
     const TapsB m = to_tapsb(make_taps(to_pixel<MRFA_COORD_PIXEL>(fx, W), to_pixel<MRFA_COORD_PIXEL>(fy, H), H, W), n, C);
-    run_walk<V, LPPE>(m, in, out_r, gp0, total, C, plane, C, lane);
+    run_walk<V, LPPE>(m, in, out_r, gp0, total, C, plane, C, lane, pw);
   }
   {   // coarse warp: normalised prior grid, align_corners=False (raft.py:271); may land in a channel slice of a wider buffer
     const float2 pg = __ldg(reinterpret_cast<const float2*>(prior) + gp);
     const TapsB m = to_tapsb(make_taps(to_pixel<MRFA_COORD_NORM_ACF>(pg.x, W), to_pixel<MRFA_COORD_NORM_ACF>(pg.y, H), H, W), n, C);
-    run_walk<V, LPPE>(m, in, out_c, gp0, total, C, plane, cstride, lane);
+    run_walk<V, LPPE>(m, in, out_c, gp0, total, C, plane, cstride, lane, pw);
   }
 }
 
@@ -530,9 +531,10 @@ static inline int lanes_per_pixel_v(int C, int V) {
   while (l < 32 && l * 2 * V <= C) l *= 2;
   return l;
 }
-// MRFA_WARP_RUN=0 selects the plain (4 loads per pixel) kernels, MRFA_WARP_VEC=4 the 128-bit run-walk (A/B measurements only)
+// MRFA_WARP_RUN: 0 = plain (4 loads per pixel) kernels everywhere, 1 = run-walk for >= 100k output pixels, 2 (default) =
+// run-walk for every size; MRFA_WARP_VEC=4 forces the 128-bit run-walk (A/B measurements only)
 static int warp_run_mode() {
-  static const int v = []() { const char* e = getenv("MRFA_WARP_RUN"); return e ? atoi(e) : 1; }();
+  static const int v = []() { const char* e = getenv("MRFA_WARP_RUN"); return e ? atoi(e) : 2; }();
   return v;
 }
 static int warp_vec_pref() {
@@ -544,14 +546,28 @@ static inline int pick_vec(int C, const void* a, const void* b, const void* c, i
   return (warp_vec_pref() == 8 && C % 8 == 0 && ostride % 8 == 0 && al32) ? 8 : 4;
 }
 
+// pixels per warp: enough warps (>= ~16k) to fill 148 SMs a few times over at the mid-sized levels, never fewer pixels than
+// lane groups.  MRFA_WARP_PW overrides (A/B measurements only).
+static inline int pick_pw(int64_t pixels, int lanes_pp) {
+  static const int forced = []() { const char* e = getenv("MRFA_WARP_PW"); return e ? atoi(e) : 0; }();
+  int pw = 32;
+  while (pw > 1 && pixels / pw < 16384) pw >>= 1;
+  if (forced > 0) pw = forced;
+  const int G = 32 / lanes_pp;
+  if (pw < G) pw = G;
+  if (pw > 32) pw = 32;
+  return pw;
+}
+
 template <int MODE, int PAD, bool ADD_ID>
 static int launch_fwd_nhwc_run(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C,
                                int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
   const int64_t pixels = (int64_t)N * Ho * Wo;
-  dim3 g((unsigned)cdiv64(cdiv64(pixels, 32), kThreads / 32));
   const int V = pick_vec(C, in, out, out, C);
+  const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V));
+  dim3 g((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
 #define MRFA_GSR_CASE(VV, L)                                                                                          \
-  case L: grid_sample_fwd_nhwc_run_kernel<MODE, PAD, ADD_ID, VV, L><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div); break;
+  case L: grid_sample_fwd_nhwc_run_kernel<MODE, PAD, ADD_ID, VV, L><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, pw); break;
   if (V == 8) {
     switch (lanes_per_pixel_v(C, 8)) { MRFA_GSR_CASE(8, 1) MRFA_GSR_CASE(8, 2) MRFA_GSR_CASE(8, 4) MRFA_GSR_CASE(8, 8) MRFA_GSR_CASE(8, 16) MRFA_GSR_CASE(8, 32) }
   } else {
@@ -566,7 +582,8 @@ static int launch_fwd_nhwc_lpp(const float* in, const float* grid, mrfa_grid_str
                                int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
   const int64_t pixels = (int64_t)N * Ho * Wo;
   const bool small = pixels < kSmallPixels;
-  if (!small && warp_run_mode()) return launch_fwd_nhwc_run<MODE, PAD, ADD_ID>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
+  if (warp_run_mode() && (!small || warp_run_mode() == 2))
+    return launch_fwd_nhwc_run<MODE, PAD, ADD_ID>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
   static const int unroll = []() { const char* e = getenv("MRFA_WARP_UNROLL"); return e ? atoi(e) : 2; }();
   dim3 g((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
 #define MRFA_GS_CASE(L)                                                                                            \
@@ -691,11 +708,12 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
     dim3 gn((unsigned)cdiv64(cdiv64(pixels, small ? 4 : 32), kThreads / 32));
     cudaStream_t st = as_stream(stream);
     const int64_t cs = coarse_pixel_stride > 0 ? coarse_pixel_stride : C;
-    if (!small && warp_run_mode()) {
-      dim3 gr((unsigned)cdiv64(cdiv64(pixels, 32), kThreads / 32));
+    if (warp_run_mode() && (!small || warp_run_mode() == 2)) {
       const int V = pick_vec(C, in, out_refined, out_coarse, cs);
+      const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V));
+      dim3 gr((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
 #define MRFA_DWR_CASE(VV, L)                                                                                         \
-  case L: dual_warp_fwd_nhwc_run_kernel<VV, L><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs); break;
+  case L: dual_warp_fwd_nhwc_run_kernel<VV, L><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs, pw); break;
       if (V == 8) {
         switch (lanes_per_pixel_v(C, 8)) { MRFA_DWR_CASE(8, 1) MRFA_DWR_CASE(8, 2) MRFA_DWR_CASE(8, 4) MRFA_DWR_CASE(8, 8) MRFA_DWR_CASE(8, 16) MRFA_DWR_CASE(8, 32) }
       } else {

@@ -50,7 +50,7 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   constexpr int n = 2 * R + 1, F = n + 1, FF = F * F;
   constexpr int kStride = 2 * FF + 1;                 // odd -> conflict-free lane-per-query reads
   __shared__ float foot[kQPB * kStride];
-  __shared__ float frac[kQPB][4];
+  __shared__ float frac[kQPB][2][2][n];               // per-tap fractional offsets [level][axis][tap] (see lookup_geometry)
   __shared__ int org[kQPB][4];                        // footprint origin (x0, y0) per level
 
   const int b = blockIdx.y;
@@ -58,18 +58,23 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int H1 = H / 2, W1 = W / 2;
 
-  // ---- phase 0: lane = query.  The IEEE coordinate round trip is evaluated once per query
-  //      (not once per lane of the gathering warp) and parked in shared memory. ----
-  if (warp == 0) {
-    const int q = q0 + lane;
-    if (q < Q) {
-      const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
-      const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
+  // ---- phase 0: one thread per (query, level, axis).  The reference adds the integer window offsets before the
+  //      coordinate round trip of util.bilinear_sampler (raft.py:31-37), so every tap gets its own fraction.
+  {
+    const int t = threadIdx.x;
+    const int qi = t >> 2, lvl = (t >> 1) & 1, axis = t & 1;
+    if (q0 + qi < Q) {
+      const float c = __ldg(coords + ((int64_t)b * 2 + axis) * Q + q0 + qi);
+      const int size = axis ? (lvl ? H1 : H) : (lvl ? W1 : W);
+      const float cs = __fdiv_rn(c, lvl ? 2.f : 1.f);
+      const float pc = to_pixel<MRFA_COORD_PIXEL>(cs, size);
+      const bool fin = fabsf(pc) < 1e8f;
+      const int base = fin ? (int)floorf(pc) - R : -(1 << 20);
+      org[qi][2 * lvl + axis] = base;
 #pragma unroll
-      for (int lvl = 0; lvl < 2; ++lvl) {
-        const QueryGeom g = query_geom(cx, cy, lvl, lvl ? H1 : H, lvl ? W1 : W, R);
-        frac[lane][2 * lvl] = g.fx; frac[lane][2 * lvl + 1] = g.fy;
-        org[lane][2 * lvl] = g.x0; org[lane][2 * lvl + 1] = g.y0;
+      for (int a = 0; a < n; ++a) {
+        const float pa = to_pixel<MRFA_COORD_PIXEL>(__fadd_rn(cs, (float)(a - R)), size);
+        frac[qi][lvl][axis][a] = fin ? pa - (float)(base + a) : 0.f;
       }
     }
   }
@@ -132,7 +137,7 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
       for (int k = lane; k < 2 * n * n; k += 32) {
         const int lvl = k / (n * n), kk = k - lvl * n * n;
         const int a = kk / n, bb = kk - a * n;
-        const float fx = frac[qi][2 * lvl], fy = frac[qi][2 * lvl + 1];
+        const float fx = frac[qi][lvl][0][a], fy = frac[qi][lvl][1][bb];
         const float* c = fq + lvl * FF + bb * F + a;
         float acc = c[0] * ((1.f - fx) * (1.f - fy));
         acc = fmaf(c[1], fx * (1.f - fy), acc);
@@ -150,11 +155,11 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
   float* dst = out + (int64_t)b * (2 * n * n) * Q + q;
 #pragma unroll
   for (int lvl = 0; lvl < 2; ++lvl) {
-    const float fx = frac[lane][2 * lvl], fy = frac[lane][2 * lvl + 1];
-    // same evaluation order as ATen: nw, ne, sw, se
-    const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
     for (int k = warp; k < n * n; k += kLookupThreads / 32) {
       const int a = k / n, bb = k - a * n;             // channel a*n+b: x offset a-r, y offset b-r
+      const float fx = frac[lane][lvl][0][a], fy = frac[lane][lvl][1][bb];
+      // same evaluation order as ATen: nw, ne, sw, se
+      const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
       const float* c = fq + lvl * FF + bb * F + a;
       float acc = c[0] * w_nw;
       acc = fmaf(c[1], w_ne, acc);
@@ -168,126 +173,194 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
 
 // ---------------------------------------------------------------------------------------------
 // Tiled bf16 pyramid maps (the volume written by mrfa_corr_volume for w = 64 / 128), r <= 3.
-// One warp instruction fetches BOTH footprints of a query: lane = (level, footprint row, tile
-// column) loads one 16-byte tile row -- 8 rows x 2 tile columns x 2 levels = 32 lanes -- so a
-// query costs 4-6 64-byte granules per level instead of 8 scattered 16-byte row pieces, and
-// kGroupT queries per lane are in flight before the first shared-memory store.
-// Shared memory keeps the 8 x 16 bf16 patches; phase 2 evaluates from them (fp32 arithmetic).
+//
+// Persistent blocks walk groups of 32 consecutive queries of one sample, software-pipelined:
+//   geometry  one thread per (query, level, axis): the reference evaluates the coordinate round trip of
+//             util.bilinear_sampler for every window tap separately (raft.py:31-37 adds the integer offsets BEFORE the
+//             normalisation), so each tap a gets its own fractional offset frac_a = pixel(c / 2^lvl + a - r) - (x0 + a);
+//             x0 = floor(pixel(c / 2^lvl)) - r is the shared footprint origin.  Bit-for-bit the reference's sample
+//             positions, also for coordinates far from the origin where the rounding of c + a differs per tap;
+//   gather    one warp instruction fetches BOTH footprints of a query: lane = (level, footprint row, tile column) loads
+//             one 16-byte tile row, so a query costs 4-6 64-byte DRAM granules per level instead of 8 scattered row
+//             pieces; the loads of group g+1 are issued before group g is evaluated and stay in flight meanwhile;
+//   patch     the 8 x 8 footprint of each level is parked in shared memory as fp32, aligned to x0 (conflict-free reads);
+//   evaluate  lane = query, warp = (level, half of the window columns): separable bilinear weights, each row's
+//             horizontal interpolation shared by the two window rows that use it (2.3 shared loads per output);
+//   write     through a staging tile so both output layouts leave as full 128-byte lines (NHWC: the 32 queries of a
+//             group are one contiguous 12.5 KB run).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPatchWords = 2 * 8 * 16 / 2;          // two levels x 8 rows x 16 columns of bf16, in 32-bit words
-constexpr int kPatchStride = kPatchWords + 1;        // odd -> lane-per-query reads spread over the banks
+constexpr int kPatchStride = 2 * 64 + 1;             // two levels x 8 x 8 fp32, odd stride: lane-per-query reads hit 32 banks
+constexpr int kFracStride = 2 * 2 * 8 + 1;           // [level][axis][tap] fractions per query (padded)
+constexpr int kGroupT = 8;                           // queries per warp per group = loads in flight per lane
+constexpr int kTiledBlocksPerSM = 5;                 // resident persistent blocks per SM (38 KB of shared memory each)
 
-__device__ __forceinline__ float bf16_at(const uint32_t* patch, int e) {      // element e of a patch held as packed words
-  const uint32_t wv = patch[e >> 1];
-  return __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+template <int R>
+struct LookupSmem {
+  static constexpr int n = 2 * R + 1;
+  static constexpr int kOutStride = 2 * n * n + 1;
+  float patch[kQPB * kPatchStride];
+  float outs[kQPB * kOutStride];
+  float frac[2][kQPB * kFracStride];
+  int org[2][kQPB][4];                               // footprint origin (x0, y0) per level
+};
+
+template <int R>
+__device__ __forceinline__ void lookup_geometry(LookupSmem<R>& sm, int buf, const float* __restrict__ coords, int b, int q0,
+                                                int Q, int H, int W) {
+  constexpr int n = 2 * R + 1;
+  const int t = threadIdx.x;                         // 128 threads = 32 queries x 2 levels x 2 axes
+  const int qi = t >> 2, lvl = (t >> 1) & 1, axis = t & 1;
+  const int q = q0 + qi;
+  if (q >= Q) return;
+  const float c = __ldg(coords + ((int64_t)b * 2 + axis) * Q + q);
+  const int size = (axis ? H : W) >> lvl;
+  const float cs = __fdiv_rn(c, lvl ? 2.f : 1.f);
+  const float pc = to_pixel<MRFA_COORD_PIXEL>(cs, size);
+  const bool fin = fabsf(pc) < 1e8f;
+  const int base = fin ? (int)floorf(pc) - R : -(1 << 20);
+  sm.org[buf][qi][2 * lvl + axis] = base;
+  float* f = sm.frac[buf] + qi * kFracStride + (lvl * 2 + axis) * 8;
+#pragma unroll
+  for (int a = 0; a < n; ++a) {
+    const float pa = to_pixel<MRFA_COORD_PIXEL>(__fadd_rn(cs, (float)(a - R)), size);
+    f[a] = fin ? pa - (float)(base + a) : 0.f;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void lookup_issue_loads(const LookupSmem<R>& sm, int buf, uint4 (&v)[kGroupT],
+                                                   const __nv_bfloat16* __restrict__ level0,
+                                                   const __nv_bfloat16* __restrict__ level1, int b, int q0, int Q, int H,
+                                                   int W, int64_t map_batch_stride, int64_t row_offset) {
+  constexpr int F = 2 * R + 2;
+  constexpr int kWarps = kLookupThreads / 32;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
+  const int Hl = H >> lvl, Wl = W >> lvl;
+  const __nv_bfloat16* lbase = lvl ? level1 : level0;
+  const int64_t map_elems = (int64_t)Hl * Wl;
+#pragma unroll
+  for (int g = 0; g < kGroupT; ++g) {
+    const int qi = warp + g * kWarps;
+    const int x0 = sm.org[buf][qi][2 * lvl], y0 = sm.org[buf][qi][2 * lvl + 1];
+    const int y = y0 + r, tx = (x0 >> 3) + half;          // arithmetic shift: floor for negative origins
+    // the second tile column is only needed when the footprint crosses an 8-column boundary
+    const bool ok = (q0 + qi < Q) && r < F && y >= 0 && y < Hl && tx >= 0 && tx < (Wl >> 3) && (half == 0 || (x0 & 7) + F > 8);
+    v[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) {
+      const int64_t map = (int64_t)b * map_batch_stride + row_offset + q0 + qi;
+      v[g] = __ldg(reinterpret_cast<const uint4*>(lbase + map * map_elems + map_offset<true>(lvl, y, tx * 8, Wl)));
+    }
+  }
 }
 
 template <int R>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __nv_bfloat16* __restrict__ level1,
-                             const float* __restrict__ coords, float* __restrict__ out, int Q, int H, int W,
+                             const float* __restrict__ coords, float* __restrict__ out, int B, int Q, int H, int W,
                              int64_t map_batch_stride, int64_t row_offset, int out_channels_last) {
-  constexpr int n = 2 * R + 1, F = n + 1;
-  static_assert(F <= 8, "the footprint must fit the 8 x 16 patch");
-  __shared__ uint32_t patch[kQPB * kPatchStride];
-  __shared__ float frac[kQPB][4];
-  __shared__ int org[kQPB][4];
-
-  const int b = blockIdx.y;
-  const int q0 = blockIdx.x * kQPB;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int H1 = H / 2, W1 = W / 2;
-
-  if (warp == 0) {                                    // phase 0: lane = query, IEEE coordinate round trip once per query
-    const int q = q0 + lane;
-    if (q < Q) {
-      const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * Q + q);
-      const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * Q + q);
-#pragma unroll
-      for (int lvl = 0; lvl < 2; ++lvl) {
-        const QueryGeom g = query_geom(cx, cy, lvl, lvl ? H1 : H, lvl ? W1 : W, R);
-        frac[lane][2 * lvl] = g.fx; frac[lane][2 * lvl + 1] = g.fy;
-        org[lane][2 * lvl] = g.x0; org[lane][2 * lvl + 1] = g.y0;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 1: lane = (level, row, tile column); kGroupT queries per round
+  constexpr int n = 2 * R + 1, F = n + 1, NN = n * n;
+  static_assert(F <= 8, "the footprint must fit the 8 x 8 patch");
   constexpr int kWarps = kLookupThreads / 32;
-  constexpr int kPerWarp = kQPB / kWarps;
-  constexpr int kGroupT = 8;
-  static_assert(kPerWarp % kGroupT == 0, "query grouping");
-  const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
-  const int Hl = lvl ? H1 : H, Wl = lvl ? W1 : W;
-  const __nv_bfloat16* lbase = lvl ? level1 : level0;
-  const int64_t map_elems = (int64_t)Hl * Wl;
-#pragma unroll 1
-  for (int g0 = 0; g0 < kPerWarp; g0 += kGroupT) {
-    uint4 v[kGroupT];
-#pragma unroll
-    for (int g = 0; g < kGroupT; ++g) {
-      const int qi = warp + (g0 + g) * kWarps;
-      const int x0 = org[qi][2 * lvl], y0 = org[qi][2 * lvl + 1];
-      const int y = y0 + r, tx = (x0 >> 3) + half;          // arithmetic shift: floor for negative origins
-      // the second tile column is only needed when the footprint crosses an 8-column boundary
-      const bool ok = (q0 + qi < Q) && r < F && y >= 0 && y < Hl && tx >= 0 && tx < (Wl >> 3) &&
-                      (half == 0 || (x0 & 7) + F > 8);
-      v[g] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) {
-        const int64_t map = (int64_t)b * map_batch_stride + row_offset + q0 + qi;
-        v[g] = __ldg(reinterpret_cast<const uint4*>(lbase + map * map_elems + map_offset<true>(lvl, y, tx * 8, Wl)));
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < kGroupT; ++g) {
-      const int qi = warp + (g0 + g) * kWarps;
-      uint32_t* d = patch + qi * kPatchStride + lane * 4;    // word (lvl*64 + r*8 + half*4) == lane*4
-      d[0] = v[g].x; d[1] = v[g].y; d[2] = v[g].z; d[3] = v[g].w;
-    }
-  }
-  __syncthreads();
+  constexpr int kOutStride = LookupSmem<R>::kOutStride;
+  static_assert(kQPB == kWarps * kGroupT, "one gather round per group");
+  __shared__ LookupSmem<R> sm;
 
-  if (out_channels_last) {
-    // ---- phase 2 (NHWC output): warp per query, lanes along the 2*(2r+1)^2 contiguous channels
-    for (int qi = warp; qi < kQPB; qi += kWarps) {
-      const int q = q0 + qi;
-      if (q >= Q) break;
-      const uint32_t* pq = patch + qi * kPatchStride;
-      float* dst = out + ((int64_t)b * Q + q) * (2 * n * n);
-      for (int k = lane; k < 2 * n * n; k += 32) {
-        const int l = k / (n * n), kk = k - l * n * n;
-        const int a = kk / n, bb = kk - a * n;
-        const float fx = frac[qi][2 * l], fy = frac[qi][2 * l + 1];
-        const int e = l * 128 + bb * 16 + (org[qi][2 * l] & 7) + a;
-        float acc = bf16_at(pq, e) * ((1.f - fx) * (1.f - fy));
-        acc = fmaf(bf16_at(pq, e + 1), fx * (1.f - fy), acc);
-        acc = fmaf(bf16_at(pq, e + 16), (1.f - fx) * fy, acc);
-        acc = fmaf(bf16_at(pq, e + 17), fx * fy, acc);
-        dst[k] = acc;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int groups_per_b = (Q + kQPB - 1) / kQPB;
+  const int64_t total = (int64_t)B * groups_per_b;
+  int64_t grp = blockIdx.x;
+  if (grp >= total) return;
+
+  uint4 v[kGroupT];
+  int buf = 0;
+  {
+    const int b = (int)(grp / groups_per_b), q0 = (int)(grp - (int64_t)b * groups_per_b) * kQPB;
+    lookup_geometry<R>(sm, 0, coords, b, q0, Q, H, W);
+    __syncthreads();
+    lookup_issue_loads<R>(sm, 0, v, level0, level1, b, q0, Q, H, W, map_batch_stride, row_offset);
+  }
+  for (; grp < total; grp += gridDim.x, buf ^= 1) {
+    const int b = (int)(grp / groups_per_b), q0 = (int)(grp - (int64_t)b * groups_per_b) * kQPB;
+    // ---- park the gathered tile rows as fp32, shifted so that patch column 0 is the footprint origin x0
+    {
+      const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
+#pragma unroll
+      for (int g = 0; g < kGroupT; ++g) {
+        const int qi = warp + g * kWarps;
+        const int dx = sm.org[buf][qi][2 * lvl] & 7;
+        float* d = sm.patch + qi * kPatchStride + lvl * 64 + r * 8 + half * 8 - dx;
+        const uint32_t wv[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = half * 8 + i - dx;
+          if (col >= 0 && col < 8) d[i] = __uint_as_float((i & 1) ? (wv[i >> 1] & 0xFFFF0000u) : (wv[i >> 1] << 16));
+        }
       }
     }
-    return;
-  }
-  // ---- phase 2 (NCHW output): lane = query, warps stride over the channels
-  const int q = q0 + lane;
-  if (q >= Q) return;
-  const uint32_t* pq = patch + lane * kPatchStride;
-  float* dst = out + (int64_t)b * (2 * n * n) * Q + q;
-#pragma unroll
-  for (int l = 0; l < 2; ++l) {
-    const float fx = frac[lane][2 * l], fy = frac[lane][2 * l + 1];
-    const float w_nw = (1.f - fx) * (1.f - fy), w_ne = fx * (1.f - fy), w_sw = (1.f - fx) * fy, w_se = fx * fy;
-    const int e0 = l * 128 + (org[lane][2 * l] & 7);
-    for (int k = warp; k < n * n; k += kWarps) {
-      const int a = k / n, bb = k - a * n;
-      const int e = e0 + bb * 16 + a;
-      float acc = bf16_at(pq, e) * w_nw;
-      acc = fmaf(bf16_at(pq, e + 1), w_ne, acc);
-      acc = fmaf(bf16_at(pq, e + 16), w_sw, acc);
-      acc = fmaf(bf16_at(pq, e + 17), w_se, acc);
-      *(dst + (int64_t)(l * n * n + k) * Q) = acc;
+    // ---- geometry + loads of the next group: in flight while this group is evaluated and written
+    const int64_t nxt = grp + gridDim.x;
+    if (nxt < total) {
+      const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
+      lookup_geometry<R>(sm, buf ^ 1, coords, nb, nq0, Q, H, W);
     }
+    __syncthreads();                                  // patches of this group and geometry of the next are visible
+    if (nxt < total) {
+      const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
+      lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, nb, nq0, Q, H, W, map_batch_stride, row_offset);
+    }
+    // ---- evaluate: lane = query, warp = (level, half of the window columns)
+    {
+      const int lvl = warp >> 1, ahalf = warp & 1;
+      const int a_begin = ahalf ? (n + 1) / 2 : 0, a_end = ahalf ? n : (n + 1) / 2;
+      const float* pq = sm.patch + lane * kPatchStride + lvl * 64;
+      const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 16;
+      float* oq = sm.outs + lane * kOutStride + lvl * NN;
+      float fy[n];
+#pragma unroll
+      for (int bb = 0; bb < n; ++bb) fy[bb] = fq[8 + bb];
+#pragma unroll 1
+      for (int a = a_begin; a < a_end; ++a) {
+        const float fx = fq[a];
+        const float wx0 = 1.f - fx;
+        float hprev = fmaf(pq[a + 1], fx, pq[a] * wx0);
+#pragma unroll
+        for (int bb = 0; bb < n; ++bb) {
+          const float hnext = fmaf(pq[(bb + 1) * 8 + a + 1], fx, pq[(bb + 1) * 8 + a] * wx0);
+          oq[a * n + bb] = fmaf(hnext, fy[bb], hprev * (1.f - fy[bb]));
+          hprev = hnext;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- write out
+    const int nq = min(kQPB, Q - q0);
+    if (out_channels_last) {
+      // the group's outputs are one contiguous run of nq * 2*n*n floats (16-byte aligned: q0 is a multiple of 32)
+      float* dst = out + ((int64_t)b * Q + q0) * (2 * NN);
+      // float4 stores when the run starts 16-byte aligned (always for even Q); the remainder / unaligned case is scalar
+      const int total4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? nq * (2 * NN) / 4 : 0;
+      for (int f4 = threadIdx.x; f4 < total4; f4 += kLookupThreads) {
+        float4 o;
+        float* op = &o.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = f4 * 4 + i;
+          const int qq = e / (2 * NN), k = e - qq * (2 * NN);
+          op[i] = sm.outs[qq * kOutStride + k];
+        }
+        *reinterpret_cast<float4*>(dst + (int64_t)f4 * 4) = o;
+      }
+      for (int e = total4 * 4 + threadIdx.x; e < nq * 2 * NN; e += kLookupThreads) {
+        const int qq = e / (2 * NN), k = e - qq * (2 * NN);
+        dst[e] = sm.outs[qq * kOutStride + k];
+      }
+    } else if (lane < nq) {
+      float* dst = out + (int64_t)b * (2 * NN) * Q + q0 + lane;
+      for (int k = warp; k < 2 * NN; k += kWarps) dst[(int64_t)k * Q] = sm.outs[lane * kOutStride + k];
+    }
+    // the next iteration's patch stores only touch sm.patch (last read before the barrier above); sm.outs is rewritten
+    // after the next barrier, by which time every thread has left this write phase
   }
 }
 
@@ -417,13 +490,16 @@ static int launch_lookup_fwd(const void* l0, const void* l1, const float* coords
 // bf16 tiled maps, radius <= 3: the vectorised tile walk
 static int launch_lookup_fwd_tiled(const void* l0, const void* l1, const float* coords, float* out, int B, int Q, int H,
                                    int W, int64_t mbs, int64_t ro, int radius, int ocl, cudaStream_t st) {
-  dim3 g((unsigned)cdiv64(Q, kQPB), (unsigned)B);
+  // persistent blocks: each walks groups of 32 queries with the next group's loads in flight
+  const int64_t groups = (int64_t)B * cdiv64(Q, kQPB);
+  const int64_t cap = (int64_t)148 * kTiledBlocksPerSM;
+  const unsigned g = (unsigned)(groups < cap ? groups : cap);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(l0);
   const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(l1);
   switch (radius) {
-    case 1: corr_lookup_fwd_tiled_kernel<1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
-    case 2: corr_lookup_fwd_tiled_kernel<2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
-    case 3: corr_lookup_fwd_tiled_kernel<3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, Q, H, W, mbs, ro, ocl); break;
+    case 1: corr_lookup_fwd_tiled_kernel<1><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, B, Q, H, W, mbs, ro, ocl); break;
+    case 2: corr_lookup_fwd_tiled_kernel<2><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, B, Q, H, W, mbs, ro, ocl); break;
+    case 3: corr_lookup_fwd_tiled_kernel<3><<<g, kLookupThreads, 0, st>>>(a, b, coords, out, B, Q, H, W, mbs, ro, ocl); break;
     default: return launch_lookup_fwd<__nv_bfloat16, true>(l0, l1, coords, out, B, Q, H, W, mbs, ro, radius, ocl, st);
   }
   return MRFA_LAUNCH_RESULT();

@@ -525,6 +525,53 @@ def corr_pack_debug(q_d: Tensor, k_s: Tensor) -> Tuple[Tensor, Tensor]:
     return a_op, b_op
 
 
+@torch.library.custom_op("mrfa::corr_pyramid_bwd", mutates_args=(), device_types="cuda")
+def corr_pyramid_bwd(g0: Tensor, g1: Tensor, q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
+    """Gradients of mrfa::corr_pyramid w.r.t. (q_d, k_s) from the fp32 volume gradients g0 (B, rows_total, hw) and
+    g1 (B, rows_total, hw/4): two tcgen05 GEMMs (dA = G Bm, dB = G^T A) plus pack / transpose / un-pool passes.
+    Returns channels_last (B,C,h,w) tensors."""
+    (q_d, cl), (k_s, cl2) = _req_image(q_d, "q_d"), _req_image(k_s, "k_s")
+    if cl != cl2:
+        k_s = _like_layout(k_s, cl)
+    g0, g1 = _req(g0, "g0"), _req(g1, "g1")
+    B, C, h, w = q_d.shape
+    N, rows = h * w, corr_rows_total(h, w)
+    rows_pad = int(lib.mrfa_corr_bwd_rows_pad(h, w))
+    if tuple(g0.shape) != (B, rows, N) or tuple(g1.shape) != (B, rows, N // 4):
+        raise RuntimeError("mrfa_b200: corr_pyramid_bwd gradient shapes do not match the pyramid of (q_d, k_s)")
+    dev = q_d.device
+    bf = dict(device=dev, dtype=torch.bfloat16)
+    a_op, b_op = torch.empty((B, rows, C), **bf), torch.empty((B, N, C), **bf)
+    G, GT = torch.empty((B, rows, N), **bf), torch.empty((B, N, rows_pad), **bf)
+    aT, bT = torch.empty((B, C, rows_pad), **bf), torch.empty((B, C, N), **bf)
+    dA = torch.empty((B, rows, C), device=dev, dtype=torch.float32)
+    dB = torch.empty((B, N, C), device=dev, dtype=torch.float32)
+    d_q, d_k = _empty_image((B, C, h, w), dev, True), _empty_image((B, C, h, w), dev, True)
+    with torch.cuda.device(dev):
+        st = _stream()
+        nsm = sm_count(dev)
+        with _timed("corr_pack", 8 * q_d.numel() + 2 * (a_op.numel() + b_op.numel())):
+            check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, int(cl), st), "mrfa_corr_pack")
+        with _timed("corr_bwd_pack", 4 * (g0.numel() + g1.numel()) + 2 * (G.numel() + B * N * rows)):
+            check(lib.mrfa_corr_bwd_pack(_p(g0), _p(g1), _p(G), _p(GT), B, h, w, scale, st), "mrfa_corr_bwd_pack")
+        with _timed("corr_bwd_transpose", 4 * (a_op.numel() + b_op.numel()), launches=2):
+            check(lib.mrfa_transpose_bf16(_p(a_op), _p(aT), B, rows, C, rows_pad, st), "mrfa_transpose_bf16")
+            check(lib.mrfa_transpose_bf16(_p(b_op), _p(bT), B, N, C, N, st), "mrfa_transpose_bf16")
+        with _timed("corr_bwd_gemm", 2 * (2 * G.numel() + a_op.numel() + b_op.numel()) + 4 * (dA.numel() + dB.numel()),
+                    2 * 2 * B * rows * N * C, launches=2):
+            check(lib.mrfa_corr_bwd_gemm(_p(G), _p(bT), _p(dA), B, rows, C, N, N, N, nsm, st), "mrfa_corr_bwd_gemm")
+            check(lib.mrfa_corr_bwd_gemm(_p(GT), _p(aT), _p(dB), B, N, C, rows, rows_pad, rows_pad, nsm, st), "mrfa_corr_bwd_gemm")
+        with _timed("corr_bwd_unpack", 4 * (dA.numel() + dB.numel() + 2 * d_q.numel())):
+            check(lib.mrfa_corr_bwd_unpack(_p(dA), _p(dB), _p(d_q), _p(d_k), B, C, h, w, st), "mrfa_corr_bwd_unpack")
+    return d_q, d_k
+
+
+@corr_pyramid_bwd.register_fake
+def _(g0, g1, q_d, k_s, scale):
+    f = lambda t: torch.empty_like(t).contiguous(memory_format=torch.channels_last)
+    return f(q_d), f(k_s)
+
+
 @torch.library.custom_op("mrfa::avg_pool2x2", mutates_args=(), device_types="cuda")
 def avg_pool2x2(x: Tensor) -> Tensor:
     x = _req(x, "x")

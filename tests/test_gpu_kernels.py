@@ -356,6 +356,44 @@ def test_corr_lookup_backward_tiled_pyramid():
         assert rel < 3e-2, (name, rel)                                        # bf16 volume and bf16 gradient GEMM operands
 
 
+@pytest.mark.parametrize("h,w,C,cl", [(16, 16, 64, False), (8, 64, 128, True), (16, 64, 256, False), (8, 16, 512, True)])
+def test_corr_pyramid_backward_gemms(h, w, C, cl):
+    """mrfa::corr_pyramid_bwd (tcgen05 GEMMs dA = G Bm, dB = G^T A + pack / transpose / un-pool kernels) against fp64 autograd
+    through the dense formulation the reference differentiates: einsum volume at every pooled driving level (raft.py:185,
+    :219), avg_pool2d level 1 (raft.py:20).  Row-major (w = 16) and tiled (w = 64) map layouts, NCHW and NHWC operands."""
+    m = mb()
+    torch.manual_seed(h * w + C)
+    B = 2
+    N, rows = h * w, m.ops.corr_rows_total(h, w)
+    scale = C ** -0.5
+    q = torch.randn(B, C, h, w, dtype=torch.float64)
+    k = torch.randn(B, C, h, w, dtype=torch.float64)
+    g0 = torch.randn(B, rows, N)                       # gradients in the STORED map layout
+    g1 = torch.randn(B, rows, N // 4)
+    layout = m.ops.corr_map_layout(h, w)
+    assert layout == (m._lib.MAP_TILED if w == 64 else m._lib.MAP_ROWMAJOR)
+    p0 = m.ops.corr_map_permutation(layout, 0, h, w, "cpu")
+    p1 = m.ops.corr_map_permutation(layout, 1, h // 2, w // 2, "cpu")
+    g0d, g1d = g0.index_select(2, p0).double(), g1.index_select(2, p1).double()      # row-major view of the same gradients
+    q64, k64 = q.clone().requires_grad_(), k.clone().requires_grad_()
+    kd = k64.flatten(2).transpose(1, 2)
+    levels = [q64] + [F.avg_pool2d(q64, 2 ** l) for l in (1, 2, 3)]
+    a_full = torch.cat([t.flatten(2).transpose(1, 2) for t in levels], dim=1)          # (B, rows_total, C)
+    vol0 = torch.einsum("bic,bjc->bij", a_full, kd) * scale
+    vol1 = F.avg_pool2d(vol0.view(B, rows, h, w), 2).flatten(2)
+    ((vol0 * g0d).sum() + (vol1 * g1d).sum()).backward()
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    dq, dk = torch.ops.mrfa.corr_pyramid_bwd(g0.to(DEV), g1.to(DEV), q.float().to(DEV).contiguous(memory_format=fmt),
+                                             k.float().to(DEV).contiguous(memory_format=fmt), scale)
+    assert dq.shape == q.shape and dk.shape == k.shape
+    for name, got, ref in (("d_q", dq, q64.grad), ("d_k", dk, k64.grad)):
+        a, b = got.double().cpu().flatten(), ref.flatten()
+        rel = float((a - b).norm() / b.norm())
+        # bf16 G and bf16 operands, fp32 accumulation over K = hw / rows_total
+        assert rel < 1e-2, (name, rel)
+        rel_close(got, ref, 5e-2)
+
+
 def test_corr_lookup_edge_cases():
     m = mb()
     torch.manual_seed(5)
