@@ -517,6 +517,144 @@ grid_sample_bwd_nhwc_kernel(const float* __restrict__ grad_out, const float* __r
   if (live && j == 0) reinterpret_cast<float2*>(grad_grid)[gp] = make_float2(gix * mx, giy * my);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Run-walk backward (NHWC): the scatter-add pre-reduction.  ATen issues one atomic per tap (4 per output pixel and
+// channel); along a row of a smooth motion field the right-hand cells (ne, se) of pixel x are the left-hand cells (nw, sw)
+// of pixel x + 1, so a lane group that walks a run of consecutive pixels carries the right column's contributions in
+// registers and merges them with the next pixel's left column before issuing ONE red.global.add.v4.f32 per cell:
+// 2 vector atomics per pixel and channel quad instead of 4 when the cells chain (checked per pixel on the exact cell
+// addresses; anything else flushes and falls back to 4).  The input taps needed for the coordinate gradient chain the same
+// way (2 loads instead of 4); that gradient is reduced over the channel axis with warp shuffles and written once per pixel.
+// ---------------------------------------------------------------------------------------------
+struct TapsG {              // TapsB + what the coordinate gradient needs
+  TapsB t;
+  float ax, ay, bx, by;     // distances to the west / north and east / south cell centres
+  int valid;                // bit 0 nw, 1 ne, 2 sw, 3 se: tap inside the image (zeros padding contributes nothing)
+};
+__device__ __forceinline__ TapsG shfl_tapsg(const TapsG& g, int src) {
+  TapsG r;
+  r.t = shfl_taps(g.t, src);
+  r.ax = __shfl_sync(0xffffffffu, g.ax, src); r.ay = __shfl_sync(0xffffffffu, g.ay, src);
+  r.bx = __shfl_sync(0xffffffffu, g.bx, src); r.by = __shfl_sync(0xffffffffu, g.by, src);
+  r.valid = __shfl_sync(0xffffffffu, g.valid, src);
+  return r;
+}
+__device__ __forceinline__ float4 scale4(float4 g, float w) { return make_float4(g.x * w, g.y * w, g.z * w, g.w * w); }
+__device__ __forceinline__ float4 fma4(float4 g, float w, float4 a) {
+  return make_float4(fmaf(g.x, w, a.x), fmaf(g.y, w, a.y), fmaf(g.z, w, a.z), fmaf(g.w, w, a.w));
+}
+__device__ __forceinline__ bool nonzero4(float4 a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f; }
+
+template <int MODE, int PAD, bool ADD_ID, int LPPE>
+__global__ void __launch_bounds__(kThreads)
+grid_sample_bwd_nhwc_run_kernel(const float* __restrict__ grad_out, const float* __restrict__ in,
+                                const float* __restrict__ grid, mrfa_grid_strides_t gs, float* __restrict__ grad_in,
+                                float* __restrict__ grad_grid, int N, int C, int H, int W, int Ho, int Wo, int in_batch_div,
+                                int pw) {
+  constexpr int G = 32 / LPPE;
+  const int HoWo = Ho * Wo;
+  const int lane = threadIdx.x % 32;
+  const int64_t total = (int64_t)N * HoWo;
+  const int64_t gp0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * pw;
+  if (gp0 >= total) return;
+  const int own = lane & (pw - 1);                       // the pixel of the warp this lane evaluated the geometry of
+  TapsG mine;
+  float mx, my;
+  {
+    const int64_t gp = min(gp0 + own, total - 1);
+    const int n = (int)(gp / HoWo);
+    const int p = (int)(gp - (int64_t)n * HoWo);
+    const int y = p / Wo, x = p - y * Wo;
+    float ix, iy;
+    load_sample_point<MODE, PAD, ADD_ID>(grid, gs, n, y, x, H, W, ix, iy, mx, my);
+    mine.t = to_tapsb(make_taps(ix, iy, H, W), n / in_batch_div, C);
+    const float fx = floorf(ix), fy = floorf(iy);
+    mine.ax = ix - fx; mine.ay = iy - fy; mine.bx = (fx + 1.f) - ix; mine.by = (fy + 1.f) - iy;
+    const bool fin = (fabsf(ix) < 1e9f) && (fabsf(iy) < 1e9f);
+    const int x0 = fin ? (int)fx : -2, y0 = fin ? (int)fy : -2;
+    const int vx0 = (x0 >= 0) & (x0 < W), vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+    const int vy0 = (y0 >= 0) & (y0 < H), vy1 = (y0 + 1 >= 0) & (y0 + 1 < H);
+    mine.valid = (vx0 & vy0) | ((vx1 & vy0) << 1) | ((vx0 & vy1) << 2) | ((vx1 & vy1) << 3);
+  }
+  const int run = pw / G;
+  const int grp = lane / LPPE, cl = (lane % LPPE) * 4;
+  const int64_t plane = (int64_t)H * W * C;
+  float gix_own = 0.f, giy_own = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 < C; c0 += LPPE * 4) {              // warp-uniform trip count (shuffles inside)
+    const int c = c0 + cl;
+    const bool act = c < C;
+    float4 cn = z4, cs = z4;                              // carried contributions to the cells (o_ne, o_se) of the previous pixel
+    int ko_n = -1, ko_s = -1, kn = -1;
+    float4 pv_ne = z4, pv_se = z4;                        // carried input taps (coordinate gradient)
+    int lo_n = -1, lo_s = -1, ln = -1;
+#pragma unroll 2
+    for (int i = 0; i < run; ++i) {
+      const TapsG tg = shfl_tapsg(mine, grp * run + i);
+      const TapsB& t = tg.t;
+      const int64_t gp = gp0 + grp * run + i;
+      const bool live = act && gp < total;
+      float gix = 0.f, giy = 0.f;
+      if (live) {
+        const float4 g = ldg4(grad_out + gp * C + c);
+        if (grad_in != nullptr) {
+          float* gi = grad_in + (int64_t)t.n_in * plane + c;
+          float4 an = scale4(g, t.w_nw), as = scale4(g, t.w_sw);
+          if ((t.o_nw == ko_n) & (t.o_sw == ko_s) & (t.n_in == kn)) {
+            an.x += cn.x; an.y += cn.y; an.z += cn.z; an.w += cn.w;
+            as.x += cs.x; as.y += cs.y; as.z += cs.z; as.w += cs.w;
+          } else if (kn >= 0) {                            // the chain broke: flush the carried column
+            float* gk = grad_in + (int64_t)kn * plane + c;
+            if (nonzero4(cn)) atomicAdd(reinterpret_cast<float4*>(gk + ko_n), cn);
+            if (nonzero4(cs)) atomicAdd(reinterpret_cast<float4*>(gk + ko_s), cs);
+          }
+          if (nonzero4(an)) atomicAdd(reinterpret_cast<float4*>(gi + t.o_nw), an);
+          if (nonzero4(as)) atomicAdd(reinterpret_cast<float4*>(gi + t.o_sw), as);
+          cn = scale4(g, t.w_ne); cs = scale4(g, t.w_se);
+          ko_n = t.o_ne; ko_s = t.o_se; kn = t.n_in;
+        }
+        if (grad_grid != nullptr) {
+          const float* s = in + (int64_t)t.n_in * plane + c;
+          float4 nw, sw;
+          if ((t.o_nw == lo_n) & (t.o_sw == lo_s) & (t.n_in == ln)) { nw = pv_ne; sw = pv_se; }
+          else { nw = ldg4(s + t.o_nw); sw = ldg4(s + t.o_sw); }
+          const float4 ne = ldg4(s + t.o_ne), se = ldg4(s + t.o_se);
+          pv_ne = ne; pv_se = se; lo_n = t.o_ne; lo_s = t.o_se; ln = t.n_in;
+          // a tap outside the image contributes 0 (its value is the zero padding, the clamped address holds something else)
+          const float m0 = (tg.valid & 1) ? 1.f : 0.f, m1 = (tg.valid & 2) ? 1.f : 0.f;
+          const float m2 = (tg.valid & 4) ? 1.f : 0.f, m3 = (tg.valid & 8) ? 1.f : 0.f;
+          const float* pnw = &nw.x; const float* pne = &ne.x; const float* psw = &sw.x; const float* pse = &se.x;
+          const float* pg = &g.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float vnw = pnw[e] * m0, vne = pne[e] * m1, vsw = psw[e] * m2, vse = pse[e] * m3;
+            gix += pg[e] * ((vne - vnw) * tg.by + (vse - vsw) * tg.ay);
+            giy += pg[e] * ((vsw - vnw) * tg.bx + (vse - vne) * tg.ax);
+          }
+        }
+      }
+      if (grad_grid != nullptr) {
+        // reduce over the channel lanes of the group, then hand the sums to the lane that owns this pixel's geometry
+#pragma unroll
+        for (int o = LPPE / 2; o > 0; o >>= 1) {
+          gix += __shfl_xor_sync(0xffffffffu, gix, o);
+          giy += __shfl_xor_sync(0xffffffffu, giy, o);
+        }
+        const int src = (own / run) * LPPE;                // leader lane of the group that walks this lane's pixel
+        const float rx = __shfl_sync(0xffffffffu, gix, src), ry = __shfl_sync(0xffffffffu, giy, src);
+        if (own % run == i) { gix_own += rx; giy_own += ry; }
+      }
+    }
+    if (grad_in != nullptr && kn >= 0) {                    // end of the run: flush the last right-hand column
+      float* gk = grad_in + (int64_t)kn * plane + c;
+      if (nonzero4(cn)) atomicAdd(reinterpret_cast<float4*>(gk + ko_n), cn);
+      if (nonzero4(cs)) atomicAdd(reinterpret_cast<float4*>(gk + ko_s), cs);
+    }
+  }
+  if (grad_grid != nullptr && lane < pw && gp0 + lane < total)
+    reinterpret_cast<float2*>(grad_grid)[gp0 + lane] = make_float2(gix_own * mx, giy_own * my);
+}
+
 static inline int lanes_per_pixel(int C) {
   int lpp = 1;
   while (lpp < 32 && lpp * 2 * 4 <= C) lpp *= 2;
@@ -548,12 +686,15 @@ static inline int pick_vec(int C, const void* a, const void* b, const void* c, i
 
 // pixels per warp: enough warps (>= ~16k) to fill 148 SMs a few times over at the mid-sized levels, never fewer pixels than
 // lane groups.  MRFA_WARP_PW overrides (A/B measurements only).
-static inline int pick_pw(int64_t pixels, int lanes_pp) {
+// `max_run`: cap on the pixels one lane group walks (0 = none).  The dual warp makes two passes over its pixels and wants the
+// input neighbourhood of pass 1 still in L1 for pass 2: measured best at runs of 8 (pw = 8 * G), the single warp at 32.
+static inline int pick_pw(int64_t pixels, int lanes_pp, int max_run) {
   static const int forced = []() { const char* e = getenv("MRFA_WARP_PW"); return e ? atoi(e) : 0; }();
+  const int G = 32 / lanes_pp;
   int pw = 32;
+  if (max_run > 0 && max_run * G < pw) pw = max_run * G;
   while (pw > 1 && pixels / pw < 16384) pw >>= 1;
   if (forced > 0) pw = forced;
-  const int G = 32 / lanes_pp;
   if (pw < G) pw = G;
   if (pw > 32) pw = 32;
   return pw;
@@ -564,7 +705,7 @@ static int launch_fwd_nhwc_run(const float* in, const float* grid, mrfa_grid_str
                                int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
   const int64_t pixels = (int64_t)N * Ho * Wo;
   const int V = pick_vec(C, in, out, out, C);
-  const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V));
+  const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V), 0);
   dim3 g((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
 #define MRFA_GSR_CASE(VV, L)                                                                                          \
   case L: grid_sample_fwd_nhwc_run_kernel<MODE, PAD, ADD_ID, VV, L><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, pw); break;
@@ -607,9 +748,33 @@ static int launch_fwd_nhwc(const float* in, const float* grid, mrfa_grid_strides
   return launch_fwd_nhwc_lpp<MODE, PAD, false>(in, grid, gs, out, N, C, H, W, Ho, Wo, div, st);
 }
 
+template <int MODE, int PAD, bool ADD_ID>
+static int launch_bwd_nhwc_run(const float* go, const float* in, const float* grid, mrfa_grid_strides_t gs, float* gi,
+                               float* gg, int N, int C, int H, int W, int Ho, int Wo, int div, cudaStream_t st) {
+  const int64_t pixels = (int64_t)N * Ho * Wo;
+  const int lpp = lanes_per_pixel_v(C, 4);
+  const int pw = pick_pw(pixels, lpp, 0);
+  dim3 g((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
+#define MRFA_GSB_CASE(L)                                                                                              \
+  case L: grid_sample_bwd_nhwc_run_kernel<MODE, PAD, ADD_ID, L><<<g, kThreads, 0, st>>>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div, pw); break;
+  switch (lpp) { MRFA_GSB_CASE(1) MRFA_GSB_CASE(2) MRFA_GSB_CASE(4) MRFA_GSB_CASE(8) MRFA_GSB_CASE(16) MRFA_GSB_CASE(32) }
+#undef MRFA_GSB_CASE
+  return MRFA_LAUNCH_RESULT();
+}
+
+// MRFA_BWD_RUN=0 selects the plain backward (4 atomics per pixel and channel quad; A/B measurements only)
+static int bwd_run_mode() {
+  static const int v = []() { const char* e = getenv("MRFA_BWD_RUN"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 template <int MODE, int PAD>
 static int launch_bwd_nhwc(const float* go, const float* in, const float* grid, mrfa_grid_strides_t gs, float* gi,
                            float* gg, int N, int C, int H, int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
+  if (bwd_run_mode()) {
+    if (add_id) return launch_bwd_nhwc_run<MODE, PAD, true>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div, st);
+    return launch_bwd_nhwc_run<MODE, PAD, false>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div, st);
+  }
   dim3 g((unsigned)cdiv64((int64_t)N * Ho * Wo * kNhwcGroup, kThreads));
   if (add_id)
     grid_sample_bwd_nhwc_kernel<MODE, PAD, true><<<g, kThreads, 0, st>>>(go, in, grid, gs, gi, gg, N, C, H, W, Ho, Wo, div);
@@ -710,7 +875,7 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
     const int64_t cs = coarse_pixel_stride > 0 ? coarse_pixel_stride : C;
     if (warp_run_mode() && (!small || warp_run_mode() == 2)) {
       const int V = pick_vec(C, in, out_refined, out_coarse, cs);
-      const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V));
+      const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V), 8);
       dim3 gr((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
 #define MRFA_DWR_CASE(VV, L)                                                                                         \
   case L: dual_warp_fwd_nhwc_run_kernel<VV, L><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs, pw); break;
