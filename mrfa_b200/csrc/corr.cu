@@ -469,6 +469,7 @@ constexpr uint32_t kStageWarpBytes = 4096 + 4096 + 2048;   // two 32x64 bf16 box
 // and (ty,1) -- 64 contiguous columns -- scales, packs to bf16 into the 64-column staging box `sub`, and 2x2-pools them
 // into rows 2*ty, 2*ty+1 of the level-1 tile (16 contiguous level-1 values); the pooled sum keeps the order of
 // F.avg_pool2d ((a + b) + (c + d), then * 1/4).
+template <bool HYBRID>
 __device__ __forceinline__ void stage_supertile(uint32_t taddr, float scale, float scale4, uint32_t box0, uint32_t box1,
                                                 uint32_t boxl, uint32_t row128, uint32_t row64, uint32_t sw128,
                                                 uint32_t sw64) {
@@ -482,7 +483,8 @@ __device__ __forceinline__ void stage_supertile(uint32_t taddr, float scale, flo
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       p0[j] = pack_bf16(__uint_as_float(v0[2 * j]) * scale, __uint_as_float(v0[2 * j + 1]) * scale);
-      p1[j] = pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
+      p1[j] = HYBRID ? pack_bf16_fma(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale)
+                     : pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
     }
     // tile element (row r, column c) = v[r * 8 + c]; pooled (r2, c2) = rows 2*r2, 2*r2+1 x columns 2*c2, 2*c2+1
     float a[8], b[8];
@@ -523,6 +525,7 @@ __device__ __forceinline__ void stage_supertile(uint32_t taddr, float scale, flo
 // Half a super-tile (64 accumulator columns = tiles (ty,0), (ty,1)) into ONE staging half-buffer: a 32 x 64 level-0 box
 // (SWIZZLE_128B) and a 32 x 16 level-1 box (32-byte rows, SWIZZLE_32B).  Two half-buffers per warp alternate, so the TMA
 // engine drains one while the warp fills the other (store mode 2).
+template <bool HYBRID>
 __device__ __forceinline__ void stage_half(uint32_t taddr, float scale, float scale4, uint32_t box, uint32_t boxl,
                                            uint32_t row128, uint32_t row32, uint32_t sw128, uint32_t sw32) {
   uint32_t v0[32], v1[32];
@@ -533,7 +536,8 @@ __device__ __forceinline__ void stage_half(uint32_t taddr, float scale, float sc
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     p0[j] = pack_bf16(__uint_as_float(v0[2 * j]) * scale, __uint_as_float(v0[2 * j + 1]) * scale);
-    p1[j] = pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
+    p1[j] = HYBRID ? pack_bf16_fma(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale)
+                   : pack_bf16(__uint_as_float(v1[2 * j]) * scale, __uint_as_float(v1[2 * j + 1]) * scale);
   }
   float a[8], b[8];
 #pragma unroll
@@ -586,6 +590,7 @@ struct Gemm2Params {
   int N;                     // hw
   int64_t rows_total;
   __nv_bfloat16 *vol0, *vol1;
+  int cvt_mode;              // 1 (default) = half of the bf16 conversions on the FMA / ALU pipes (pack_bf16_fma), 0 = all on XU
   int debug;   // MRFA_CORR_DEBUG bit mask (timing decomposition only; breaks results): 1 = no TMA stores,
                // 2 = epilogue skips TMEM loads / math / staging, 4 = no wait on staging reuse
 };
@@ -753,8 +758,8 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const uint32_t hb = st_base + (hcount & 1u) * (kStageWarpBytes / 2);
                 if (lane == 0) tma_store_wait_read1();           // the group that last used this half-buffer has been read
                 __syncwarp();
-                stage_half(taddr + gs * 128 + sub * 64, scale, scale4, hb, hb + 4096, row128, (uint32_t)lane * 32, sw128,
-                           (uint32_t)((lane >> 2) & 1));
+                if (prm.cvt_mode) stage_half<true>(taddr + gs * 128 + sub * 64, scale, scale4, hb, hb + 4096, row128, (uint32_t)lane * 32, sw128, (uint32_t)((lane >> 2) & 1));
+                else stage_half<false>(taddr + gs * 128 + sub * 64, scale, scale4, hb, hb + 4096, row128, (uint32_t)lane * 32, sw128, (uint32_t)((lane >> 2) & 1));
                 if (half == kMTiles - 1 && gs == Cfg::kSuper - 1 && sub == 1) {
                   tcgen05_fence_before();                        // every TMEM read of this accumulator stage is done
                   __syncwarp();
@@ -1026,7 +1031,7 @@ corr_volume_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int gs = 0; gs < Cfg::kSuper; ++gs) {
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
-          stage_supertile(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
+          stage_supertile<true>(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
           if (gs == Cfg::kSuper - 1) {
             tcgen05_fence_before();
             __syncwarp();
@@ -1106,6 +1111,8 @@ static int launch_corr_volume_tma(const void* a_op, const void* b_op, void* v0, 
   {
     const char* e = getenv("MRFA_CORR_DEBUG");
     prm.debug = e ? atoi(e) : 0;
+    const char* cv = getenv("MRFA_CORR_CVT");
+    prm.cvt_mode = cv ? atoi(cv) : 1;
     const char* m = getenv("MRFA_CORR_STORE");
     prm.store_mode = m ? atoi(m) : 2;
   }

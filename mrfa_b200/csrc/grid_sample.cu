@@ -428,8 +428,10 @@ grid_sample_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __res
   run_walk<V, LPPE>(mine, in, out, gp0, total, C, (int64_t)H * W * C, C, lane, pw);
 }
 
-template <int V, int LPPE>
-__global__ void __launch_bounds__(kThreads)
+// OCC4: cap the kernel at 64 registers (4 blocks = 32 resident warps per SM) -- ncu shows the walk is long-scoreboard bound
+// at 3 blocks, so more warps means more tap loads in flight; costs a 16-byte spill
+template <int V, int LPPE, bool OCC4>
+__global__ void __launch_bounds__(kThreads, OCC4 ? 4 : 1)
 dual_warp_fwd_nhwc_run_kernel(const float* __restrict__ in, const float* __restrict__ flow, const float* __restrict__ prior,
                               float* __restrict__ out_r, float* __restrict__ out_c, int N, int C, int H, int W,
                               int64_t cstride, int pw) {
@@ -877,8 +879,12 @@ extern "C" int mrfa_dual_warp_fwd(const float* in, const float* flow, const floa
       const int V = pick_vec(C, in, out_refined, out_coarse, cs);
       const int pw = pick_pw(pixels, lanes_per_pixel_v(C, V), 8);
       dim3 gr((unsigned)cdiv64(cdiv64(pixels, pw), kThreads / 32));
+      static const bool occ4 = []() { const char* e = getenv("MRFA_WARP_OCC4"); return e ? atoi(e) != 0 : true; }();
 #define MRFA_DWR_CASE(VV, L)                                                                                         \
-  case L: dual_warp_fwd_nhwc_run_kernel<VV, L><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs, pw); break;
+  case L:                                                                                                            \
+    if (occ4) dual_warp_fwd_nhwc_run_kernel<VV, L, true><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs, pw); \
+    else dual_warp_fwd_nhwc_run_kernel<VV, L, false><<<gr, kThreads, 0, st>>>(in, flow, prior_grid, out_refined, out_coarse, N, C, H, W, cs, pw);   \
+    break;
       if (V == 8) {
         switch (lanes_per_pixel_v(C, 8)) { MRFA_DWR_CASE(8, 1) MRFA_DWR_CASE(8, 2) MRFA_DWR_CASE(8, 4) MRFA_DWR_CASE(8, 8) MRFA_DWR_CASE(8, 16) MRFA_DWR_CASE(8, 32) }
       } else {

@@ -189,19 +189,19 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
 //   write     through a staging tile so both output layouts leave as full 128-byte lines (NHWC: the 32 queries of a
 //             group are one contiguous 12.5 KB run).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPatchStride = 2 * 64 + 1;             // two levels x 8 x 8 fp32, odd stride: lane-per-query reads hit 32 banks
-constexpr int kFracStride = 2 * 2 * 8 + 1;           // [level][axis][tap] fractions per query (padded)
+constexpr int kPatchStride = 2 * 8 * 8 + 1;          // two levels x 8 rows x 16 bf16 columns = 128 words; odd stride
+constexpr int kFracStride = 2 * 2 * 7 + 1;           // [level][axis][tap] fractions per query (odd stride)
 constexpr int kGroupT = 8;                           // queries per warp per group = loads in flight per lane
-constexpr int kTiledBlocksPerSM = 5;                 // resident persistent blocks per SM (38 KB of shared memory each)
+constexpr int kTiledBlocksPerSM = 5;                 // resident persistent blocks per SM (~37 KB of shared memory each)
 
 template <int R>
 struct LookupSmem {
   static constexpr int n = 2 * R + 1;
-  static constexpr int kOutStride = 2 * n * n + 1;
-  float patch[kQPB * kPatchStride];
-  float outs[kQPB * kOutStride];
+  static constexpr int kOut = 2 * n * n;               // outputs per query, stored back to back (float4 copy-out)
+  alignas(16) float outs[kQPB * kOut];
+  uint32_t patch[kQPB * kPatchStride];                 // per query: [level][row 0..7][8 words = tile columns tx, tx+1 as loaded]
   float frac[2][kQPB * kFracStride];
-  int org[2][kQPB][4];                               // footprint origin (x0, y0) per level
+  alignas(16) int org[2][kQPB][4];                     // footprint origin (x0, y0) per level
 };
 
 template <int R>
@@ -214,12 +214,12 @@ __device__ __forceinline__ void lookup_geometry(LookupSmem<R>& sm, int buf, cons
   if (q >= Q) return;
   const float c = __ldg(coords + ((int64_t)b * 2 + axis) * Q + q);
   const int size = (axis ? H : W) >> lvl;
-  const float cs = __fdiv_rn(c, lvl ? 2.f : 1.f);
+  const float cs = __fmul_rn(c, lvl ? 0.5f : 1.f);   // coords / 2**lvl (raft.py:34), exact
   const float pc = to_pixel<MRFA_COORD_PIXEL>(cs, size);
   const bool fin = fabsf(pc) < 1e8f;
   const int base = fin ? (int)floorf(pc) - R : -(1 << 20);
   sm.org[buf][qi][2 * lvl + axis] = base;
-  float* f = sm.frac[buf] + qi * kFracStride + (lvl * 2 + axis) * 8;
+  float* f = sm.frac[buf] + qi * kFracStride + (lvl * 2 + axis) * 7;
 #pragma unroll
   for (int a = 0; a < n; ++a) {
     const float pa = to_pixel<MRFA_COORD_PIXEL>(__fadd_rn(cs, (float)(a - R)), size);
@@ -236,21 +236,24 @@ __device__ __forceinline__ void lookup_issue_loads(const LookupSmem<R>& sm, int 
   constexpr int kWarps = kLookupThreads / 32;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
-  const int Hl = H >> lvl, Wl = W >> lvl;
-  const __nv_bfloat16* lbase = lvl ? level1 : level0;
-  const int64_t map_elems = (int64_t)Hl * Wl;
+  const int Hl = H >> lvl, tiles_w = (W >> lvl) >> 3;
+  const int map_elems = Hl * (W >> lvl);
+  // map of query (b, q0 + warp) on this lane's level; the other queries of the warp are 4 maps apart
+  const __nv_bfloat16* base = (lvl ? level1 : level0) + ((int64_t)b * map_batch_stride + row_offset + q0 + warp) * map_elems;
 #pragma unroll
   for (int g = 0; g < kGroupT; ++g) {
     const int qi = warp + g * kWarps;
-    const int x0 = sm.org[buf][qi][2 * lvl], y0 = sm.org[buf][qi][2 * lvl + 1];
-    const int y = y0 + r, tx = (x0 >> 3) + half;          // arithmetic shift: floor for negative origins
+    const int2 o = *reinterpret_cast<const int2*>(&sm.org[buf][qi][2 * lvl]);
+    const int y = o.y + r, tx = (o.x >> 3) + half;          // arithmetic shift: floor for negative origins
     // the second tile column is only needed when the footprint crosses an 8-column boundary
-    const bool ok = (q0 + qi < Q) && r < F && y >= 0 && y < Hl && tx >= 0 && tx < (Wl >> 3) && (half == 0 || (x0 & 7) + F > 8);
+    const bool ok = (q0 + qi < Q) & (r < F) & ((unsigned)y < (unsigned)Hl) & ((unsigned)tx < (unsigned)tiles_w) &
+                    ((half == 0) | ((o.x & 7) + F > 8));
+    // tile index inside the map (include/mrfa_b200.h "Map layouts"): level 0 in 2 x 2 super-tiles, level 1 plain
+    const int t0 = (((y >> 3) * (tiles_w >> 1) + (tx >> 1)) << 2) + (((y >> 2) & 1) << 1) + (tx & 1);
+    const int t1 = (y >> 2) * tiles_w + tx;
+    const int off = ((lvl ? t1 : t0) << 5) + ((y & 3) << 3) + g * (kWarps * map_elems);
     v[g] = make_uint4(0u, 0u, 0u, 0u);
-    if (ok) {
-      const int64_t map = (int64_t)b * map_batch_stride + row_offset + q0 + qi;
-      v[g] = __ldg(reinterpret_cast<const uint4*>(lbase + map * map_elems + map_offset<true>(lvl, y, tx * 8, Wl)));
-    }
+    if (ok) v[g] = __ldg(reinterpret_cast<const uint4*>(base + off));
   }
 }
 
@@ -260,9 +263,9 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
                              const float* __restrict__ coords, float* __restrict__ out, int B, int Q, int H, int W,
                              int64_t map_batch_stride, int64_t row_offset, int out_channels_last) {
   constexpr int n = 2 * R + 1, F = n + 1, NN = n * n;
-  static_assert(F <= 8, "the footprint must fit the 8 x 8 patch");
+  static_assert(F <= 8, "the footprint must fit 8 rows x 2 tile columns");
   constexpr int kWarps = kLookupThreads / 32;
-  constexpr int kOutStride = LookupSmem<R>::kOutStride;
+  constexpr int kOut = LookupSmem<R>::kOut;
   static_assert(kQPB == kWarps * kGroupT, "one gather round per group");
   __shared__ LookupSmem<R> sm;
 
@@ -282,51 +285,50 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
   }
   for (; grp < total; grp += gridDim.x, buf ^= 1) {
     const int b = (int)(grp / groups_per_b), q0 = (int)(grp - (int64_t)b * groups_per_b) * kQPB;
-    // ---- park the gathered tile rows as fp32, shifted so that patch column 0 is the footprint origin x0
-    {
-      const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
+    // ---- park the gathered tile rows as loaded (packed bf16): word (level*64 + row*8 + half*4 + i) == lane*4 + i
 #pragma unroll
-      for (int g = 0; g < kGroupT; ++g) {
-        const int qi = warp + g * kWarps;
-        const int dx = sm.org[buf][qi][2 * lvl] & 7;
-        float* d = sm.patch + qi * kPatchStride + lvl * 64 + r * 8 + half * 8 - dx;
-        const uint32_t wv[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int col = half * 8 + i - dx;
-          if (col >= 0 && col < 8) d[i] = __uint_as_float((i & 1) ? (wv[i >> 1] & 0xFFFF0000u) : (wv[i >> 1] << 16));
-        }
-      }
+    for (int g = 0; g < kGroupT; ++g) {
+      uint32_t* d = sm.patch + (warp + g * kWarps) * kPatchStride + lane * 4;
+      d[0] = v[g].x; d[1] = v[g].y; d[2] = v[g].z; d[3] = v[g].w;
     }
     // ---- geometry + loads of the next group: in flight while this group is evaluated and written
     const int64_t nxt = grp + gridDim.x;
-    if (nxt < total) {
-      const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
-      lookup_geometry<R>(sm, buf ^ 1, coords, nb, nq0, Q, H, W);
-    }
+    const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
+    if (nxt < total) lookup_geometry<R>(sm, buf ^ 1, coords, nb, nq0, Q, H, W);
     __syncthreads();                                  // patches of this group and geometry of the next are visible
-    if (nxt < total) {
-      const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
-      lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, nb, nq0, Q, H, W, map_batch_stride, row_offset);
-    }
-    // ---- evaluate: lane = query, warp = (level, half of the window columns)
+    if (nxt < total) lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, nb, nq0, Q, H, W, map_batch_stride, row_offset);
+    // ---- evaluate: lane = query, warp = (level, half of the window columns).  Window column a reads elements dx + a and
+    //      dx + a + 1 of every patch row (dx = x0 & 7: where the footprint starts inside the two loaded tile columns); each
+    //      bf16 is widened with one PRMT whose selector depends on the element's parity.
     {
       const int lvl = warp >> 1, ahalf = warp & 1;
       const int a_begin = ahalf ? (n + 1) / 2 : 0, a_end = ahalf ? n : (n + 1) / 2;
-      const float* pq = sm.patch + lane * kPatchStride + lvl * 64;
-      const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 16;
-      float* oq = sm.outs + lane * kOutStride + lvl * NN;
+      const uint32_t* pq = sm.patch + lane * kPatchStride + lvl * 64;
+      const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 14;
+      float* oq = sm.outs + lane * kOut + lvl * NN;
+      const int dx = sm.org[buf][lane][2 * lvl] & 7;
       float fy[n];
 #pragma unroll
-      for (int bb = 0; bb < n; ++bb) fy[bb] = fq[8 + bb];
+      for (int bb = 0; bb < n; ++bb) fy[bb] = fq[7 + bb];
 #pragma unroll 1
       for (int a = a_begin; a < a_end; ++a) {
+        const int e0 = dx + a;
+        const bool odd = e0 & 1;
+        const uint32_t* pw = pq + (e0 >> 1);
+        const uint32_t sel0 = odd ? 0x3244u : 0x1044u;     // element e0: high / low half of word A -> fp32
+        const uint32_t sel1 = odd ? 0x1044u : 0x3244u;     // element e0 + 1: low half of word B / high half of word A
         const float fx = fq[a];
         const float wx0 = 1.f - fx;
-        float hprev = fmaf(pq[a + 1], fx, pq[a] * wx0);
+        float hprev;
+        {
+          const uint32_t wa = pw[0], wb = pw[1];
+          hprev = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx, __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
+        }
 #pragma unroll
         for (int bb = 0; bb < n; ++bb) {
-          const float hnext = fmaf(pq[(bb + 1) * 8 + a + 1], fx, pq[(bb + 1) * 8 + a] * wx0);
+          const uint32_t wa = pw[(bb + 1) * 8], wb = pw[(bb + 1) * 8 + 1];
+          const float hnext = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx,
+                                   __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
           oq[a * n + bb] = fmaf(hnext, fy[bb], hprev * (1.f - fy[bb]));
           hprev = hnext;
         }
@@ -336,28 +338,16 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
     // ---- write out
     const int nq = min(kQPB, Q - q0);
     if (out_channels_last) {
-      // the group's outputs are one contiguous run of nq * 2*n*n floats (16-byte aligned: q0 is a multiple of 32)
-      float* dst = out + ((int64_t)b * Q + q0) * (2 * NN);
-      // float4 stores when the run starts 16-byte aligned (always for even Q); the remainder / unaligned case is scalar
-      const int total4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? nq * (2 * NN) / 4 : 0;
-      for (int f4 = threadIdx.x; f4 < total4; f4 += kLookupThreads) {
-        float4 o;
-        float* op = &o.x;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = f4 * 4 + i;
-          const int qq = e / (2 * NN), k = e - qq * (2 * NN);
-          op[i] = sm.outs[qq * kOutStride + k];
-        }
-        *reinterpret_cast<float4*>(dst + (int64_t)f4 * 4) = o;
-      }
-      for (int e = total4 * 4 + threadIdx.x; e < nq * 2 * NN; e += kLookupThreads) {
-        const int qq = e / (2 * NN), k = e - qq * (2 * NN);
-        dst[e] = sm.outs[qq * kOutStride + k];
-      }
+      // the group's outputs are one contiguous run of nq * 2*n*n floats, in shared memory as in global memory
+      float* dst = out + ((int64_t)b * Q + q0) * kOut;
+      // float4 copies when the run starts 16-byte aligned (always for even Q); the remainder / unaligned case is scalar
+      const int total4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? nq * kOut / 4 : 0;
+      for (int f4 = threadIdx.x; f4 < total4; f4 += kLookupThreads)
+        reinterpret_cast<float4*>(dst)[f4] = reinterpret_cast<const float4*>(sm.outs)[f4];
+      for (int e = total4 * 4 + threadIdx.x; e < nq * kOut; e += kLookupThreads) dst[e] = sm.outs[e];
     } else if (lane < nq) {
-      float* dst = out + (int64_t)b * (2 * NN) * Q + q0 + lane;
-      for (int k = warp; k < 2 * NN; k += kWarps) dst[(int64_t)k * Q] = sm.outs[lane * kOutStride + k];
+      float* dst = out + (int64_t)b * kOut * Q + q0 + lane;
+      for (int k = warp; k < kOut; k += kWarps) dst[(int64_t)k * Q] = sm.outs[lane * kOut + k];
     }
     // the next iteration's patch stores only touch sm.patch (last read before the barrier above); sm.outs is rewritten
     // after the next barrier, by which time every thread has left this write phase

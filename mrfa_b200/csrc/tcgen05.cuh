@@ -67,6 +67,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// The same round-to-nearest-even bf16 pack WITHOUT the XU pipe.  F2FP.BF16.F32.PACK_AB issues at a fraction of the FP32 rate
+// on sm_100 (ncu: the XU pipe was 63 % busy in the correlation epilogue, whose four warps each own one XU), so half of the
+// conversions go through the FMA / ALU pipes instead: adding m = sign(x) * 1.5 * 2^(e+16) (e = exponent of x) pushes x into
+// a binade whose ulp is the bf16 ulp of x, the hardware add rounds to nearest-even there, subtracting m back is exact.
+// Bit-identical to cvt.rn for normal finite values (|x| < 2^111); NaN / inf are not preserved (the volume is finite).
+__device__ __forceinline__ uint32_t pack_bf16_fma(float lo, float hi) {
+  const float ml = __fmul_rn(__uint_as_float((__float_as_uint(lo) & 0xFF800000u) | 0x00400000u), 65536.f);
+  const float mh = __fmul_rn(__uint_as_float((__float_as_uint(hi) & 0xFF800000u) | 0x00400000u), 65536.f);
+  const float rl = __fsub_rn(__fadd_rn(lo, ml), ml);
+  const float rh = __fsub_rn(__fadd_rn(hi, mh), mh);
+  return __byte_perm(__float_as_uint(rl), __float_as_uint(rh), 0x7632);
+}
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");

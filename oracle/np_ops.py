@@ -61,7 +61,10 @@ def _unnormalize(g: np.ndarray, size: int, align_corners: bool) -> np.ndarray:
     g = g.astype(F32)
     if align_corners:
         return ((g + F32(1)) / F32(2)) * F32(size - 1)
-    return ((g + F32(1)) * F32(size) - F32(1)) / F32(2)
+    # ATen rounds (g + 1) * size - 1 ONCE (an FMA in both its CUDA kernel and its vectorised CPU kernel, where it reads
+    # (g + 1) * (size / 2) - 0.5): the fp64 product of an fp32 number and an integer is exact, so one cast reproduces it
+    u = (g + F32(1)).astype(np.float64)
+    return ((u * size - 1.0).astype(F32)) / F32(2)
 
 
 def _reflect(x: np.ndarray, twice_low: int, twice_high: int) -> np.ndarray:

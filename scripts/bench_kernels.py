@@ -189,6 +189,50 @@ with torch.no_grad():
                 report(f"stock_grid_sample[C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R))
             del feat
 
+if want("bwd"):
+    # backward kernels of the training-step configuration (B = 16 per GPU)
+    Bt = min(B, 16)
+    qb = torch.randn(Bt, C, h, w, device=dev).contiguous(memory_format=torch.channels_last)
+    kb = torch.randn(Bt, C, h, w, device=dev).contiguous(memory_format=torch.channels_last)
+    rows = ops.corr_rows_total(h, w)
+    g0 = torch.randn(Bt, rows, N, device=dev)
+    g1 = torch.randn(Bt, rows, N // 4, device=dev)
+    with torch.no_grad(), ops.KernelTimer() as kt:
+        for _ in range(5):
+            torch.ops.mrfa.corr_pyramid_bwd(g0, g1, qb, kb, C ** -0.5)
+    for name, r in kt.summary().items():
+        ms = r["total_ms"] / r["calls"]
+        report(f"{name}[bwd, B={Bt}]", ms, r["bytes"] // r["calls"], r["flops"] // r["calls"], note="in sequence, no L2 flush")
+    a_op, b_op = ops.corr_pack_debug(qb, kb)
+    gb = (g0 * 0.0625).to(torch.bfloat16)
+    with torch.no_grad():
+        ms = timeit(lambda: (torch.bmm(gb, b_op), torch.bmm(gb.transpose(1, 2), a_op)))
+    report(f"cublas_bmm_bf16 x2 [dA, dB; B={Bt}] (round-1 path, GEMMs only)", ms, 0, 2 * 2 * Bt * rows * N * C)
+    del g0, g1, gb
+    for (Cc, R) in ((64, 256), (128, 128), (256, 64)):
+        feat = torch.randn(Bt, Cc, R, R, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+        lo = max(2, R // 8)
+        flow = F.interpolate(torch.randn(Bt, 2, lo, lo, device=dev) * 3.0, size=(R, R), mode="bilinear", align_corners=True).requires_grad_()
+        go = torch.randn(Bt, Cc, R, R, device=dev).contiguous(memory_format=torch.channels_last)
+        grid = flow.permute(0, 2, 3, 1)
+        fn = lambda: torch.ops.mrfa.grid_sample_bwd(go, feat.detach(), grid.detach(), _lib.COORD_PIXEL, _lib.PAD_ZEROS, True, 1, True, True)
+        ms = timeit(fn)
+        elems = Bt * Cc * R * R
+        report(f"grid_sample_bwd[nhwc C={Cc} R={R}]", ms, 4 * (4 * elems + 4 * Bt * R * R), run=os.environ.get("MRFA_BWD_RUN", "1"),
+               note="bytes: grad_out + input read, grad_input zero-fill + scatter")
+        if a.stock:
+            ident = mrfa_b200.coords_grid(Bt, R, R, dev)
+            gg = (flow.detach() + ident).permute(0, 2, 3, 1)
+            gn = torch.stack([2 * gg[..., 0] / (R - 1) - 1, 2 * gg[..., 1] / (R - 1) - 1], -1).requires_grad_()
+            f2 = feat.detach().contiguous().requires_grad_()
+
+            def stock():
+                o = F.grid_sample(f2, gn, align_corners=True)
+                torch.autograd.grad(o, (f2, gn), go.contiguous())
+            ms = timeit(stock)
+            report(f"stock_grid_sample fwd+bwd[C={Cc} R={R}]", ms, 0)
+
+with torch.no_grad():
     if want("prior"):
         src = torch.rand(B, 3, h, w, device=dev)
         kp_s = torch.rand(B, 10, 2, device=dev) * 1.6 - 0.8
