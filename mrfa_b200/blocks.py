@@ -47,6 +47,23 @@ class _Cache:
         return self.val
 
 
+def invalidate_caches(module: nn.Module) -> None:
+    """Drop every folded / merged / packed weight cached for the inference fast path under `module`.
+
+    The caches key on (data_ptr, _version) of their source tensors, which in-place writes through ``.data`` (EMA, weight
+    averaging) do not bump.  Called automatically after ``load_state_dict`` and on ``train()`` of the drop-in networks;
+    call it by hand after editing parameters through ``.data``."""
+    for m in module.modules():
+        for v in vars(m).values():
+            if isinstance(v, _Cache):
+                v.key, v.val = None, None
+
+
+def install_cache_hooks(module: nn.Module) -> None:
+    """load_state_dict post-hook + train() invalidation for a top-level drop-in network."""
+    module.register_load_state_dict_post_hook(lambda mod, _incompatible: invalidate_caches(mod))
+
+
 def _bn_affine(bn: nn.BatchNorm2d):
     """Eval-mode BatchNorm as y = x * scale + shift."""
     scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
@@ -72,7 +89,8 @@ SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for m
 def _small7_ok(conv: nn.Conv2d, x: torch.Tensor) -> bool:
     """7x7 / pad 3 / stride 1 with 2-3 input channels: served by the tcgen05 TF32 kernel instead of cuDNN's
     legacy indexed path (raft.py:56,63 convf1, generator.py:13 first)."""
-    return (SMALL_CONV and tuple(conv.kernel_size) == (7, 7) and tuple(conv.padding) == (3, 3)
+    # the kernel multiplies in TF32 (tcgen05 kind::tf32): only when the caller allows TF32 convolutions, like cuDNN
+    return (SMALL_CONV and torch.backends.cudnn.allow_tf32 and tuple(conv.kernel_size) == (7, 7) and tuple(conv.padding) == (3, 3)
             and tuple(conv.stride) == (1, 1) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
             and ops.conv7x7_small_ok(x, conv.in_channels, conv.out_channels))
 

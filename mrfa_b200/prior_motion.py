@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
-from .blocks import AntiAliasInterpolation2d, Hourglass
+from .blocks import AntiAliasInterpolation2d, Hourglass, install_cache_hooks, invalidate_caches
 
 
 def _dropout_softmax(X, P):
@@ -58,9 +58,14 @@ class DenseMotionNetwork(nn.Module):
         self.kp_variance = kp_variance
         if self.scale_factor != 1:
             self.down = AntiAliasInterpolation2d(num_channels, self.scale_factor)
+        install_cache_hooks(self)
 
     channels_last = False
     auto_channels_last = True
+
+    def train(self, mode: bool = True):
+        invalidate_caches(self)                   # folded inference weights are rebuilt from the live parameters
+        return super().train(mode)
 
     def channels_last_(self, enable: bool = True):
         """Run the hourglass convolutions in NHWC memory (see RaftFlow.channels_last_)."""

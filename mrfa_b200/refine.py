@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops, sampling
-from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_path
+from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_path, install_cache_hooks, invalidate_caches
 from .corr import CorrPyramid
 
 
@@ -108,7 +108,12 @@ class BasicMotionEncoder(nn.Module):
 
 
 class RefineFlow(nn.Module):
-    """raft.py:70-87: motion feature + warped-source context -> (d_flow(2) ++ d_occ(1))."""
+    """raft.py:70-87: motion feature + warped-source context -> (d_flow(2) ++ d_occ(1)).
+
+    Returns ``(out, inp)`` like the reference.  ``inp`` (the concatenated 256-channel input, which the reference returns
+    but never uses: raft.py:256 discards it) is ``None`` on the inference fast path with MRFA_SPLIT_K=1, where the two
+    halves feed two accumulating convolutions and the concatenation is never materialised; set MRFA_SPLIT_K=0 (or run
+    with grad enabled / in train mode) to get the tensor."""
 
     def __init__(self):
         super().__init__()
@@ -174,6 +179,7 @@ class RaftFlow(nn.Module):
         widths = (512, 512, 512, 256, 128, 64)             # raft.py:105-113, coarsest first
         self.total_iter = self.num_iter = int(math.log(2 ** 5, 2)) + 1
         self.basic_res_index = int(math.log(self.h // (size // 32), 2))
+        install_cache_hooks(self)
         if self.prior_only:
             return
         self.kp = Hourglass(**driving_encoder)
@@ -187,7 +193,12 @@ class RaftFlow(nn.Module):
         self.to_context = nn.ModuleList(nn.Conv2d(widths[i], 192, 1, padding=0) for i in range(self.num_iter))
 
     channels_last = False
-    auto_channels_last = True      # inference on CUDA switches to NHWC memory on first use (values unchanged)
+    auto_channels_last = True      # inference on CUDA switches to NHWC memory on first use (values unchanged; sticky: the
+                                   # module stays channels_last afterwards -- set False to keep the reference's NCHW memory)
+
+    def train(self, mode: bool = True):
+        invalidate_caches(self)                   # folded / merged inference weights are rebuilt from the live parameters
+        return super().train(mode)
 
     def channels_last_(self, enable: bool = True):
         """Run the decoder in NHWC memory (torch.channels_last): the layout the sm_100 tensor-core
