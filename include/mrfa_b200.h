@@ -272,6 +272,13 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
+/* torch.cat([F.interpolate(o, size=(Ho,Wo), mode='bilinear', align_corners=True) for o in maps], dim=3) one map at a
+ * time (raft.py:304-306, the occlusion strip returned next to the prediction): x (planes, H, W) planar -> columns
+ * [y_col_offset, y_col_offset + Wo) of y (planes, Ho, y_row_pitch).  Wo, y_row_pitch, y_col_offset multiples of 4,
+ * y 16-byte aligned.  act as above.                                                                                */
+int mrfa_resize_bilinear_strip(const float* x, float* y, int64_t planes, int H, int W, int Ho, int Wo,
+                               int64_t y_row_pitch, int64_t y_col_offset, int act, mrfa_stream_t stream);
+
 /* Backward of mrfa_avg_pool2x2_nhwc: grad_y (N,C,H/2,W/2) -> grad_x (N,C,H,W), both NHWC; H, W even, C % 4 == 0. */
 int mrfa_avg_pool2x2_nhwc_bwd(const float* grad_y, float* grad_x, int N, int C, int H, int W, mrfa_stream_t stream);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_antialias_down": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "mrfa_resize_bilinear_strip": (c_int, [c_void_p, c_void_p, c_int64] + [c_int] * 4 + [c_int64, c_int64, c_int, c_void_p]),
     "mrfa_random_warp_grid": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_conv7x7_small_kpad": (c_int, [c_int]),
     "mrfa_conv7x7_small": (c_int, [c_void_p, GridStrides] + [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),

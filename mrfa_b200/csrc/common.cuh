@@ -117,6 +117,53 @@ __host__ __device__ __forceinline__ int64_t map_offset(int lvl, int y, int x, in
   return (int64_t)((y >> 2) * (Wl >> 3) + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7);
 }
 
+// Division by a launch-time constant without the integer-division sequence (the streaming kernels decompose a flat
+// element index into (channel quad, x, y, sample) per element: with 64-bit `/` and `%` that was most of their issued
+// instructions).  q = umulhi(x, mul) >> shr is exact for x < 2^31 (ceil(2^(31+L) / d) with L = ceil(log2 d)).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;                                   // ceil(log2 d), 1..31 for the sizes that occur
+    const uint32_t p = 31 + l;
+    f.mul = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv& f) {
+  return f.d == 1 ? x : (__umulhi(x, f.mul) >> f.shr);
+}
+// i = ((n * h + y) * w + x) * c + ci  ->  (ci, x, y, n) and pix = i / c; 32-bit multiply-shift when i < 2^31
+struct IndexSplit {
+  FastDiv c, w, h;
+};
+__device__ __forceinline__ void split_index(int64_t i, const IndexSplit& s, int& ci, int& x, int& y, int64_t& n, int64_t& pix) {
+  if (i < ((int64_t)1 << 31)) {
+    const uint32_t u = (uint32_t)i;
+    const uint32_t p = fast_div(u, s.c);
+    const uint32_t r = fast_div(p, s.w);
+    const uint32_t nn = fast_div(r, s.h);
+    ci = (int)(u - p * s.c.d); x = (int)(p - r * s.w.d); y = (int)(r - nn * s.h.d);
+    n = nn; pix = p;
+  } else {
+    ci = (int)(i % s.c.d);
+    pix = i / s.c.d;
+    x = (int)(pix % s.w.d);
+    y = (int)((pix / s.w.d) % s.h.d);
+    n = pix / ((int64_t)s.w.d * s.h.d);
+  }
+}
+static inline IndexSplit make_index_split(int c, int w, int h) {
+  IndexSplit s;
+  s.c = make_fastdiv((uint32_t)c); s.w = make_fastdiv((uint32_t)w); s.h = make_fastdiv((uint32_t)h);
+  return s;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -778,6 +778,11 @@ corr_volume_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             }
             // the staging boxes are free once the previous bulk stores have read them
             if (prm.store_mode == 0 && lane == 0 && !(prm.debug & 4)) tma_store_wait_read();
+            __syncwarp();
+            if (!(prm.debug & 2)) {
+              if (prm.cvt_mode) stage_supertile<true>(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
+              else stage_supertile<false>(taddr + gs * 128, scale, scale4, box0, box1, boxl, row128, row64, sw128, sw64);
+            }
             if (half == kMTiles - 1 && gs == Cfg::kSuper - 1) {
               // every TMEM read of this accumulator stage is done: hand it back to the MMA warp
               tcgen05_fence_before();

@@ -102,18 +102,25 @@ __device__ __forceinline__ void resize_axis(int o, float scale, int in, int& i0,
 // a warp is one contiguous pixel.
 constexpr int kResizeRun = 8;
 
+// The two source rows are blended first (one fused multiply-add per component when a column enters the window), so an
+// output costs two operations per component instead of seven: hx * (hy v00 + ly v10) + lx * (hy v01 + ly v11) is the
+// same bilinear form as ATen's hy (hx v00 + lx v01) + ly (hx v10 + lx v11), rounded in a different order (~1e-7
+// relative; the kernel is issue-bound, not HBM-bound, with the ATen order).
+__device__ __forceinline__ float4 resize_vblend(const float* r0, const float* r1, float hy, float ly) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(r0)), b = __ldg(reinterpret_cast<const float4*>(r1));
+  return make_float4(fmaf(ly, b.x, hy * a.x), fmaf(ly, b.y, hy * a.y), fmaf(ly, b.z, hy * a.z), fmaf(ly, b.w, hy * a.w));
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(256)
 resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
-                            float sy, float sx, int64_t total_runs, int act) {
+                            float sy, float sx, int64_t total_runs, IndexSplit sp) {
   const int cq = C / 4;
-  const int runs_per_row = (Wo + kResizeRun - 1) / kResizeRun;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_runs; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cq) * 4;
-    int64_t rem = i / cq;
-    const int run = (int)(rem % runs_per_row);
-    rem /= runs_per_row;
-    const int oy = (int)(rem % Ho);
-    const int64_t n = rem / Ho;
+    int c4, run, oy;
+    int64_t n, unused;
+    split_index(i, sp, c4, run, oy, n, unused);        // (channel quad, run of the row, output row, sample)
+    const int c = c4 * 4;
     int y0, y1;
     float ly;
     resize_axis(oy, sy, H, y0, y1, ly);
@@ -122,7 +129,7 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
     const float* r1 = x + (n * H + y1) * (int64_t)W * C + c;
     float4* dst = reinterpret_cast<float4*>(y + ((n * Ho + oy) * (int64_t)Wo + run * kResizeRun) * C + c);
     int cx0 = -1, cx1 = -1;
-    float4 v00 = make_float4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
+    float4 vl = make_float4(0, 0, 0, 0), vr = vl;      // vertically blended left / right source columns
 #pragma unroll
     for (int j = 0; j < kResizeRun; ++j) {
       const int ox = run * kResizeRun + j;
@@ -131,27 +138,17 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
       float lx;
       resize_axis(ox, sx, W, x0, x1, lx);
       if (x0 != cx0) {
-        if (x0 == cx1) { v00 = v01; v10 = v11; }          // slide: the old right column becomes the left one
-        else {
-          v00 = __ldg(reinterpret_cast<const float4*>(r0 + (int64_t)x0 * C));
-          v10 = __ldg(reinterpret_cast<const float4*>(r1 + (int64_t)x0 * C));
-        }
+        vl = (x0 == cx1) ? vr : resize_vblend(r0 + (int64_t)x0 * C, r1 + (int64_t)x0 * C, hy, ly);   // slide or fetch
         cx0 = x0;
       }
       if (x1 != cx1) {
-        if (x1 == x0) { v01 = v00; v11 = v10; }
-        else {
-          v01 = __ldg(reinterpret_cast<const float4*>(r0 + (int64_t)x1 * C));
-          v11 = __ldg(reinterpret_cast<const float4*>(r1 + (int64_t)x1 * C));
-        }
+        vr = (x1 == x0) ? vl : resize_vblend(r0 + (int64_t)x1 * C, r1 + (int64_t)x1 * C, hy, ly);
         cx1 = x1;
       }
       const float hx = 1.f - lx;
-      float4 r;
-      r.x = act_fn(hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x), act);
-      r.y = act_fn(hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y), act);
-      r.z = act_fn(hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z), act);
-      r.w = act_fn(hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w), act);
+      float4 r = make_float4(fmaf(lx, vr.x, hx * vl.x), fmaf(lx, vr.y, hx * vl.y), fmaf(lx, vr.z, hx * vl.z),
+                             fmaf(lx, vr.w, hx * vl.w));
+      if (ACT != 0) { r.x = act_fn(r.x, ACT); r.y = act_fn(r.y, ACT); r.z = act_fn(r.z, ACT); r.w = act_fn(r.w, ACT); }
       dst[(int64_t)j * cq] = r;
     }
   }
@@ -199,6 +196,38 @@ resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, 
 }
 
 
+// Planar maps whose output rows are whole float4s (the 1-2 channel flow / occlusion maps resized to every decoder
+// resolution): one thread per 4 consecutive outputs of a row -- the row taps and the plane decomposition are evaluated
+// once per 4 outputs and the store is one 16-byte vector.
+__global__ void __launch_bounds__(256)
+resize_bilinear_nchw_v4_kernel(const float* __restrict__ x, float4* __restrict__ y, int H, int W, int Ho, int Wo4, float sy,
+                               float sx, int64_t total4, int act, int64_t y_row_pitch4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Wo4);
+    const int oy = (int)((i / Wo4) % Ho);
+    const int64_t plane = i / ((int64_t)Wo4 * Ho);
+    int y0, y1;
+    float ly;
+    resize_axis(oy, sy, H, y0, y1, ly);
+    const float hy = 1.f - ly;
+    const float* r0 = x + (plane * H + y0) * W;
+    const float* r1 = x + (plane * H + y1) * W;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int x0, x1;
+      float lx;
+      resize_axis(4 * q + j, sx, W, x0, x1, lx);
+      const float hx = 1.f - lx;
+      o[j] = act_fn(hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1)), act);
+    }
+    // y_row_pitch4: float4s per output row of the destination (== Wo4 for a dense map; wider when the map is one column
+    // block of a strip, mrfa_resize_bilinear_strip)
+    y[(plane * Ho + oy) * y_row_pitch4 + q] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+
 // Flow / occlusion carry to the next (2x finer) level (raft.py:276-295).
 // The reference issues ~10 align_corners bilinear resizes of 1-2 channel maps plus as many
 // elementwise kernels per level; here one thread per fine pixel evaluates the whole update:
@@ -213,7 +242,7 @@ struct CarryTaps {
   float ly, lx;
 };
 
-__device__ __forceinline__ float carry_interp(const float* __restrict__ p, int64_t sy, int64_t sx, const CarryTaps& t) {
+__device__ __forceinline__ float carry_interp(const float* __restrict__ p, int sy, int sx, const CarryTaps& t) {
   const float hy = 1.f - t.ly, hx = 1.f - t.lx;
   return hy * (hx * __ldg(p + t.y0 * sy + t.x0 * sx) + t.lx * __ldg(p + t.y0 * sy + t.x1 * sx)) +
          t.ly * (hx * __ldg(p + t.y1 * sy + t.x0 * sx) + t.lx * __ldg(p + t.y1 * sy + t.x1 * sx));
@@ -224,21 +253,22 @@ flow_carry_kernel(const float* __restrict__ d_flow, mrfa_grid_strides_t ds, cons
                   const float* __restrict__ prior_occ, const float* __restrict__ d_f_pre,
                   const float* __restrict__ d_occ_pre, float* __restrict__ flow, float* __restrict__ occ,
                   float* __restrict__ d_f_acc, float* __restrict__ d_occ_acc, int R, int h, float scale, int cl,
-                  float s_r, float s_h, int64_t total) {
+                  float s_r, float s_h, int64_t total, IndexSplit sp) {
   const int Ro = 2 * R;
+  const int dsy = (int)ds.sy, dsx = (int)ds.sx;          // strides inside one sample: checked to fit 32 bits at launch
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % Ro);
-    const int oy = (int)((i / Ro) % Ro);
-    const int64_t n = i / ((int64_t)Ro * Ro);
+    int zero, ox, oy;
+    int64_t n, same;
+    split_index(i, sp, zero, ox, oy, n, same);           // sp.c divides by 1: i -> (ox, oy, n)
     CarryTaps tr, th;
     resize_axis(oy, s_r, R, tr.y0, tr.y1, tr.ly);
     resize_axis(ox, s_r, R, tr.x0, tr.x1, tr.lx);
     resize_axis(oy, s_h, h, th.y0, th.y1, th.ly);
     resize_axis(ox, s_h, h, th.x0, th.x1, th.lx);
     const float* df = d_flow + n * ds.sn;
-    const float dfx = __fmul_rn(carry_interp(df, ds.sy, ds.sx, tr), 2.f);
-    const float dfy = __fmul_rn(carry_interp(df + ds.sc, ds.sy, ds.sx, tr), 2.f);
-    const float dov = carry_interp(df + 2 * ds.sc, ds.sy, ds.sx, tr);
+    const float dfx = __fmul_rn(carry_interp(df, dsy, dsx, tr), 2.f);
+    const float dfy = __fmul_rn(carry_interp(df + ds.sc, dsy, dsx, tr), 2.f);
+    const float dov = carry_interp(df + 2 * ds.sc, dsy, dsx, tr);
     const float* fi = init_flow + n * 2 * h * h;
     float fx = __fadd_rn(dfx, __fdiv_rn(carry_interp(fi, h, 1, th), scale));
     float fy = __fadd_rn(dfy, __fdiv_rn(carry_interp(fi + (int64_t)h * h, h, 1, th), scale));
@@ -247,7 +277,7 @@ flow_carry_kernel(const float* __restrict__ d_flow, mrfa_grid_strides_t ds, cons
     if (d_f_pre != nullptr) {
       // the accumulated update of the previous level lives at R x R in the caller's memory format
       const float* pp = d_f_pre + n * 2 * R * R;
-      const int64_t psy = cl ? 2 * R : R, psx = cl ? 2 : 1, psc = cl ? 1 : (int64_t)R * R;
+      const int psy = cl ? 2 * R : R, psx = cl ? 2 : 1, psc = cl ? 1 : R * R;
       const float ux = __fmul_rn(carry_interp(pp, psy, psx, tr), 2.f);
       const float uy = __fmul_rn(carry_interp(pp + psc, psy, psx, tr), 2.f);
       const float uo = carry_interp(d_occ_pre + n * R * R, R, 1, tr);
@@ -297,6 +327,45 @@ antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ we
 }
 
 
+// The configuration the path runs (scale 0.25: stride 4, K = 13, ka = 6): a block produces a 16 x 16 output tile of one
+// plane from a 76 x 76 input patch staged in shared memory (zero-filled outside the image, so skipped taps of the
+// generic kernel become exact +0 terms of the same fused-multiply-add chain).  The patch is stored de-interleaved by
+// x mod 4 with a row pitch of 20 words: lane tx reads column 4 tx + b at plane b & 3, word tx + (b >> 2) -- consecutive
+// lanes, consecutive banks; the two output rows of a warp sit 16 banks apart.
+constexpr int kAaTile = 16, kAaStride = 4, kAaK = 13, kAaKa = 6;
+constexpr int kAaPatch = kAaTile * kAaStride + kAaK - 1;          // 76 input rows / columns per tile
+constexpr int kAaPitch = 20;                                      // words per de-interleaved row (19 used)
+
+__global__ void __launch_bounds__(256)
+antialias_down_s4k13_kernel(const float* __restrict__ in, const float* __restrict__ weight, float* __restrict__ out, int C,
+                            int H, int W, int Ho, int Wo) {
+  __shared__ float patch[4][kAaPatch][kAaPitch];
+  __shared__ float wk[kAaK * kAaK];
+  const int tiles_x = (Wo + kAaTile - 1) / kAaTile;
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  const int64_t plane = blockIdx.y;
+  const float* src = in + plane * H * W;
+  const int gy0 = tile_y * kAaTile * kAaStride - kAaKa, gx0 = tile_x * kAaTile * kAaStride - kAaKa;
+  for (int e = threadIdx.x; e < kAaPatch * kAaPatch; e += 256) {
+    const int py = e / kAaPatch, px = e - py * kAaPatch;
+    const int yy = gy0 + py, xx = gx0 + px;
+    patch[px & 3][py][px >> 2] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(src + (int64_t)yy * W + xx) : 0.f;
+  }
+  if (threadIdx.x < kAaK * kAaK) wk[threadIdx.x] = __ldg(weight + (int64_t)(plane % C) * kAaK * kAaK + threadIdx.x);
+  __syncthreads();
+  const int tx = threadIdx.x % kAaTile, ty = threadIdx.x / kAaTile;
+  const int ox = tile_x * kAaTile + tx, oy = tile_y * kAaTile + ty;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int a = 0; a < kAaK; ++a) {
+    const int py = ty * kAaStride + a;
+#pragma unroll
+    for (int b = 0; b < kAaK; ++b) acc = fmaf(patch[b & 3][py][tx + (b >> 2)], wk[a * kAaK + b], acc);
+  }
+  if (ox < Wo && oy < Ho) out[(plane * Ho + oy) * Wo + ox] = acc;
+}
+
+
 // Occlusion blend whose second operand is a "sub-pixel" up-convolution result: a 3x3 conv on a
 // x2 nearest-upsampled map equals four 2x2 convs on the low-resolution map (one per output
 // parity), so UpBlock2d (util.py:160-177) runs as ONE 2x2 conv with 4*C outputs on the padded
@@ -308,14 +377,14 @@ antialias_down_kernel(const float* __restrict__ in, const float* __restrict__ we
 // 7x7 convolution (generator.py:32,61) can run as a 3x3 convolution with r*r*3 outputs.
 __global__ void __launch_bounds__(256)
 occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ occ,
-                                float4* __restrict__ y, int64_t n4, int C, int H, int W, int r, int64_t ostride) {
+                                float4* __restrict__ y, int64_t n4, int C, int H, int W, int r, int64_t ostride, IndexSplit sp,
+                                FastDiv fr) {
   const int cq = C / 4, W2 = 2 * W, H2 = 2 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cq) * 4;
-    const int64_t pix = i / cq;
-    const int X = (int)(pix % W2);
-    const int Y = (int)((pix / W2) % H2);
-    const int64_t n = pix / ((int64_t)W2 * H2);
+    int c4, X, Y;
+    int64_t n, pix;
+    split_index(i, sp, c4, X, Y, n, pix);
+    const int c = c4 * 4;
     const int pa = Y & 1, pb = X & 1;
     const float o = __ldg(occ + pix);
     const float4 w = __ldg(reinterpret_cast<const float4*>(
@@ -326,8 +395,9 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
     if (r == 1) {
       y[(pix * ostride + c) / 4] = v;
     } else {
-      const int64_t blk = (n * (H2 / r) + Y / r) * (W2 / r) + X / r;
-      y[(blk * (r * r) + (Y % r) * r + (X % r)) * cq + c / 4] = v;
+      const int Yb = (int)fast_div((uint32_t)Y, fr), Xb = (int)fast_div((uint32_t)X, fr);
+      const int64_t blk = (n * (H2 / r) + Yb) * (W2 / r) + Xb;
+      y[(blk * (r * r) + (Y - Yb * r) * r + (X - Xb * r)) * cq + c4] = v;
     }
   }
 }
@@ -340,16 +410,14 @@ occlusion_blend_subpixel_kernel(const float4* __restrict__ a, const float* __res
 // b2 (N, H+1, W+1, 4C) NHWC; skip (N, Cs, 2H, 2W) with element strides; y (N, 2H, 2W, C+Cs) NHWC.
 __global__ void __launch_bounds__(256)
 subpixel_shuffle_cat_v4_kernel(const float* __restrict__ b2, const float4* __restrict__ skip, float4* __restrict__ y,
-                               int64_t n4, int C, int Cs, int H, int W) {
-  const int ct = C + Cs, cq = ct / 4, W2 = 2 * W, H2 = 2 * H;
+                               int64_t n4, int C, int Cs, int H, int W, IndexSplit sp) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cq) * 4;
-    const int64_t pix = i / cq;
+    int c4, X, Y;
+    int64_t n, pix;
+    split_index(i, sp, c4, X, Y, n, pix);
+    const int c = c4 * 4;
     float4 v;
     if (c < C) {
-      const int X = (int)(pix % W2);
-      const int Y = (int)((pix / W2) % H2);
-      const int64_t n = pix / ((int64_t)W2 * H2);
       const int pa = Y & 1, pb = X & 1;
       v = __ldg(reinterpret_cast<const float4*>(
           b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C + c));
@@ -360,24 +428,26 @@ subpixel_shuffle_cat_v4_kernel(const float* __restrict__ b2, const float4* __res
   }
 }
 
+// Any channel counts / any skip strides (the hourglass inputs: 10, 13 or 44 channels, NCHW): a warp owns one output pixel
+// per step, so the pixel decomposition is evaluated once per pixel instead of once per element, lanes run along the
+// channels (contiguous 4C-channel phase block of b2, contiguous output pixel), and the strided reads of a planar skip map
+// fall into sectors that the neighbouring warps of the block (the next pixels of the row) reuse out of L1.
 __global__ void __launch_bounds__(256)
 subpixel_shuffle_cat_kernel(const float* __restrict__ b2, const float* __restrict__ skip, mrfa_grid_strides_t ss,
-                            float* __restrict__ y, int64_t total, int C, int Cs, int H, int W) {
-  const int ct = C + Cs, W2 = 2 * W, H2 = 2 * H;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ct);
-    const int64_t pix = i / ct;
-    const int X = (int)(pix % W2);
-    const int Y = (int)((pix / W2) % H2);
-    const int64_t n = pix / ((int64_t)W2 * H2);
-    float v;
-    if (c < C) {
-      const int pa = Y & 1, pb = X & 1;
-      v = __ldg(b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C + c);
-    } else {
-      v = __ldg(skip + n * ss.sn + (int64_t)(c - C) * ss.sc + (int64_t)Y * ss.sy + (int64_t)X * ss.sx);
-    }
-    y[i] = v;
+                            float* __restrict__ y, int64_t pixels, int C, int Cs, int H, int W, IndexSplit sp) {
+  const int ct = C + Cs;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < pixels; pix += nwarps) {
+    int zero, X, Y;
+    int64_t n, same;
+    split_index(pix, sp, zero, X, Y, n, same);          // sp.c divides by 1: pix -> (X, Y, n)
+    const int pa = Y & 1, pb = X & 1;
+    const float* src = b2 + ((n * (H + 1) + (Y >> 1) + pa) * (W + 1) + (X >> 1) + pb) * (4 * (int64_t)C) + (2 * pa + pb) * C;
+    const float* sk = skip + n * ss.sn + (int64_t)Y * ss.sy + (int64_t)X * ss.sx;
+    float* dst = y + pix * ct;
+    for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
+    for (int c = lane; c < Cs; c += 32) dst[C + c] = __ldg(sk + (int64_t)c * ss.sc);
   }
 }
 
@@ -424,14 +494,12 @@ cat2_nhwc_kernel(const float4* __restrict__ a, const float4* __restrict__ b, flo
 // 1 store, window summed row-major then divided by 4 like ATen.  (The stock NHWC avg_pool2d
 // kernel runs at ~0.8 TB/s on the 2 GB encoder maps.)
 __global__ void __launch_bounds__(256)
-avg_pool2x2_nhwc_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int H, int W, int64_t n4) {
-  const int cq = C / 4, Wo = W / 2, Ho = H / 2;
+avg_pool2x2_nhwc_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int H, int W, int64_t n4, IndexSplit sp) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cq) * 4;
-    const int64_t pix = i / cq;
-    const int ox = (int)(pix % Wo);
-    const int oy = (int)((pix / Wo) % Ho);
-    const int64_t n = pix / ((int64_t)Wo * Ho);
+    int c4, ox, oy;
+    int64_t n, pix;
+    split_index(i, sp, c4, ox, oy, n, pix);
+    const int c = c4 * 4;
     const float* p = x + ((n * H + 2 * oy) * W + 2 * ox) * (int64_t)C + c;
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + C));
     const float4 d = __ldg(reinterpret_cast<const float4*>(p + (int64_t)W * C));
@@ -499,13 +567,36 @@ extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int 
   if (channels_last && C % 4 == 0 &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     const int64_t runs = (int64_t)N * Ho * ((Wo + kResizeRun - 1) / kResizeRun) * (C / 4);
-    resize_bilinear_nhwc_kernel<<<stream_blocks(runs), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, act);
+    const IndexSplit sp = make_index_split(C / 4, (Wo + kResizeRun - 1) / kResizeRun, Ho);
+    const unsigned g = stream_blocks(runs);
+    cudaStream_t st = as_stream(stream);
+    if (act == 0) resize_bilinear_nhwc_kernel<0><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
+    else if (act == 1) resize_bilinear_nhwc_kernel<1><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
+    else resize_bilinear_nhwc_kernel<2><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
   } else if (channels_last) {
     resize_bilinear_nhwc_scalar_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
                                                                                             total, act);
+  } else if (Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    resize_bilinear_nchw_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), H, W,
+                                                                                           Ho, Wo / 4, sy, sx, total / 4, act, Wo / 4);
   } else {
     resize_bilinear_nchw_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, H, W, Ho, Wo, sy, sx, total, act);
   }
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_resize_bilinear_strip(const float* x, float* y, int64_t planes, int H, int W, int Ho, int Wo,
+                                         int64_t y_row_pitch, int64_t y_col_offset, int act, mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(x && y && planes >= 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && act >= 0 && act <= 2);
+  MRFA_CHECK_ARG(y_col_offset >= 0 && y_row_pitch >= y_col_offset + Wo);
+  MRFA_CHECK_SHAPE(Wo % 4 == 0 && y_row_pitch % 4 == 0 && y_col_offset % 4 == 0);
+  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0) return MRFA_E_ALIGN;
+  if (planes == 0) return 0;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t total4 = planes * Ho * (Wo / 4);
+  resize_bilinear_nchw_v4_kernel<<<stream_blocks(total4), 256, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<float4*>(y + y_col_offset), H, W, Ho, Wo / 4, sy, sx, total4, act, y_row_pitch / 4);
   return MRFA_LAUNCH_RESULT();
 }
 
@@ -516,6 +607,11 @@ extern "C" int mrfa_antialias_down(const float* in, const float* weight, float* 
   const int Ho = H / stride, Wo = W / stride;       // floor(H * scale) of F.interpolate(scale_factor = 1/stride)
   MRFA_CHECK_SHAPE(Ho > 0 && Wo > 0);
   const int64_t total = (int64_t)N * C * Ho * Wo;
+  if (stride == kAaStride && K == kAaK && ka == kAaKa && (int64_t)N * C <= 65535) {
+    dim3 grid((unsigned)(((Wo + kAaTile - 1) / kAaTile) * ((Ho + kAaTile - 1) / kAaTile)), (unsigned)(N * C));
+    antialias_down_s4k13_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, weight, out, C, H, W, Ho, Wo);
+    return MRFA_LAUNCH_RESULT();
+  }
   antialias_down_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(in, weight, out, C, H, W, Ho, Wo, K, ka, stride, total);
   return MRFA_LAUNCH_RESULT();
 }
@@ -531,7 +627,7 @@ extern "C" int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, co
   const int64_t n4 = (int64_t)N * 4 * H * W * C / 4;
   occlusion_blend_subpixel_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(a), b2, occ, reinterpret_cast<float4*>(y), n4, C, H, W, out_block,
-      out_pixel_stride > 0 ? out_pixel_stride : (int64_t)C);
+      out_pixel_stride > 0 ? out_pixel_stride : (int64_t)C, make_index_split(C / 4, 2 * W, 2 * H), make_fastdiv((uint32_t)out_block));
   return MRFA_LAUNCH_RESULT();
 }
 
@@ -541,7 +637,8 @@ extern "C" int mrfa_avg_pool2x2_nhwc(const float* x, float* y, int N, int C, int
   if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return MRFA_E_ALIGN;
   if (N == 0) return 0;
   const int64_t n4 = (int64_t)N * (H / 2) * (W / 2) * C / 4;
-  avg_pool2x2_nhwc_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, H, W, n4);
+  avg_pool2x2_nhwc_kernel<<<stream_blocks(n4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, H, W, n4,
+                                                                            make_index_split(C / 4, W / 2, H / 2));
   return MRFA_LAUNCH_RESULT();
 }
 
@@ -552,6 +649,7 @@ extern "C" int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_stride
   MRFA_CHECK_ARG(d_flow && init_flow && prior_occ && flow && occ && d_f_acc && d_occ_acc);
   MRFA_CHECK_ARG((d_f_pre == nullptr) == (d_occ_pre == nullptr));
   MRFA_CHECK_ARG(B >= 0 && R > 0 && h > 0 && scale != 0.f);
+  MRFA_CHECK_SHAPE(R <= 16384 && h <= 16384 && d_strides.sy * R < ((int64_t)1 << 31) && d_strides.sx * R < ((int64_t)1 << 31));
   if (B == 0) return 0;
   if (channels_last && ((reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(d_f_acc)) & 7) != 0)
     return MRFA_E_ALIGN;
@@ -561,7 +659,8 @@ extern "C" int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_stride
   const int64_t total = (int64_t)B * Ro * Ro;
   flow_carry_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(d_flow, d_strides, init_flow, prior_occ, d_f_pre,
                                                                          d_occ_pre, flow, occ, d_f_acc, d_occ_acc, R, h,
-                                                                         scale, channels_last, s_r, s_h, total);
+                                                                         scale, channels_last, s_r, s_h, total,
+                                                                         make_index_split(1, Ro, Ro));
   return MRFA_LAUNCH_RESULT();
 }
 
@@ -575,10 +674,12 @@ extern "C" int mrfa_subpixel_shuffle_cat(const float* b2, const float* skip, mrf
   if (C % 4 == 0 && Cs % 4 == 0 && (Cs == 0 || dense_nhwc) &&
       ((reinterpret_cast<uintptr_t>(b2) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     subpixel_shuffle_cat_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(
-        b2, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(y), total / 4, C, Cs, H, W);
+        b2, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(y), total / 4, C, Cs, H, W,
+        make_index_split((C + Cs) / 4, 2 * W, 2 * H));
   } else {
-    subpixel_shuffle_cat_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(b2, skip, skip_strides, y, total, C, Cs,
-                                                                                    H, W);
+    const int64_t pixels = (int64_t)N * 4 * H * W;
+    subpixel_shuffle_cat_kernel<<<stream_blocks(pixels * 32), 256, 0, as_stream(stream)>>>(
+        b2, skip, skip_strides, y, pixels, C, Cs, H, W, make_index_split(1, 2 * W, 2 * H));
   }
   return MRFA_LAUNCH_RESULT();
 }

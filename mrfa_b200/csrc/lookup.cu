@@ -189,7 +189,11 @@ corr_lookup_fwd_kernel(const T* __restrict__ level0, const T* __restrict__ level
 //   write     through a staging tile so both output layouts leave as full 128-byte lines (NHWC: the 32 queries of a
 //             group are one contiguous 12.5 KB run).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPatchStride = 2 * 8 * 8 + 1;          // two levels x 8 rows x 16 bf16 columns = 128 words; odd stride
+// two levels x 8 rows x 16 bf16 columns = 128 words per query, + 4: a multiple of 4 so a gathering lane parks its 16-byte
+// tile row with ONE conflict-free st.shared.v4.  The evaluating lanes (lane = query) then sit 4 banks apart, so queries
+// 8, 16, 24 apart would collide on the same word: the 4 words of every 16-byte chunk are stored XOR-permuted by
+// (query >> 3), which spreads those four lanes over the chunk's four banks (conflict-free for equal word indices).
+constexpr int kPatchStride = 2 * 8 * 8 + 4;
 constexpr int kFracStride = 2 * 2 * 7 + 1;           // [level][axis][tap] fractions per query (odd stride)
 constexpr int kGroupT = 8;                           // queries per warp per group = loads in flight per lane
 constexpr int kTiledBlocksPerSM = 5;                 // resident persistent blocks per SM (~37 KB of shared memory each)
@@ -199,7 +203,7 @@ struct LookupSmem {
   static constexpr int n = 2 * R + 1;
   static constexpr int kOut = 2 * n * n;               // outputs per query, stored back to back (float4 copy-out)
   alignas(16) float outs[kQPB * kOut];
-  uint32_t patch[kQPB * kPatchStride];                 // per query: [level][row 0..7][8 words = tile columns tx, tx+1 as loaded]
+  alignas(16) uint32_t patch[kQPB * kPatchStride];                 // per query: [level][row 0..7][8 words = tile columns tx, tx+1 as loaded]
   float frac[2][kQPB * kFracStride];
   alignas(16) int org[2][kQPB][4];                     // footprint origin (x0, y0) per level
 };
@@ -288,8 +292,15 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
     // ---- park the gathered tile rows as loaded (packed bf16): word (level*64 + row*8 + half*4 + i) == lane*4 + i
 #pragma unroll
     for (int g = 0; g < kGroupT; ++g) {
-      uint32_t* d = sm.patch + (warp + g * kWarps) * kPatchStride + lane * 4;
-      d[0] = v[g].x; d[1] = v[g].y; d[2] = v[g].z; d[3] = v[g].w;
+      uint4* d = reinterpret_cast<uint4*>(sm.patch + (warp + g * kWarps) * kPatchStride + lane * 4);
+      constexpr int kW4 = kWarps == 4 ? 1 : 0;
+      static_assert(kW4 == 1, "the chunk permutation below assumes query = warp + 4 * g");
+      switch ((g >> 1) & 3) {                           // (query >> 3) with query = warp + 4 g, warp < 4: static per g
+        case 0: *d = make_uint4(v[g].x, v[g].y, v[g].z, v[g].w); break;
+        case 1: *d = make_uint4(v[g].y, v[g].x, v[g].w, v[g].z); break;
+        case 2: *d = make_uint4(v[g].z, v[g].w, v[g].x, v[g].y); break;
+        default: *d = make_uint4(v[g].w, v[g].z, v[g].y, v[g].x); break;
+      }
     }
     // ---- geometry + loads of the next group: in flight while this group is evaluated and written
     const int64_t nxt = grp + gridDim.x;
@@ -307,6 +318,7 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
       const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 14;
       float* oq = sm.outs + lane * kOut + lvl * NN;
       const int dx = sm.org[buf][lane][2 * lvl] & 7;
+      const int kx = lane >> 3;
       float fy[n];
 #pragma unroll
       for (int bb = 0; bb < n; ++bb) fy[bb] = fq[7 + bb];
@@ -314,19 +326,20 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
       for (int a = a_begin; a < a_end; ++a) {
         const int e0 = dx + a;
         const bool odd = e0 & 1;
-        const uint32_t* pw = pq + (e0 >> 1);
+        const uint32_t* pa = pq + ((e0 >> 1) ^ kx);          // word holding element e0 / the next word (chunk-permuted)
+        const uint32_t* pb = pq + (((e0 >> 1) + 1) ^ kx);
         const uint32_t sel0 = odd ? 0x3244u : 0x1044u;     // element e0: high / low half of word A -> fp32
         const uint32_t sel1 = odd ? 0x1044u : 0x3244u;     // element e0 + 1: low half of word B / high half of word A
         const float fx = fq[a];
         const float wx0 = 1.f - fx;
         float hprev;
         {
-          const uint32_t wa = pw[0], wb = pw[1];
+          const uint32_t wa = pa[0], wb = pb[0];
           hprev = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx, __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
         }
 #pragma unroll
         for (int bb = 0; bb < n; ++bb) {
-          const uint32_t wa = pw[(bb + 1) * 8], wb = pw[(bb + 1) * 8 + 1];
+          const uint32_t wa = pa[(bb + 1) * 8], wb = pb[(bb + 1) * 8];
           const float hnext = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx,
                                    __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
           oq[a * n + bb] = fmaf(hnext, fy[bb], hprev * (1.f - fy[bb]));

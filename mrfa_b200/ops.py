@@ -7,7 +7,7 @@ calling an op with CPU tensors raises.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -750,6 +750,36 @@ def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int) -> Tensor:
 def _(x, Ho, Wo, act):
     y = x.new_empty((x.shape[0], x.shape[1], Ho, Wo))
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
+
+
+@torch.library.custom_op("mrfa::resize_strip", mutates_args=(), device_types="cuda")
+def resize_strip(maps: Sequence[Tensor], Ho: int, Wo: int) -> Tensor:
+    """torch.cat([F.interpolate(m, (Ho,Wo), mode='bilinear', align_corners=True) for m in maps], dim=3) (raft.py:304-306)
+    without the intermediate maps and the cat pass: every map is resized straight into its column block of the strip.
+    maps: (N, C, H_i, W_i) float32 CUDA tensors, plain contiguous (or C == 1); Wo % 4 == 0."""
+    if len(maps) == 0:
+        raise RuntimeError("mrfa_b200: resize_strip needs at least one map")
+    N, C = maps[0].shape[:2]
+    for m in maps:
+        if not m.is_cuda or m.dtype != torch.float32 or m.dim() != 4 or m.shape[0] != N or m.shape[1] != C:
+            raise RuntimeError("mrfa_b200: resize_strip expects 4-D float32 CUDA maps with equal N, C (there is no CPU fallback)")
+    if Wo % 4 != 0:
+        raise RuntimeError("mrfa_b200: resize_strip needs Wo % 4 == 0")
+    y = torch.empty((N, C, Ho, Wo * len(maps)), device=maps[0].device, dtype=torch.float32)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(y.device):
+        for i, m in enumerate(maps):
+            m = m.contiguous()                          # planar (N*C, H, W); a no-op for C == 1 maps in either memory format
+            with _timed("resize_bilinear", 4 * (m.numel() + N * C * Ho * Wo)):
+                check(lib.mrfa_resize_bilinear_strip(_p(m), _p(y), N * C, m.shape[2], m.shape[3], Ho, Wo, Wo * len(maps), i * Wo, 0,
+                                                     _stream()), "mrfa_resize_bilinear_strip")
+    return y
+
+
+@resize_strip.register_fake
+def _(maps, Ho, Wo):
+    return maps[0].new_empty((maps[0].shape[0], maps[0].shape[1], Ho, Wo * len(maps)))
 
 
 def conv7x7_small_pack(weight: Tensor) -> Tensor:

@@ -333,5 +333,8 @@ class RaftFlow(nn.Module):
         warp_img = sampling.warp_by_flow(img_full, flow)                                   # raft.py:302
         out = self.generator.decode(out_warp_f, warp_img, out_occlusion, out_warp_f_c, out_occlusion_c, coarse_cat=cat_bufs)
         vis = out_occlusion + [torch.sigmoid(prior_occ)]
-        occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in vis], dim=3)
+        if img_full.is_cuda and not torch.is_grad_enabled() and self.size % 4 == 0:
+            occlusion = torch.ops.mrfa.resize_strip(vis, self.size, self.size)           # raft.py:304-306 in one strip
+        else:
+            occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in vis], dim=3)
         return out, warp_img, occlusion

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, GPU call E: epilogue-variant diagnosis, ncu of the current lookup, ncu --set full of the "next"-row kernels in one step
+mkdir -p gpurun_out/r2e
+timeout 300 python scripts/diag/epilogue_variants.py > gpurun_out/r2e/epilogue_variants.txt 2>&1
+NCU="ncu --set full --clock-control none --import-source on"
+timeout 600 $NCU -k regex:corr_lookup_fwd_tiled -s 1 -c 1 -f -o gpurun_out/r2e/ncu_lookup python scripts/ncu_targets.py --only lookup > gpurun_out/r2e/ncu_lookup.log 2>&1
+timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"resize_bilinear|conv7x7_small|subpixel_shuffle|antialias|occlusion_blend|flow_carry|dense_motion_prior|kp2gaussian|corr_lookup|corr_pack|cast_bf16" -f -o gpurun_out/r2e/ncu_next python scripts/profile_step.py > gpurun_out/r2e/ncu_next.log 2>&1
+ncu -i gpurun_out/r2e/ncu_next.ncu-rep --page raw --csv > gpurun_out/r2e/ncu_next_raw.csv 2>/dev/null
+ls -la gpurun_out/r2e
+cat gpurun_out/r2e/epilogue_variants.txt

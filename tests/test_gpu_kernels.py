@@ -328,7 +328,18 @@ def test_corr_lookup_from_tiled_pyramid(h, w, C):
     coords = torch.rand(B, 2, h, w) * torch.tensor([w + 6.0, h + 6.0]).view(1, 2, 1, 1) - 3.0
     l0, l1 = pyr.dense(0).cpu().numpy(), pyr.dense(0, 1).cpu().numpy()
     for r in (1, 2, 4):
-        close(pyr.block(0, radius=r)(coords.to(DEV)), O.corr_lookup([l0, l1], coords.numpy(), radius=r))
+        exp = O.corr_lookup([l0, l1], coords.numpy(), radius=r)
+        close(pyr.block(0, radius=r)(coords.to(DEV)), exp)
+        close(pyr.block(0, radius=r)(coords.to(DEV), True), exp)            # channels-last output: the warp-autonomous kernel
+    # ragged query counts (Q not a multiple of the 4 queries a warp pass takes; a pass never straddles two samples)
+    for hq, wq in ((3, 5), (1, 1), (7, 9)):
+        coords = torch.rand(B, 2, hq, wq) * torch.tensor([w + 6.0, h + 6.0]).view(1, 2, 1, 1) - 3.0
+        blk = pyr.block(0)
+        blk._stride, blk._offset = pyr.rows_total, 0
+        exp = O.corr_lookup([l0.reshape(B, h * w, 1, h, w)[:, :hq * wq].reshape(B * hq * wq, 1, h, w),
+                             l1.reshape(B, h * w, 1, h // 2, w // 2)[:, :hq * wq].reshape(B * hq * wq, 1, h // 2, w // 2)], coords.numpy())
+        close(blk(coords.to(DEV), True), exp)
+        close(blk(coords.to(DEV)), exp)
 
 
 def test_corr_lookup_backward_tiled_pyramid():
@@ -768,6 +779,22 @@ def test_resize_bilinear(cl):
     close(out, F.interpolate(flow.cpu().contiguous(), size=(18, 18), mode="bilinear", align_corners=True), 2e-6)
 
 
+def test_resize_strip_matches_cat_of_resizes():
+    """raft.py:304-306: the occlusion strip = cat of align_corners resizes along the width, written by one kernel per map."""
+    torch.manual_seed(22)
+    maps = [torch.rand(3, 1, r, r, device=DEV) for r in (2, 4, 8, 16, 32, 64, 16)]
+    maps[2] = maps[2].contiguous(memory_format=torch.channels_last)
+    ref = torch.cat([F.interpolate(m.cpu().contiguous(), size=(64, 64), mode="bilinear", align_corners=True) for m in maps], dim=3)
+    out = torch.ops.mrfa.resize_strip(maps, 64, 64)
+    assert out.shape == (3, 1, 64, 7 * 64)
+    close(out, ref, 2e-6)
+    two = [torch.rand(2, 2, 5, 7, device=DEV), torch.rand(2, 2, 9, 3, device=DEV)]
+    ref = torch.cat([F.interpolate(m.cpu(), size=(10, 12), mode="bilinear", align_corners=True) for m in two], dim=3)
+    close(torch.ops.mrfa.resize_strip(two, 10, 12), ref, 2e-6)
+    with pytest.raises(Exception):
+        torch.ops.mrfa.resize_strip(two, 10, 10)                       # Wo % 4 != 0
+
+
 @pytest.mark.parametrize("cl", [False, True])
 def test_flow_carry_matches_reference_chain(cl):
     """raft.py:276-295 (the per-level flow / occlusion hand-over) as one kernel vs the torch op chain on CPU."""
@@ -806,7 +833,7 @@ def test_flow_carry_matches_reference_chain(cl):
 def test_antialias_down_matches_reference_order():
     from mrfa_b200 import blocks
     torch.manual_seed(14)
-    for scale, size in ((0.25, 64), (0.25, 256), (0.5, 32)):
+    for scale, size in ((0.25, 64), (0.25, 256), (0.25, 100), (0.5, 32)):
         aa = blocks.AntiAliasInterpolation2d(3, scale).to(DEV).eval()
         x = torch.rand(2, 3, size, size, device=DEV)
         with torch.no_grad():
