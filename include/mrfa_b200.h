@@ -174,6 +174,12 @@ int64_t mrfa_corr_map_offset(int map_layout, int level, int y, int x, int W_leve
 int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op,
                    int B, int C, int h, int w, int channels_last, mrfa_stream_t stream);
 
+/* mrfa_corr_pack for NHWC inputs with the per-channel biases of the two 1x1 head convolutions that produce q_d / k_s
+ * (raft.py:180-181 kp_img_head, kp_head) added on the fly: packs (q_d + q_bias) and (k_s + k_bias), so the heads can run
+ * as plain GEMMs without a separate bias pass over the (B,C,h,w) maps.  q_bias / k_bias (C) fp32 or NULL, 16-byte aligned. */
+int mrfa_corr_pack_bias(const float* q_d, const float* q_bias, const float* k_s, const float* k_bias, void* a_op, void* b_op,
+                        int B, int C, int h, int w, mrfa_stream_t stream);
+
 /* volume0[b,i,j]  = scale * sum_c a_op[b,i,c] * b_op[b,j,c]            (B, rows_total, h*w)  bf16
  * volume1[b,i,j'] = mean over the 2x2 source block j' of the above      (B, rows_total, hw/4) bf16
  * (raft.py:185 einsum * self.scale; CorrBlock.__init__ raft.py:20 avg_pool2d level 1).
@@ -268,8 +274,10 @@ int mrfa_occlusion_blend_subpixel(const float* a, const float* b2, const float* 
 /* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=True) raft.py:243 (and :205,228,
  * 266,...) fused with an optional activation (act as above).  SURVEY.md 8(f) N1: used as
  * relu(upsample(convc1(corr))) == relu(convc1(upsample(corr))) (raft.py:241-243, :61).
- * x (N,C,H,W) -> y (N,C,Ho,Wo); NCHW or NHWC memory (any C; vectorised when C % 4 == 0).       */
-int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
+ * x (N,C,H,W) -> y (N,C,Ho,Wo); NCHW or NHWC memory (any C; vectorised when C % 4 == 0).
+ * bias (C) or NULL: added after the interpolation and before the activation -- the bias of the 1x1 convolution that
+ * was commuted below the resize (the bilinear weights sum to one, so resize(conv + b) == resize(conv) + b).      */
+int mrfa_resize_bilinear(const float* x, const float* bias, float* y, int N, int C, int H, int W, int Ho, int Wo,
                          int channels_last, int act, mrfa_stream_t stream);
 
 /* torch.cat([F.interpolate(o, size=(Ho,Wo), mode='bilinear', align_corners=True) for o in maps], dim=3) one map at a

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mrfa_corr_map_layout": (c_int, [c_int, c_int]),
     "mrfa_corr_map_offset": (c_int64, [c_int] * 5),
     "mrfa_corr_pack": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    "mrfa_corr_pack_bias": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
     "mrfa_corr_volume": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "mrfa_corr_bwd_rows_pad": (c_int64, [c_int, c_int]),
     "mrfa_corr_bwd_pack": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_void_p]),
@@ -56,7 +57,7 @@ SIGNATURES = {
     "mrfa_occlusion_blend_subpixel": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_int64, c_void_p]),
     "mrfa_avg_pool2x2_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_antialias_down": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
-    "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "mrfa_resize_bilinear": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "mrfa_resize_bilinear_strip": (c_int, [c_void_p, c_void_p, c_int64] + [c_int] * 4 + [c_int64, c_int64, c_int, c_void_p]),
     "mrfa_random_warp_grid": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "mrfa_conv7x7_small_kpad": (c_int, [c_int]),

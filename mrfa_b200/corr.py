@@ -77,13 +77,19 @@ class CorrPyramid:
     i.e. level 1 of every ``CorrBlock`` the reference rebuilds per iteration (raft.py:20,238).
     """
 
-    def __init__(self, q_d: torch.Tensor, k_s: torch.Tensor, scale: float):
+    def __init__(self, q_d: torch.Tensor, k_s: torch.Tensor, scale: float, q_bias=None, k_bias=None):
         self.B, self.C, self.h, self.w = q_d.shape
         self._holder_box = [None]
-        if torch.is_grad_enabled() and (q_d.requires_grad or k_s.requires_grad):
+        if torch.is_grad_enabled() and (q_d.requires_grad or k_s.requires_grad or
+                                        any(b is not None and b.requires_grad for b in (q_bias, k_bias))):
+            if q_bias is not None:
+                q_d = q_d + q_bias.view(1, -1, 1, 1)
+            if k_bias is not None:
+                k_s = k_s + k_bias.view(1, -1, 1, 1)
             self.volume0, self.volume1 = _CorrPyramidFn.apply(q_d, k_s, float(scale), self._holder_box)
         else:
-            self.volume0, self.volume1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, float(scale))
+            # q_bias / k_bias: the biases of the 1x1 heads that produced q_d / k_s, added inside the pack kernel
+            self.volume0, self.volume1 = torch.ops.mrfa.corr_pyramid(q_d, k_s, float(scale), q_bias, k_bias)
         self.rows_total = self.volume0.shape[1]
         self.layout = ops.corr_map_layout(self.h, self.w)      # _lib.MAP_TILED for w = 64 / 128, else row-major
 

@@ -101,8 +101,8 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
 // exactly once; the 2x2 / 4x4 / 8x8 means are built hierarchically in registers and written as
 // the pooled rows of a_op.  Lanes run along the channel quads -> 512-byte loads, 256-byte stores.
 __global__ void __launch_bounds__(256)
-corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, __nv_bfloat16* __restrict__ a_op, int C, int h, int w,
-                        int rows_total) {
+corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, const float* __restrict__ bias, __nv_bfloat16* __restrict__ a_op, int C,
+                        int h, int w, int rows_total) {
   const int cq = C / 4, bw = w / 8;
   const int nblk = (h / 8) * bw;
   const int b = blockIdx.y;
@@ -114,6 +114,9 @@ corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, __nv_bfloat16* __restrict
     const int blk = (int)(i / (uint32_t)cq);
     const int c = (int)(i - (uint32_t)blk * cq) * 4;
     const int by = blk / bw, bx = blk - by * bw;
+    // bias of the 1x1 head convolution that produced q_d (raft.py:181 kp_head), added here instead of by a separate
+    // elementwise pass over the map; the pooled rows see it through the means
+    const float4 bq = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s8 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q8 = 0; q8 < 4; ++q8) {                      // 4x4 quadrants of the 8x8 block
@@ -126,6 +129,8 @@ corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, __nv_bfloat16* __restrict
 #pragma unroll
         for (int p = 0; p < 4; ++p)
           v[p] = __ldg(reinterpret_cast<const float4*>(qb + ((int64_t)(y2 + (p >> 1)) * w + x2 + (p & 1)) * C + c));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { v[p].x += bq.x; v[p].y += bq.y; v[p].z += bq.z; v[p].w += bq.w; }
 #pragma unroll
         for (int p = 0; p < 4; ++p)
           *reinterpret_cast<uint2*>(ab + ((int64_t)(y2 + (p >> 1)) * w + x2 + (p & 1)) * C + c) = pack_bf16x4(v[p]);
@@ -147,22 +152,34 @@ corr_pack_nhwc_q_kernel(const float* __restrict__ q_d, __nv_bfloat16* __restrict
 
 // Source operand: a plain vectorised cast
 __global__ void __launch_bounds__(256)
-cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = pack_bf16x4(__ldg(x + i));
+cast_bf16_kernel(const float4* __restrict__ x, const float* __restrict__ bias, uint2* __restrict__ y, int64_t n4, int cq) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (bias != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % cq));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    y[i] = pack_bf16x4(v);
+  }
 }
 
 // Source operand for the tiled map layout: the same cast with the pixel rows written in tile order
 // (whole C-channel rows move, so loads and stores stay contiguous 4*C / 2*C-byte runs)
 __global__ void __launch_bounds__(256)
-cast_bf16_tiled_rows_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t pixels, int hw, int w, int cq) {
+cast_bf16_tiled_rows_kernel(const float4* __restrict__ x, const float* __restrict__ bias, uint2* __restrict__ y, int64_t pixels,
+                            int hw, int w, int cq) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels * cq; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i / cq;
     const int c = (int)(i - pix * cq);
     const int64_t b = pix / hw;
     const int p = (int)(pix - b * hw);
     const int py = p / w, px = p - py * w;
-    y[(b * hw + map_offset<true>(0, py, px, w)) * cq + c] = pack_bf16x4(__ldg(x + i));
+    float4 v = __ldg(x + i);
+    if (bias != nullptr) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    }
+    y[(b * hw + map_offset<true>(0, py, px, w)) * cq + c] = pack_bf16x4(v);
   }
 }
 
@@ -1281,9 +1298,24 @@ extern "C" int64_t mrfa_corr_map_offset(int map_layout, int level, int y, int x,
   return map_layout == MRFA_MAP_TILED ? map_offset<true>(level, y, x, W_level) : map_offset<false>(level, y, x, W_level);
 }
 
+static int corr_pack_impl(const float* q_d, const float* q_bias, const float* k_s, const float* k_bias, void* a_op, void* b_op,
+                          int B, int C, int h, int w, int channels_last, mrfa_stream_t stream);
+
 extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, void* b_op, int B, int C, int h, int w,
                               int channels_last, mrfa_stream_t stream) {
+  return corr_pack_impl(q_d, nullptr, k_s, nullptr, a_op, b_op, B, C, h, w, channels_last, stream);
+}
+
+extern "C" int mrfa_corr_pack_bias(const float* q_d, const float* q_bias, const float* k_s, const float* k_bias, void* a_op,
+                                   void* b_op, int B, int C, int h, int w, mrfa_stream_t stream) {
+  if (((reinterpret_cast<uintptr_t>(q_bias) | reinterpret_cast<uintptr_t>(k_bias)) & 15) != 0) return MRFA_E_ALIGN;
+  return corr_pack_impl(q_d, q_bias, k_s, k_bias, a_op, b_op, B, C, h, w, 1, stream);
+}
+
+static int corr_pack_impl(const float* q_d, const float* q_bias, const float* k_s, const float* k_bias, void* a_op, void* b_op,
+                          int B, int C, int h, int w, int channels_last, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(q_d && k_s && a_op && b_op && B >= 0 && C > 0 && h > 0 && w > 0);
+  MRFA_CHECK_ARG(channels_last || (q_bias == nullptr && k_bias == nullptr));
   MRFA_CHECK_SHAPE(C % kPackCh == 0 && h % 8 == 0 && w % 8 == 0 && B <= 65535);
   MRFA_CHECK_SHAPE(w <= 32 || w % 32 == 0);
   if (B == 0) return 0;
@@ -1296,7 +1328,7 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
     int64_t blocks = cdiv64(items, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     corr_pack_nhwc_q_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, as_stream(stream)>>>(
-        q_d, static_cast<__nv_bfloat16*>(a_op), C, h, w, (int)rows_total);
+        q_d, q_bias, static_cast<__nv_bfloat16*>(a_op), C, h, w, (int)rows_total);
     int rc = MRFA_LAUNCH_RESULT();
     if (rc) return rc;
     const int64_t n4 = (int64_t)B * h * w * C / 4;
@@ -1304,10 +1336,10 @@ extern "C" int mrfa_corr_pack(const float* q_d, const float* k_s, void* a_op, vo
     if (cblocks > 148 * 32) cblocks = 148 * 32;
     if (tiled)
       cast_bf16_tiled_rows_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(
-          reinterpret_cast<const float4*>(k_s), static_cast<uint2*>(b_op), (int64_t)B * h * w, h * w, w, C / 4);
+          reinterpret_cast<const float4*>(k_s), k_bias, static_cast<uint2*>(b_op), (int64_t)B * h * w, h * w, w, C / 4);
     else
-      cast_bf16_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(k_s),
-                                                                        static_cast<uint2*>(b_op), n4);
+      cast_bf16_kernel<<<(unsigned)cblocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(k_s), k_bias,
+                                                                        static_cast<uint2*>(b_op), n4, C / 4);
     return MRFA_LAUNCH_RESULT();
   }
   const int tile_w = w < 32 ? w : 32;

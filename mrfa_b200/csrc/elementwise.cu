@@ -114,7 +114,7 @@ __device__ __forceinline__ float4 resize_vblend(const float* r0, const float* r1
 template <int ACT>
 __global__ void __launch_bounds__(256)
 resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
-                            float sy, float sx, int64_t total_runs, IndexSplit sp) {
+                            float sy, float sx, int64_t total_runs, IndexSplit sp, const float* __restrict__ bias) {
   const int cq = C / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_runs; i += (int64_t)gridDim.x * blockDim.x) {
     int c4, run, oy;
@@ -130,6 +130,8 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
     float4* dst = reinterpret_cast<float4*>(y + ((n * Ho + oy) * (int64_t)Wo + run * kResizeRun) * C + c);
     int cx0 = -1, cx1 = -1;
     float4 vl = make_float4(0, 0, 0, 0), vr = vl;      // vertically blended left / right source columns
+    // a per-channel bias commutes with the interpolation (the four weights sum to one): added after it, before the activation
+    const float4 bq = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int j = 0; j < kResizeRun; ++j) {
       const int ox = run * kResizeRun + j;
@@ -146,8 +148,8 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
         cx1 = x1;
       }
       const float hx = 1.f - lx;
-      float4 r = make_float4(fmaf(lx, vr.x, hx * vl.x), fmaf(lx, vr.y, hx * vl.y), fmaf(lx, vr.z, hx * vl.z),
-                             fmaf(lx, vr.w, hx * vl.w));
+      float4 r = make_float4(fmaf(lx, vr.x, hx * vl.x) + bq.x, fmaf(lx, vr.y, hx * vl.y) + bq.y, fmaf(lx, vr.z, hx * vl.z) + bq.z,
+                             fmaf(lx, vr.w, hx * vl.w) + bq.w);
       if (ACT != 0) { r.x = act_fn(r.x, ACT); r.y = act_fn(r.y, ACT); r.z = act_fn(r.z, ACT); r.w = act_fn(r.w, ACT); }
       dst[(int64_t)j * cq] = r;
     }
@@ -157,7 +159,7 @@ resize_bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, 
 // NHWC with any channel count (flows / occlusion maps coming out of channels-last convolutions)
 __global__ void __launch_bounds__(256)
 resize_bilinear_nhwc_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W, int Ho,
-                                   int Wo, float sy, float sx, int64_t total, int act) {
+                                   int Wo, float sy, float sx, int64_t total, int act, const float* __restrict__ bias) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int64_t pix = i / C;
@@ -172,13 +174,13 @@ resize_bilinear_nhwc_scalar_kernel(const float* __restrict__ x, float* __restric
     const float hy = 1.f - ly, hx = 1.f - lx;
     const float v = hy * (hx * __ldg(base + ((int64_t)y0 * W + x0) * C) + lx * __ldg(base + ((int64_t)y0 * W + x1) * C)) +
                     ly * (hx * __ldg(base + ((int64_t)y1 * W + x0) * C) + lx * __ldg(base + ((int64_t)y1 * W + x1) * C));
-    y[i] = act_fn(v, act);
+    y[i] = act_fn(bias != nullptr ? v + __ldg(bias + c) : v, act);
   }
 }
 
 __global__ void __launch_bounds__(256)
 resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int Ho, int Wo, float sy,
-                            float sx, int64_t total, int act) {
+                            float sx, int64_t total, int act, const float* __restrict__ bias, int C) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ox = (int)(i % Wo);
     const int oy = (int)((i / Wo) % Ho);
@@ -191,7 +193,7 @@ resize_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, 
     const float hy = 1.f - ly, hx = 1.f - lx;
     const float v = hy * (hx * __ldg(p + y0 * W + x0) + lx * __ldg(p + y0 * W + x1)) +
                     ly * (hx * __ldg(p + y1 * W + x0) + lx * __ldg(p + y1 * W + x1));
-    y[i] = act_fn(v, act);
+    y[i] = act_fn(bias != nullptr ? v + __ldg(bias + (int)(plane % C)) : v, act);
   }
 }
 
@@ -557,7 +559,7 @@ extern "C" int mrfa_occlusion_blend(const float* a, const float* b, const float*
   return MRFA_LAUNCH_RESULT();
 }
 
-extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int H, int W, int Ho, int Wo,
+extern "C" int mrfa_resize_bilinear(const float* x, const float* bias, float* y, int N, int C, int H, int W, int Ho, int Wo,
                                     int channels_last, int act, mrfa_stream_t stream) {
   MRFA_CHECK_ARG(x && y && N >= 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && act >= 0 && act <= 2);
   if (N == 0) return 0;
@@ -565,22 +567,22 @@ extern "C" int mrfa_resize_bilinear(const float* x, float* y, int N, int C, int 
   const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   const int64_t total = (int64_t)N * C * Ho * Wo;
   if (channels_last && C % 4 == 0 &&
-      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
     const int64_t runs = (int64_t)N * Ho * ((Wo + kResizeRun - 1) / kResizeRun) * (C / 4);
     const IndexSplit sp = make_index_split(C / 4, (Wo + kResizeRun - 1) / kResizeRun, Ho);
     const unsigned g = stream_blocks(runs);
     cudaStream_t st = as_stream(stream);
-    if (act == 0) resize_bilinear_nhwc_kernel<0><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
-    else if (act == 1) resize_bilinear_nhwc_kernel<1><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
-    else resize_bilinear_nhwc_kernel<2><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp);
+    if (act == 0) resize_bilinear_nhwc_kernel<0><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp, bias);
+    else if (act == 1) resize_bilinear_nhwc_kernel<1><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp, bias);
+    else resize_bilinear_nhwc_kernel<2><<<g, 256, 0, st>>>(x, y, C, H, W, Ho, Wo, sy, sx, runs, sp, bias);
   } else if (channels_last) {
     resize_bilinear_nhwc_scalar_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, C, H, W, Ho, Wo, sy, sx,
-                                                                                            total, act);
-  } else if (Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+                                                                                            total, act, bias);
+  } else if (bias == nullptr && Wo % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     resize_bilinear_nchw_v4_kernel<<<stream_blocks(total / 4), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), H, W,
                                                                                            Ho, Wo / 4, sy, sx, total / 4, act, Wo / 4);
   } else {
-    resize_bilinear_nchw_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, H, W, Ho, Wo, sy, sx, total, act);
+    resize_bilinear_nchw_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(x, y, H, W, Ho, Wo, sy, sx, total, act, bias, C);
   }
   return MRFA_LAUNCH_RESULT();
 }

@@ -480,11 +480,18 @@ def corr_map_permutation(layout: int, level: int, H: int, W: int, device) -> Ten
 
 
 @torch.library.custom_op("mrfa::corr_pyramid", mutates_args=(), device_types="cuda")
-def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
-    """(B,C,h,w) x2 -> volume0 (B, rows_total, h*w) bf16, volume1 (B, rows_total, h*w/4) bf16."""
+def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float, q_bias: Optional[Tensor] = None,
+                 k_bias: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """(B,C,h,w) x2 -> volume0 (B, rows_total, h*w) bf16, volume1 (B, rows_total, h*w/4) bf16.
+    q_bias / k_bias (C): per-channel biases added to q_d / k_s while they are packed (channels_last inputs)."""
     (q_d, cl), (k_s, cl2) = _req_image(q_d, "q_d"), _req_image(k_s, "k_s")
     if cl != cl2:
         k_s = _like_layout(k_s, cl)
+    if q_bias is not None or k_bias is not None:
+        if not cl:
+            raise RuntimeError("mrfa_b200: corr_pyramid biases need channels_last q_d / k_s")
+        q_bias = None if q_bias is None else _req(q_bias, "q_bias")
+        k_bias = None if k_bias is None else _req(k_bias, "k_bias")
     B, C, h, w = q_d.shape
     rows = corr_rows_total(h, w)
     dev = q_d.device
@@ -495,7 +502,11 @@ def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor
     with torch.cuda.device(dev):
         st = _stream()
         with _timed("corr_pack", 8 * q_d.numel() + 2 * (a_op.numel() + b_op.numel())):
-            check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, int(cl), st), "mrfa_corr_pack")
+            if q_bias is not None or k_bias is not None:
+                check(lib.mrfa_corr_pack_bias(_p(q_d), _p(q_bias), _p(k_s), _p(k_bias), _p(a_op), _p(b_op), B, C, h, w, st),
+                      "mrfa_corr_pack_bias")
+            else:
+                check(lib.mrfa_corr_pack(_p(q_d), _p(k_s), _p(a_op), _p(b_op), B, C, h, w, int(cl), st), "mrfa_corr_pack")
         # algorithmic FLOPs: the basic-resolution contraction only; bytes: operands + pyramid
         with _timed("corr_volume", 2 * (a_op.numel() + b_op.numel() + vol0.numel() + vol1.numel()),
                     2 * B * (h * w) ** 2 * C):
@@ -505,7 +516,7 @@ def corr_pyramid(q_d: Tensor, k_s: Tensor, scale: float) -> Tuple[Tensor, Tensor
 
 
 @corr_pyramid.register_fake
-def _(q_d, k_s, scale):
+def _(q_d, k_s, scale, q_bias=None, k_bias=None):
     B, C, h, w = q_d.shape
     rows = h * w + (h * w) // 4 + (h * w) // 16 + (h * w) // 64
     return (q_d.new_empty((B, rows, h * w), dtype=torch.bfloat16),
@@ -729,11 +740,15 @@ def _(a, b, occ):
 
 
 @torch.library.custom_op("mrfa::resize_bilinear", mutates_args=(), device_types="cuda")
-def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int) -> Tensor:
-    """F.interpolate(x, (Ho,Wo), mode='bilinear', align_corners=True) + activation (0/1 relu/2 sigmoid).
-    The memory format of `x` (NCHW or channels_last, any C) is preserved."""
+def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int, bias: Optional[Tensor] = None) -> Tensor:
+    """act(F.interpolate(x, (Ho,Wo), mode='bilinear', align_corners=True) + bias[None, :, None, None]) with act 0 / 1 relu /
+    2 sigmoid.  The memory format of `x` (NCHW or channels_last, any C) is preserved."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
         raise RuntimeError("mrfa_b200: resize_bilinear expects a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    if bias is not None:
+        bias = _req(bias, "bias")
+        if bias.numel() != x.shape[1]:
+            raise RuntimeError("mrfa_b200: resize_bilinear bias must have one value per channel")
     cl = _suggest_channels_last(x)
     x = x.contiguous(memory_format=torch.channels_last) if cl else x.contiguous()
     N, C, H, W = x.shape
@@ -742,12 +757,12 @@ def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int) -> Tensor:
         return y
     with torch.cuda.device(x.device):
         with _timed("resize_bilinear", 4 * (x.numel() + y.numel())):
-            check(lib.mrfa_resize_bilinear(_p(x), _p(y), N, C, H, W, Ho, Wo, int(cl), act, _stream()), "mrfa_resize_bilinear")
+            check(lib.mrfa_resize_bilinear(_p(x), _p(bias), _p(y), N, C, H, W, Ho, Wo, int(cl), act, _stream()), "mrfa_resize_bilinear")
     return y
 
 
 @resize_bilinear.register_fake
-def _(x, Ho, Wo, act):
+def _(x, Ho, Wo, act, bias=None):
     y = x.new_empty((x.shape[0], x.shape[1], Ho, Wo))
     return y.contiguous(memory_format=torch.channels_last) if _suggest_channels_last(x) else y
 

@@ -74,8 +74,10 @@ class BasicMotionEncoder(nn.Module):
             # correlation features still at the basic resolution (levels above it, raft.py:241-243):
             # the 1x1 convc1 commutes with the align_corners bilinear resize, so apply it first and
             # let one kernel produce relu(resize(.)) -- the 98-channel upsampled tensor is never built
-            c1 = F.conv2d(corr, self.convc1.weight, self.convc1.bias)
-            c = torch.ops.mrfa.resize_bilinear(c1, delta_flow.shape[-2], delta_flow.shape[-1], 1)
+            # (the bias commutes as well -- the bilinear weights sum to one -- and rides in the same kernel instead of a
+            # separate elementwise pass behind the GEMM)
+            c1 = F.conv2d(corr, self.convc1.weight)
+            c = torch.ops.mrfa.resize_bilinear(c1, delta_flow.shape[-2], delta_flow.shape[-1], 1, self.convc1.bias)
             c = conv_relu(self.convc2, c)
         else:
             c = conv_relu(self.convc2, conv_relu(self.convc1, corr))
@@ -226,14 +228,20 @@ class RaftFlow(nn.Module):
         occlusion = torch.cat([_resize(o, (self.size, self.size)) for o in occs], dim=3)
         return out, warp_img, occlusion
 
-    def structure_features(self, kp_s, kp_d, img):
-        """raft.py:177-182: Gaussian key-point maps (+ positional embedding) -> q_d, k_s."""
+    def structure_features(self, kp_s, kp_d, img, fused_bias: bool = False):
+        """raft.py:177-182: Gaussian key-point maps (+ positional embedding) -> q_d, k_s.
+        fused_bias=True (forward's own call) returns (q_d, k_s, q_bias, k_bias) where, on the channels-last inference
+        path, q_d / k_s are the head outputs WITHOUT their biases and the biases ride into CorrPyramid."""
         h, w = img.shape[2:]
         g_s = torch.ops.mrfa.kp2gaussian(kp_s, self.pos_embedding, h, w, 0.1)
         g_d = torch.ops.mrfa.kp2gaussian(kp_d, self.pos_embedding, h, w, 0.1)
-        k_s = self.kp_img_head(self.kp_img(torch.cat([g_s, img], dim=1)))
-        q_d = self.kp_head(self.kp(g_d))
-        return q_d, k_s
+        f_s, f_d = self.kp_img(torch.cat([g_s, img], dim=1)), self.kp(g_d)
+        if fused_bias and fast_path(self, f_d) and self.channels_last:
+            # inference: the 1x1 heads run as plain GEMMs; their biases are added while CorrPyramid packs the operands
+            # (one fewer read + write of each (B,256,h,w) map)
+            return F.conv2d(f_d, self.kp_head.weight), F.conv2d(f_s, self.kp_img_head.weight), self.kp_head.bias, self.kp_img_head.bias
+        q_d, k_s = self.kp_head(f_d), self.kp_img_head(f_s)
+        return (q_d, k_s, None, None) if fused_bias else (q_d, k_s)
 
     def forward(self, kp_s, kp_d, dense_motion, img, img_full):
         if self.auto_channels_last and not self.channels_last and not self.training and img_full.is_cuda:
@@ -251,8 +259,8 @@ class RaftFlow(nn.Module):
         h, w, base = self.h, self.w, self.basic_res_index
 
         # structure correlation volume + pyramid at the basic resolution (raft.py:177-186, :208)
-        q_d, k_s = self.structure_features(kp_s, kp_d, img)
-        pyramid = CorrPyramid(q_d, k_s, self.scale)
+        q_d, k_s, q_bias, k_bias = self.structure_features(kp_s, kp_d, img, fused_bias=True)
+        pyramid = CorrPyramid(q_d, k_s, self.scale, q_bias, k_bias)
 
         prior = dense_motion["deformation"]
         prior_occ = dense_motion["occlusion"]

@@ -121,6 +121,17 @@ with torch.no_grad():
             ms = timeit(lambda: torch.bmm(a_op, bb))
             report("cublas_bmm_bf16[5440x4096x256 -> bf16]", ms, 2 * (a_op.numel() + b_op.numel() + B * rows * N), 2 * B * N * N * C,
                    note="all driving levels, still without the source-pooled level 1 (0.8x of our output bytes)")
+            # the library route to the SAME output (all driving levels, scaled, plus the 2x2 source-pooled level 1): the scale
+            # folded into the A operand (free), one cuBLAS bf16 GEMM, one avg_pool2d pass over its result
+            a_sc = (a_op.float() * C ** -0.5).to(torch.bfloat16)
+
+            def same_output():
+                c0 = torch.bmm(a_sc, bb)
+                return c0, F.avg_pool2d(c0.view(B * rows, 1, h, w), 2)
+            ms_same = timeit(same_output)
+            report("cublas_bmm_bf16 + avg_pool2d [same output as corr_volume]", ms_same,
+                   2 * (a_op.numel() + b_op.numel() + v0.numel() + v1.numel()) + 2 * v0.numel(), 2 * B * N * N * C,
+                   note="bytes include the re-read of level 0 by the pooling pass; row-major maps (ours are 4x8-tiled)")
         # lookups at the six levels
         for i, R in enumerate([S // 32 * 2 ** j for j in range(6)]):
             Rq = min(R, h)

@@ -706,6 +706,19 @@ def test_corr_channels_last_inputs_and_lookup_output(golden):
         b = ref.block(lvl)(coords, True)
         assert b.is_contiguous(memory_format=torch.channels_last)
         assert torch.equal(a, b.contiguous())
+    # biases of the 1x1 heads added while packing (mrfa_corr_pack_bias) == packing the biased maps
+    torch.manual_seed(31)
+    bq, bk = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    qcl, kcl = q.contiguous(memory_format=torch.channels_last), k.contiguous(memory_format=torch.channels_last)
+    fused = m.CorrPyramid(qcl, kcl, C ** -0.5, bq, bk)
+    plain = m.CorrPyramid((qcl + bq.view(1, -1, 1, 1)).contiguous(memory_format=torch.channels_last),
+                          (kcl + bk.view(1, -1, 1, 1)).contiguous(memory_format=torch.channels_last), C ** -0.5)
+    assert torch.equal(fused.volume0, plain.volume0) and torch.equal(fused.volume1, plain.volume1)
+    only_k = m.CorrPyramid(qcl, kcl, C ** -0.5, None, bk)
+    assert torch.equal(only_k.volume0[:, :h * w],
+                       m.CorrPyramid(qcl, (kcl + bk.view(1, -1, 1, 1)).contiguous(memory_format=torch.channels_last), C ** -0.5).volume0[:, :h * w])
+    with pytest.raises(Exception):
+        m.CorrPyramid(q, k, C ** -0.5, bq, bk)                     # NCHW inputs: no fused bias
 
 
 # ------------------------------------------------------------------ fused elementwise passes
@@ -771,6 +784,8 @@ def test_resize_bilinear(cl):
         assert out.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
         close(out, ref, 2e-6)
         close(torch.ops.mrfa.resize_bilinear(x, size[0], size[1], 1), torch.relu(ref), 2e-6)
+        bias = torch.randn(8, device=DEV)                              # per-channel bias between interpolation and activation
+        close(torch.ops.mrfa.resize_bilinear(x, size[0], size[1], 1, bias), torch.relu(ref + bias.cpu().view(1, -1, 1, 1)), 3e-6)
     flow = torch.randn(2, 2, 9, 9, device=DEV)                        # 2-channel maps keep their layout too
     if cl:
         flow = flow.contiguous(memory_format=torch.channels_last)
