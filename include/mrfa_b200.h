@@ -319,6 +319,14 @@ enum { MRFA_TPS_L1 = 0, MRFA_TPS_L2SQ = 1 };
 int mrfa_random_warp_grid(const float* theta, const float* control_points, const float* control_params, float* grid,
                           int B, int P, int h, int w, int metric, mrfa_stream_t stream);
 
+/* Per-level update of the refinement loop (raft.py:256-262) as one pass:
+ *   flow_w = flow + d_flow[:,0:2];  occ_new = occ + d_flow[:,2:3];  occ_sig = sigmoid(occ_new)
+ * flow, flow_w (B,2,H,W) planar or (channels_last) pixel-interleaved; occ, occ_new, occ_sig (B,1,H,W) dense;
+ * d_flow (B,>=3,H,W) with element strides d_strides {sn, sy, sx, sc}.                                            */
+int mrfa_flow_update(const float* flow, const float* occ, const float* d_flow, mrfa_grid_strides_t d_strides,
+                     float* flow_w, float* occ_new, float* occ_sig, int B, int H, int W, int channels_last,
+                     mrfa_stream_t stream);
+
 /* Flow / occlusion carry to the next, 2x finer refinement level (raft.py:276-295) as one pass:
  *   d_f = 2*up(d_flow[:,0:2]);  flow = d_f + up(init_flow)/scale;  d_o = up(d_flow[:,2]);  occ = d_o + up(prior_occ)
  *   if d_f_pre: up_f = 2*up(d_f_pre), up_o = up(d_occ_pre); flow += up_f; occ += up_o; d_f_acc = d_f + up_f; d_occ_acc = d_o + up_o

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mrfa_subpixel_shuffle_cat": (c_int, [c_void_p, c_void_p, GridStrides, c_void_p] + [c_int] * 5 + [c_void_p]),
     "mrfa_avg_pool2x2_nhwc_bwd": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "mrfa_cat2_nhwc": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_void_p]),
+    "mrfa_flow_update": (c_int, [c_void_p] * 3 + [GridStrides] + [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "mrfa_flow_carry": (c_int, [c_void_p, GridStrides] + [c_void_p] * 8 + [c_int] * 3 + [c_float, c_int, c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4

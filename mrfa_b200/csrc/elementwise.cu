@@ -300,6 +300,34 @@ flow_carry_kernel(const float* __restrict__ d_flow, mrfa_grid_strides_t ds, cons
 }
 
 
+// Per-level flow / occlusion update (raft.py:256-262): flow_w = flow + d_flow[:, 0:2]; occlusion += d_flow[:, 2:3];
+// sigmoid(occlusion) for the decoder -- three strided elementwise passes and a sigmoid in the reference's op order,
+// one thread per pixel here.  flow / flow_w are planar (B,2,R,R) or pixel-interleaved (channels_last).
+__global__ void __launch_bounds__(256)
+flow_update_kernel(const float* __restrict__ flow, const float* __restrict__ occ, const float* __restrict__ d_flow,
+                   mrfa_grid_strides_t ds, float* __restrict__ flow_w, float* __restrict__ occ_new,
+                   float* __restrict__ occ_sig, int64_t total, int cl, IndexSplit sp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int zero, x, y;
+    int64_t n, same;
+    split_index(i, sp, zero, x, y, n, same);
+    const int64_t plane = (int64_t)sp.w.d * sp.h.d, pix = i - n * plane;
+    const float* d = d_flow + n * ds.sn + (int64_t)y * ds.sy + (int64_t)x * ds.sx;
+    const float dx = __ldg(d), dy = __ldg(d + ds.sc), dz = __ldg(d + 2 * ds.sc);
+    if (cl) {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
+      reinterpret_cast<float2*>(flow_w)[i] = make_float2(__fadd_rn(f.x, dx), __fadd_rn(f.y, dy));
+    } else {
+      flow_w[n * 2 * plane + pix] = __fadd_rn(__ldg(flow + n * 2 * plane + pix), dx);
+      flow_w[n * 2 * plane + plane + pix] = __fadd_rn(__ldg(flow + n * 2 * plane + plane + pix), dy);
+    }
+    const float o = __fadd_rn(__ldg(occ + i), dz);
+    occ_new[i] = o;
+    occ_sig[i] = act_fn(o, 2);
+  }
+}
+
+
 // AntiAliasInterpolation2d (util.py:282-326): zero-padded depthwise
 // KxK Gaussian followed by nearest sub-sampling by `stride`.  The reference convolves at full
 // resolution and throws 15/16 of the result away; this evaluates only the kept pixels.
@@ -663,6 +691,18 @@ extern "C" int mrfa_flow_carry(const float* d_flow, mrfa_grid_strides_t d_stride
                                                                          d_occ_pre, flow, occ, d_f_acc, d_occ_acc, R, h,
                                                                          scale, channels_last, s_r, s_h, total,
                                                                          make_index_split(1, Ro, Ro));
+  return MRFA_LAUNCH_RESULT();
+}
+
+extern "C" int mrfa_flow_update(const float* flow, const float* occ, const float* d_flow, mrfa_grid_strides_t d_strides,
+                                float* flow_w, float* occ_new, float* occ_sig, int B, int H, int W, int channels_last,
+                                mrfa_stream_t stream) {
+  MRFA_CHECK_ARG(flow && occ && d_flow && flow_w && occ_new && occ_sig && B >= 0 && H > 0 && W > 0);
+  if (B == 0) return 0;
+  if (channels_last && ((reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(flow_w)) & 7) != 0) return MRFA_E_ALIGN;
+  const int64_t total = (int64_t)B * H * W;
+  flow_update_kernel<<<stream_blocks(total), 256, 0, as_stream(stream)>>>(flow, occ, d_flow, d_strides, flow_w, occ_new, occ_sig,
+                                                                          total, channels_last, make_index_split(1, W, H));
   return MRFA_LAUNCH_RESULT();
 }
 

@@ -40,6 +40,31 @@ __global__ void kp2gaussian_kernel(const float* __restrict__ kp, const float* __
   }
 }
 
+// w % 4 == 0, 16-byte aligned maps: one thread per 4 consecutive pixels of a row (32-bit index arithmetic, the row
+// coordinate and the key-point loaded once, one vector load of `add`, one vector store)
+__global__ void __launch_bounds__(256)
+kp2gaussian_v4_kernel(const float* __restrict__ kp, const float4* __restrict__ add, int add_period, float4* __restrict__ out,
+                      uint32_t total4, uint32_t hw4, uint32_t w4, int h, int w, float variance) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const uint32_t p = i / hw4, r4 = i - p * hw4;
+    const uint32_t y = r4 / w4, x0 = (r4 - y * w4) * 4;
+    const float kx = __ldg(kp + 2 * p), ky = __ldg(kp + 2 * p + 1);
+    const float dy = __fsub_rn(norm_coord((int)y, h), ky);
+    const float dy2 = __fmul_rn(dy, dy);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dx = __fsub_rn(norm_coord((int)x0 + j, w), kx);
+      v[j] = expf(__fdiv_rn(__fmul_rn(-0.5f, __fadd_rn(__fmul_rn(dx, dx), dy2)), variance));
+    }
+    if (add != nullptr) {
+      const float4 a = __ldg(add + (p % (uint32_t)add_period) * hw4 + r4);
+      v[0] = __fadd_rn(v[0], a.x); v[1] = __fadd_rn(v[1], a.y); v[2] = __fadd_rn(v[2], a.z); v[3] = __fadd_rn(v[3], a.w);
+    }
+    out[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 __global__ void prior_to_flow_kernel(const float* __restrict__ deformation, float* __restrict__ flow, int B, int h,
                                      int w, float hm1) {
   const int64_t hw = (int64_t)h * w, total = (int64_t)B * hw;
@@ -81,6 +106,14 @@ extern "C" int mrfa_kp2gaussian(const float* kp, const float* add, int add_perio
   MRFA_CHECK_ARG(kp && out && P >= 0 && h > 0 && w > 0);
   MRFA_CHECK_ARG(add == nullptr || add_period > 0);
   if (P == 0) return 0;
+  const int64_t total = (int64_t)P * h * w;
+  if (w % 4 == 0 && total < ((int64_t)1 << 32) &&
+      ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add)) & 15) == 0) {
+    kp2gaussian_v4_kernel<<<blocks_for(total / 4), 256, 0, as_stream(stream)>>>(
+        kp, reinterpret_cast<const float4*>(add), add_period, reinterpret_cast<float4*>(out), (uint32_t)(total / 4),
+        (uint32_t)(h * w / 4), (uint32_t)(w / 4), h, w, variance);
+    return MRFA_LAUNCH_RESULT();
+  }
   kp2gaussian_kernel<<<blocks_for((int64_t)P * h * w), 256, 0, as_stream(stream)>>>(kp, add, add_period, out, P, h, w, variance);
   return MRFA_LAUNCH_RESULT();
 }

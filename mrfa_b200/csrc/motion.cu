@@ -38,31 +38,29 @@ __device__ __forceinline__ void sample_source(const float* __restrict__ src, flo
   }
 }
 
-// one thread per (b, k, y, x), k in [0, K]; k == 0 is the background channel
+// one thread per (b, k, y, x), k in [0, K]; k == 0 is the background channel.  A block covers 256 pixels of ONE (b, k)
+// (grid.y = b * (K+1) + k): the per-key-point algebra -- J = jac_s * inverse(jac_d) with its four IEEE divisions, the
+// key-point coordinates -- is evaluated once per block into shared memory instead of once per pixel.
+struct PriorKp {
+  float kdx, kdy, ksx, ksy, j00, j01, j10, j11;
+};
+
 __global__ void __launch_bounds__(256)
 dense_motion_prior_kernel(const float* __restrict__ kp_d, const float* __restrict__ kp_s,
                           const float* __restrict__ jac_d, const float* __restrict__ jac_s,
                           const float* __restrict__ bg_param, const float* __restrict__ source,
                           float* __restrict__ motions, float* __restrict__ hg_input,
                           int B, int K, int C, int h, int w, float variance) {
+  __shared__ PriorKp sk;
   const int hw = h * w;
-  const int64_t total = (int64_t)B * (K + 1) * hw;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int r = (int)(i % hw);
-  const int k = (int)((i / hw) % (K + 1));
-  const int b = (int)(i / ((int64_t)hw * (K + 1)));
-  const int y = r / w, x = r - y * w;
-  const float gx = norm_coord(x, w), gy = norm_coord(y, h);
-
-  float heat = 0.f;
-  float2 m;
-  if (k == 0) {
-    m = bg_param ? bg_affine(bg_param + 9 * b, gx, gy) : make_float2(gx, gy);
-  } else {
+  const int bk = blockIdx.y;
+  const int b = bk / (K + 1), k = bk - b * (K + 1);
+  if (threadIdx.x == 0 && k > 0) {
     const int kk = b * K + (k - 1);
-    heat = __fsub_rn(gauss(gx, gy, kp_d + 2 * kk, variance), gauss(gx, gy, kp_s + 2 * kk, variance));
-    float cx = __fsub_rn(gx, __ldg(kp_d + 2 * kk)), cy = __fsub_rn(gy, __ldg(kp_d + 2 * kk + 1));
+    PriorKp p;
+    p.kdx = __ldg(kp_d + 2 * kk); p.kdy = __ldg(kp_d + 2 * kk + 1);
+    p.ksx = __ldg(kp_s + 2 * kk); p.ksy = __ldg(kp_s + 2 * kk + 1);
+    p.j00 = 1.f; p.j01 = 0.f; p.j10 = 0.f; p.j11 = 1.f;
     if (jac_d != nullptr) {
       // J = jac_s * inverse(jac_d)  (dense_motion.py:54)
       const float a = __ldg(jac_d + 4 * kk), bb = __ldg(jac_d + 4 * kk + 1);
@@ -71,18 +69,41 @@ dense_motion_prior_kernel(const float* __restrict__ kp_d, const float* __restric
       const float i00 = __fdiv_rn(d, det), i01 = __fdiv_rn(-bb, det), i10 = __fdiv_rn(-c, det), i11 = __fdiv_rn(a, det);
       const float s00 = __ldg(jac_s + 4 * kk), s01 = __ldg(jac_s + 4 * kk + 1);
       const float s10 = __ldg(jac_s + 4 * kk + 2), s11 = __ldg(jac_s + 4 * kk + 3);
-      const float j00 = __fadd_rn(__fmul_rn(s00, i00), __fmul_rn(s01, i10));
-      const float j01 = __fadd_rn(__fmul_rn(s00, i01), __fmul_rn(s01, i11));
-      const float j10 = __fadd_rn(__fmul_rn(s10, i00), __fmul_rn(s11, i10));
-      const float j11 = __fadd_rn(__fmul_rn(s10, i01), __fmul_rn(s11, i11));
-      const float nx = __fadd_rn(__fmul_rn(j00, cx), __fmul_rn(j01, cy));
-      const float ny = __fadd_rn(__fmul_rn(j10, cx), __fmul_rn(j11, cy));
+      p.j00 = __fadd_rn(__fmul_rn(s00, i00), __fmul_rn(s01, i10));
+      p.j01 = __fadd_rn(__fmul_rn(s00, i01), __fmul_rn(s01, i11));
+      p.j10 = __fadd_rn(__fmul_rn(s10, i00), __fmul_rn(s11, i10));
+      p.j11 = __fadd_rn(__fmul_rn(s10, i01), __fmul_rn(s11, i11));
+    }
+    sk = p;
+  }
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hw) return;
+  const int64_t i = (int64_t)bk * hw + r;
+  const int y = r / w, x = r - y * w;
+  const float gx = norm_coord(x, w), gy = norm_coord(y, h);
+
+  float heat = 0.f;
+  float2 m;
+  if (k == 0) {
+    m = bg_param ? bg_affine(bg_param + 9 * b, gx, gy) : make_float2(gx, gy);
+  } else {
+    const PriorKp p = sk;
+    float cx = __fsub_rn(gx, p.kdx), cy = __fsub_rn(gy, p.kdy);
+    {
+      const float sx = __fsub_rn(gx, p.ksx), sy = __fsub_rn(gy, p.ksy);
+      const float dd = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), ds = __fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
+      heat = __fsub_rn(expf(__fdiv_rn(__fmul_rn(-0.5f, dd), variance)), expf(__fdiv_rn(__fmul_rn(-0.5f, ds), variance)));
+    }
+    if (jac_d != nullptr) {
+      const float nx = __fadd_rn(__fmul_rn(p.j00, cx), __fmul_rn(p.j01, cy));
+      const float ny = __fadd_rn(__fmul_rn(p.j10, cx), __fmul_rn(p.j11, cy));
       cx = nx; cy = ny;
     }
-    m = make_float2(__fadd_rn(cx, __ldg(kp_s + 2 * kk)), __fadd_rn(cy, __ldg(kp_s + 2 * kk + 1)));
+    m = make_float2(__fadd_rn(cx, p.ksx), __fadd_rn(cy, p.ksy));
   }
   reinterpret_cast<float2*>(motions)[i] = m;
-  float* dst = hg_input + ((int64_t)b * (K + 1) + k) * (C + 1) * hw;
+  float* dst = hg_input + (int64_t)bk * (C + 1) * hw;
   dst[r] = heat;
   sample_source<MRFA_COORD_NORM_ACF>(source + (int64_t)b * C * hw, dst + hw, C, h, w, m, r);
 }
@@ -278,8 +299,9 @@ extern "C" int mrfa_dense_motion_prior(const float* kp_d, const float* kp_s, con
   MRFA_CHECK_ARG((jac_d == nullptr) == (jac_s == nullptr));
   MRFA_CHECK_ARG(B >= 0 && K > 0 && C > 0 && h > 1 && w > 1 && variance > 0.f);
   if (B == 0) return 0;
-  const int64_t total = (int64_t)B * (K + 1) * h * w;
-  dense_motion_prior_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(
+  MRFA_CHECK_SHAPE((int64_t)B * (K + 1) <= 65535 && (int64_t)h * w < ((int64_t)1 << 31));
+  const dim3 grid((unsigned)cdiv64((int64_t)h * w, 256), (unsigned)(B * (K + 1)));
+  dense_motion_prior_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       kp_d, kp_s, jac_d, jac_s, bg_param, source, motions, hg_input, B, K, C, h, w, variance);
   return MRFA_LAUNCH_RESULT();
 }

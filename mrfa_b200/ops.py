@@ -955,6 +955,40 @@ def _(theta, control_points, control_params, h, w, metric):
     return theta.new_empty((theta.shape[0], h, w, 2))
 
 
+@torch.library.custom_op("mrfa::flow_update", mutates_args=(), device_types="cuda")
+def flow_update(flow: Tensor, occ: Tensor, d_flow: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """raft.py:256-262 in one kernel: (flow + d_flow[:, 0:2], occ + d_flow[:, 2:3], sigmoid(occ + d_flow[:, 2:3])).
+    flow (B,2,H,W) in either memory format (kept), occ (B,1,H,W), d_flow (B,>=3,H,W) any strides."""
+    for t, name in ((flow, "flow"), (occ, "occ"), (d_flow, "d_flow")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+            raise RuntimeError(f"mrfa_b200: flow_update `{name}` must be a 4-D float32 CUDA tensor (there is no CPU fallback)")
+    B, _, H, W = flow.shape
+    if flow.shape[1] != 2 or tuple(occ.shape) != (B, 1, H, W) or d_flow.shape[1] < 3 or tuple(d_flow.shape[2:]) != (H, W) \
+            or d_flow.shape[0] != B:
+        raise RuntimeError("mrfa_b200: flow_update shape mismatch")
+    cl = _suggest_channels_last(flow)
+    flow = flow.contiguous(memory_format=torch.channels_last) if cl else flow.contiguous()
+    occ = occ.contiguous()
+    flow_w = _empty_image((B, 2, H, W), flow.device, cl)
+    occ_new, occ_sig = torch.empty_like(occ), torch.empty_like(occ)
+    if flow_w.numel() == 0:
+        return flow_w, occ_new, occ_sig
+    st = d_flow.stride()
+    with torch.cuda.device(flow.device):
+        with _timed("flow_update", 4 * 9 * B * H * W):
+            check(lib.mrfa_flow_update(_p(flow), _p(occ), _p(d_flow), GridStrides(st[0], st[2], st[3], st[1]), _p(flow_w),
+                                       _p(occ_new), _p(occ_sig), B, H, W, int(cl), _stream()), "mrfa_flow_update")
+    return flow_w, occ_new, occ_sig
+
+
+@flow_update.register_fake
+def _(flow, occ, d_flow):
+    fw = flow.new_empty(flow.shape)
+    if _suggest_channels_last(flow):
+        fw = fw.contiguous(memory_format=torch.channels_last)
+    return fw, occ.new_empty(occ.shape), occ.new_empty(occ.shape)
+
+
 @torch.library.custom_op("mrfa::flow_carry", mutates_args=(), device_types="cuda")
 def flow_carry(d_flow: Tensor, init_flow: Tensor, prior_occ: Tensor, d_f_pre: Optional[Tensor],
                d_occ_pre: Optional[Tensor], scale: float, channels_last: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

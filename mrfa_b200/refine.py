@@ -233,8 +233,12 @@ class RaftFlow(nn.Module):
         fused_bias=True (forward's own call) returns (q_d, k_s, q_bias, k_bias) where, on the channels-last inference
         path, q_d / k_s are the head outputs WITHOUT their biases and the biases ride into CorrPyramid."""
         h, w = img.shape[2:]
-        g_s = torch.ops.mrfa.kp2gaussian(kp_s, self.pos_embedding, h, w, 0.1)
-        g_d = torch.ops.mrfa.kp2gaussian(kp_d, self.pos_embedding, h, w, 0.1)
+        if kp_s.shape == kp_d.shape and not (torch.is_grad_enabled() and (kp_s.requires_grad or kp_d.requires_grad)):
+            g = torch.ops.mrfa.kp2gaussian(torch.cat([kp_s, kp_d], dim=0), self.pos_embedding, h, w, 0.1)   # one launch for both
+            g_s, g_d = g[:kp_s.shape[0]], g[kp_s.shape[0]:]
+        else:
+            g_s = torch.ops.mrfa.kp2gaussian(kp_s, self.pos_embedding, h, w, 0.1)
+            g_d = torch.ops.mrfa.kp2gaussian(kp_d, self.pos_embedding, h, w, 0.1)
         f_s, f_d = self.kp_img(torch.cat([g_s, img], dim=1)), self.kp(g_d)
         if fused_bias and fast_path(self, f_d) and self.channels_last:
             # inference: the 1x1 heads run as plain GEMMs; their biases are added while CorrPyramid packs the operands
@@ -274,6 +278,7 @@ class RaftFlow(nn.Module):
         out_warp_f, out_occlusion, out_warp_f_c, out_occlusion_c = [], [], [], []
         cat_bufs = [None] * self.total_iter if (CAT_SLICES and fast_path(self, img) and cl) else None
         d_f_pre = d_occ_pre = None
+        fused_small = img.is_cuda and not torch.is_grad_enabled() and FUSED_CARRY
         for i in range(self.total_iter):
             R = self.size // 32 * 2 ** i
             # ---- correlation features at this level (raft.py:217-243) ----
@@ -291,9 +296,13 @@ class RaftFlow(nn.Module):
             m_f = self.corr_enc(flow, corr)
 
             # ---- warps of feature[i]: refined (at flow) and coarse (prior grid) in one pass ----
+            occ_res_sig = None
             if i != base:
                 prior_grid = _resize(prior_nchw, (R, R)).permute(0, 2, 3, 1).contiguous()
-                occ_res = _resize(prior_occ, (R, R))
+                if fused_small:
+                    occ_res, occ_res_sig = None, torch.ops.mrfa.resize_bilinear(prior_occ, R, R, 2)   # sigmoid(resize(.))
+                else:
+                    occ_res = _resize(prior_occ, (R, R))
             else:
                 prior_grid, occ_res = prior, prior_occ
             if cat_bufs is not None and 0 < i < self.num_iter - 1 and feature[i].shape[1] % 4 == 0 \
@@ -307,14 +316,19 @@ class RaftFlow(nn.Module):
             warp_f = conv_relu(self.to_context[i], warp_f)
 
             d_flow, _ = self.refine(m_f, warp_f)
-            flow_w = flow + d_flow[:, 0:2]
-            d_occ = d_flow[:, 2:]
-            occlusion = occlusion + d_occ
+            if fused_small:
+                # raft.py:256-262: both adds and the sigmoid in one pass over the (strided) update
+                flow_w, occlusion, occ_sig = torch.ops.mrfa.flow_update(flow, occlusion, d_flow)
+            else:
+                flow_w = flow + d_flow[:, 0:2]
+                d_occ = d_flow[:, 2:]
+                occlusion = occlusion + d_occ
+                occ_sig = torch.sigmoid(occlusion)
 
             out_warp_f.append(sampling.warp_by_flow(feature[i], flow_w))                     # raft.py:260
-            out_occlusion.append(torch.sigmoid(occlusion))
+            out_occlusion.append(occ_sig)
             out_warp_f_c.append(warp_c)
-            out_occlusion_c.append(torch.sigmoid(occ_res))
+            out_occlusion_c.append(occ_res_sig if occ_res_sig is not None else torch.sigmoid(occ_res))
 
             # ---- carry flow / occlusion to the next resolution (raft.py:276-295) ----
             if i < self.num_iter - 1:

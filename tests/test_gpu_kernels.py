@@ -794,6 +794,25 @@ def test_resize_bilinear(cl):
     close(out, F.interpolate(flow.cpu().contiguous(), size=(18, 18), mode="bilinear", align_corners=True), 2e-6)
 
 
+@pytest.mark.parametrize("cl", [False, True])
+def test_flow_update_matches_reference_ops(cl):
+    """raft.py:256-262: flow + d_flow[:, 0:2], occlusion + d_flow[:, 2:3] and its sigmoid, one kernel vs the torch ops."""
+    torch.manual_seed(23)
+    B, H, W = 3, 9, 12
+    flow = torch.randn(B, 2, H, W, device=DEV) * 4
+    occ = torch.randn(B, 1, H, W, device=DEV)
+    d4 = torch.randn(B, 4, H, W, device=DEV)
+    if cl:
+        flow, d4 = flow.contiguous(memory_format=torch.channels_last), d4.contiguous(memory_format=torch.channels_last)
+    d = d4[:, :3]                                                    # the strided view RefineFlow returns
+    fw, on, osig = torch.ops.mrfa.flow_update(flow, occ, d)
+    assert fw.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
+    assert torch.equal(fw, flow + d[:, 0:2]) and torch.equal(on, occ + d[:, 2:3])
+    close(osig, torch.sigmoid(occ + d[:, 2:3]), 1e-6)
+    with pytest.raises(Exception):
+        torch.ops.mrfa.flow_update(flow, occ, d4[:, :2])
+
+
 def test_resize_strip_matches_cat_of_resizes():
     """raft.py:304-306: the occlusion strip = cat of align_corners resizes along the width, written by one kernel per map."""
     torch.manual_seed(22)
