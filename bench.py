@@ -579,7 +579,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": entry["algorithmic_bytes_per_launch"],
                 "traffic": round(t / per_step) if t else None,
                 "traffic_scope": "average per launch: ncu dram__bytes_read+write summed over this kernel's launches in one step "
-                                 "(B=64, 256x256; profiles/r1_hot_kernels_ncu.md), divided by launches_per_step" if t else None}
+                                 "(B=64, 256x256; profiles/r2_hot_kernels_ncu.md), divided by launches_per_step" if t else None}
         if entry["kernel"] == "corr_volume":
             base.update({"bound": "tensor", "achieved": entry["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": entry["tensor_frac"], "peak_source": pk["source"] + " (sustained bf16)",
