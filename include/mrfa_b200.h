@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 6
+#define MRFA_B200_ABI_VERSION 7
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -132,6 +132,33 @@ int mrfa_tps_motion_prior(const float* kp_d, const float* kp_s, const float* the
                           const float* bg_param, const float* source,
                           float* motions, float* hg_input,
                           int B, int G, int C, int h, int w, float variance, mrfa_stream_t stream);
+
+/* Backward of the prior-motion synthesis (the reference back-propagates dense_motion.py:36-85 / :200-243 and
+ * util.py:59-87, :355-410 through autograd over (B,K,h,w)-sized eager ops; training, train.py:64-70).
+ * All gradient outputs and `workspace` are caller-owned; `workspace` (the number of floats
+ * mrfa_*_bwd_workspace returns), grad_kp_d, grad_kp_s and grad_source must be ZERO on entry (the kernels
+ * accumulate with red.global.add); grad_jac_d / grad_jac_s / grad_bg are overwritten.
+ *   grad_motions (same shape as motions) or NULL; grad_hg (same shape as hg_input);
+ *   grad_bg NULL unless bg_param is given; grad_source NULL when the source needs no gradient.        */
+int64_t mrfa_dense_motion_prior_bwd_workspace(int B, int K);
+int mrfa_dense_motion_prior_bwd(const float* grad_motions, const float* grad_hg, const float* kp_d,
+                                const float* kp_s, const float* jac_d, const float* jac_s,
+                                const float* bg_param, const float* source, float* workspace,
+                                float* grad_kp_d, float* grad_kp_s, float* grad_jac_d, float* grad_jac_s,
+                                float* grad_bg, float* grad_source, int B, int K, int C, int h, int w,
+                                float variance, mrfa_stream_t stream);
+/* d kp of mrfa_kp2gaussian: grad (P,h,w) -> grad_kp (P,2), zero on entry.                      */
+int mrfa_kp2gaussian_bwd(const float* grad, const float* kp, float* grad_kp, int P, int h, int w,
+                         float variance, mrfa_stream_t stream);
+/* mrfa_tps_solve + mrfa_tps_motion_prior together: the motion / heat-map / warp gradients are reduced per (b,g),
+ * then the adjoint of the 8x8 solve (the same fp64 elimination on a new right-hand side; L is symmetric) carries
+ * d theta / d control_params back to the key-points.  theta, control_params: the forward's outputs.   */
+int64_t mrfa_tps_motion_prior_bwd_workspace(int B, int G);
+int mrfa_tps_motion_prior_bwd(const float* grad_motions, const float* grad_hg, const float* kp_d,
+                              const float* kp_s, const float* theta, const float* control_params,
+                              const float* bg_param, const float* source, float* workspace,
+                              float* grad_kp_d, float* grad_kp_s, float* grad_bg, float* grad_source,
+                              int B, int G, int C, int h, int w, float variance, mrfa_stream_t stream);
 
 /* a16 raft.py:189-190: flow[b,c,y,x] = (h-1)*(deformation[b,y,x,c]+1)/2 - (c ? y : x).
  * deformation (B,h,w,2) -> flow (B,2,h,w); `hm1` is self.h - 1 for both axes.                */

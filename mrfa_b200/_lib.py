@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
 TPS_L1, TPS_L2SQ = 0, 1
@@ -35,6 +35,11 @@ SIGNATURES = {
     "mrfa_make_coordinate_grid": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mrfa_kp2gaussian": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "mrfa_dense_motion_prior": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_void_p]),
+    "mrfa_dense_motion_prior_bwd_workspace": (c_int64, [c_int, c_int]),
+    "mrfa_dense_motion_prior_bwd": (c_int, [c_void_p] * 15 + [c_int] * 5 + [c_float, c_void_p]),
+    "mrfa_kp2gaussian_bwd": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_float, c_void_p]),
+    "mrfa_tps_motion_prior_bwd_workspace": (c_int64, [c_int, c_int]),
+    "mrfa_tps_motion_prior_bwd": (c_int, [c_void_p] * 13 + [c_int] * 5 + [c_float, c_void_p]),
     "mrfa_tps_solve": (c_int, [c_void_p] * 4 + [c_int, c_void_p]),
     "mrfa_tps_motion_prior": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_void_p]),
     "mrfa_prior_to_flow": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmrfa_b200.so")
-SOURCES = ("grids.cu", "grid_sample.cu", "motion.cu", "lookup.cu", "corr.cu", "corr_bwd.cu", "conv_small.cu", "elementwise.cu", "capi.cu")
+SOURCES = ("grids.cu", "grid_sample.cu", "motion.cu", "motion_bwd.cu", "lookup.cu", "corr.cu", "corr_bwd.cu", "conv_small.cu", "elementwise.cu", "capi.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

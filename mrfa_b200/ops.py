@@ -330,16 +330,29 @@ def _kp2g_setup(ctx, inputs, output):
     ctx.cfg = (add is not None and tuple(add.shape), h, w, variance)
 
 
+@torch.library.custom_op("mrfa::kp2gaussian_bwd", mutates_args=(), device_types="cuda")
+def kp2gaussian_bwd(grad: Tensor, kp: Tensor, h: int, w: int, variance: float) -> Tensor:
+    """d kp of util.kp2gaussian (util.py:59-87): per heat-map block reduction, one atomic per block and component."""
+    grad, kp = _req(grad, "grad"), _req(kp, "kp")
+    P = kp.numel() // 2
+    gk = torch.zeros_like(kp)
+    with torch.cuda.device(kp.device):
+        with _timed("kp2gaussian_bwd", 4 * (grad.numel() + 2 * kp.numel())):
+            check(lib.mrfa_kp2gaussian_bwd(_p(grad), _p(kp), _p(gk), P, h, w, variance, _stream()), "mrfa_kp2gaussian_bwd")
+    return gk
+
+
+@kp2gaussian_bwd.register_fake
+def _(grad, kp, h, w, variance):
+    return torch.empty_like(kp)
+
+
 def _kp2g_backward(ctx, g):
     (kp,) = ctx.saved_tensors
     add_shape, h, w, variance = ctx.cfg
     gk = ga = None
     if ctx.needs_input_grad[0]:
-        # d/dkp exp(-0.5*|x-kp|^2/var) = gauss * (x-kp)/var ; tiny, recomputed with the grid kernel
-        grid = make_coordinate_grid_cuda(h, w, kp.device)
-        diff = grid.view((1,) * (kp.dim() - 1) + (h, w, 2)) - kp.view(tuple(kp.shape[:-1]) + (1, 1, 2))
-        gauss = torch.exp(-0.5 * (diff ** 2).sum(-1) / variance)
-        gk = ((g * gauss).unsqueeze(-1) * diff / variance).sum(dim=(-3, -2))
+        gk = torch.ops.mrfa.kp2gaussian_bwd(g, kp, h, w, variance)
     if ctx.needs_input_grad[1] and add_shape:
         ga = g.reshape((-1,) + add_shape).sum(0)
     return gk, ga, None, None, None
@@ -405,6 +418,69 @@ def _(kp_d, kp_s, jac_d, jac_s, bg_param, source, variance):
     return source.new_empty((B, K + 1, h, w, 2)), source.new_empty((B, (K + 1) * (C + 1), h, w))
 
 
+@torch.library.custom_op("mrfa::dense_motion_prior_bwd", mutates_args=(), device_types="cuda")
+def dense_motion_prior_bwd(grad_motions: Optional[Tensor], grad_hg: Tensor, kp_d: Tensor, kp_s: Tensor,
+                           jac_d: Optional[Tensor], jac_s: Optional[Tensor], bg_param: Optional[Tensor], source: Tensor,
+                           variance: float, need_source: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Gradients of mrfa::dense_motion_prior w.r.t. (kp_d, kp_s, jac_d, jac_s, bg_param, source); absent ones are
+    empty tensors.  One pass over the (K+1) x h x w plane + a finishing launch (csrc/motion_bwd.cu)."""
+    kp_d, kp_s, source, grad_hg = _req(kp_d, "kp_driving"), _req(kp_s, "kp_source"), _req(source, "source"), _req(grad_hg, "grad_hg")
+    jac_d = None if jac_d is None else _req(jac_d, "jac_driving")
+    jac_s = None if jac_s is None else _req(jac_s, "jac_source")
+    bg_param = None if bg_param is None else _req(bg_param, "bg_param")
+    grad_motions = None if grad_motions is None else _req(grad_motions, "grad_motions")
+    B, K, _ = kp_d.shape
+    _, C, h, w = source.shape
+    dev = source.device
+    ws = torch.zeros(int(lib.mrfa_dense_motion_prior_bwd_workspace(B, K)), device=dev, dtype=torch.float32)
+    g_kd, g_ks = torch.zeros_like(kp_d), torch.zeros_like(kp_s)
+    g_jd = torch.empty_like(jac_d) if jac_d is not None else source.new_empty(0)
+    g_js = torch.empty_like(jac_s) if jac_s is not None else source.new_empty(0)
+    g_bg = torch.empty_like(bg_param) if bg_param is not None else source.new_empty(0)
+    g_src = torch.zeros_like(source) if need_source else source.new_empty(0)
+    with torch.cuda.device(dev):
+        with _timed("dense_motion_prior_bwd", 4 * (grad_hg.numel() + source.numel() * (2 if need_source else 1)
+                                                   + (0 if grad_motions is None else grad_motions.numel())), launches=2):
+            check(lib.mrfa_dense_motion_prior_bwd(_p(grad_motions), _p(grad_hg), _p(kp_d), _p(kp_s), _p(jac_d), _p(jac_s),
+                                                  _p(bg_param), _p(source), _p(ws), _p(g_kd), _p(g_ks),
+                                                  _p(g_jd) if jac_d is not None else None,
+                                                  _p(g_js) if jac_s is not None else None,
+                                                  _p(g_bg) if bg_param is not None else None,
+                                                  _p(g_src) if need_source else None,
+                                                  B, K, C, h, w, variance, _stream()), "mrfa_dense_motion_prior_bwd")
+    return g_kd, g_ks, g_jd, g_js, g_bg, g_src
+
+
+@dense_motion_prior_bwd.register_fake
+def _(grad_motions, grad_hg, kp_d, kp_s, jac_d, jac_s, bg_param, source, variance, need_source):
+    e = source.new_empty(0)
+    return (torch.empty_like(kp_d), torch.empty_like(kp_s), torch.empty_like(jac_d) if jac_d is not None else e,
+            torch.empty_like(jac_s) if jac_s is not None else e, torch.empty_like(bg_param) if bg_param is not None else e,
+            torch.empty_like(source) if need_source else e)
+
+
+def _dmp_setup(ctx, inputs, output):
+    kp_d, kp_s, jac_d, jac_s, bg_param, source, variance = inputs
+    ctx.save_for_backward(kp_d, kp_s, jac_d, jac_s, bg_param, source)
+    ctx.variance = variance
+
+
+def _dmp_backward(ctx, g_motions, g_hg):
+    kp_d, kp_s, jac_d, jac_s, bg_param, source = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    if g_hg is None:
+        g_hg = torch.zeros((source.shape[0], (kp_d.shape[1] + 1) * (source.shape[1] + 1)) + tuple(source.shape[2:]),
+                           device=source.device, dtype=source.dtype)
+    g_kd, g_ks, g_jd, g_js, g_bg, g_src = torch.ops.mrfa.dense_motion_prior_bwd(
+        g_motions, g_hg, kp_d, kp_s, jac_d, jac_s, bg_param, source, ctx.variance, bool(need[5]))
+    return (g_kd if need[0] else None, g_ks if need[1] else None,
+            g_jd if (need[2] and jac_d is not None) else None, g_js if (need[3] and jac_s is not None) else None,
+            g_bg if (need[4] and bg_param is not None) else None, g_src if need[5] else None, None)
+
+
+dense_motion_prior.register_autograd(_dmp_backward, setup_context=_dmp_setup)
+
+
 @torch.library.custom_op("mrfa::tps_solve", mutates_args=(), device_types="cuda")
 def tps_solve(kp_1: Tensor, kp_2: Tensor) -> Tuple[Tensor, Tensor]:
     kp_1, kp_2 = _req(kp_1, "kp_1"), _req(kp_2, "kp_2")
@@ -448,6 +524,82 @@ def _(kp_d, kp_s, theta, control_params, bg_param, source, variance):
     B, G = theta.shape[:2]
     _, C, h, w = source.shape
     return source.new_empty((B, G + 1, h, w, 2)), source.new_empty((B, G * 5 + 1 + (G + 1) * C, h, w))
+
+
+@torch.library.custom_op("mrfa::tps_prior", mutates_args=(), device_types="cuda")
+def tps_prior(kp_d: Tensor, kp_s: Tensor, bg_param: Optional[Tensor], source: Tensor,
+              variance: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """mrfa::tps_solve + mrfa::tps_motion_prior as one differentiable op (dense_motion.py:200-243, util.py:355-410).
+    Returns (motions, hg_input, theta, control_params); the last two are saved for the backward."""
+    B = source.shape[0]
+    theta, params = tps_solve(kp_d.reshape(B, -1, 5, 2), kp_s.reshape(B, -1, 5, 2))
+    motions, hg = tps_motion_prior(kp_d, kp_s, theta, params, bg_param, source, variance)
+    return motions, hg, theta, params
+
+
+@tps_prior.register_fake
+def _(kp_d, kp_s, bg_param, source, variance):
+    B, KP, _ = kp_d.shape
+    G = KP // 5
+    _, C, h, w = source.shape
+    return (source.new_empty((B, G + 1, h, w, 2)), source.new_empty((B, KP + 1 + (G + 1) * C, h, w)),
+            source.new_empty((B, G, 2, 3)), source.new_empty((B, G, 5, 2)))
+
+
+@torch.library.custom_op("mrfa::tps_prior_bwd", mutates_args=(), device_types="cuda")
+def tps_prior_bwd(grad_motions: Optional[Tensor], grad_hg: Tensor, kp_d: Tensor, kp_s: Tensor, theta: Tensor,
+                  control_params: Tensor, bg_param: Optional[Tensor], source: Tensor, variance: float,
+                  need_source: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Gradients of mrfa::tps_prior w.r.t. (kp_d, kp_s, bg_param, source): heat-map, motion and warp gradients
+    reduced per transformation, then the adjoint 8x8 solve in fp64 (csrc/motion_bwd.cu)."""
+    kp_d, kp_s, source, grad_hg = _req(kp_d, "kp_driving"), _req(kp_s, "kp_source"), _req(source, "source"), _req(grad_hg, "grad_hg")
+    theta, control_params = _req(theta, "theta"), _req(control_params, "control_params")
+    bg_param = None if bg_param is None else _req(bg_param, "bg_param")
+    grad_motions = None if grad_motions is None else _req(grad_motions, "grad_motions")
+    B, G = theta.shape[:2]
+    _, C, h, w = source.shape
+    dev = source.device
+    ws = torch.zeros(int(lib.mrfa_tps_motion_prior_bwd_workspace(B, G)), device=dev, dtype=torch.float32)
+    g_kd, g_ks = torch.zeros_like(kp_d), torch.zeros_like(kp_s)
+    g_bg = torch.empty_like(bg_param) if bg_param is not None else source.new_empty(0)
+    g_src = torch.zeros_like(source) if need_source else source.new_empty(0)
+    with torch.cuda.device(dev):
+        with _timed("tps_prior_bwd", 4 * (grad_hg.numel() + source.numel()), launches=3):
+            check(lib.mrfa_tps_motion_prior_bwd(_p(grad_motions), _p(grad_hg), _p(kp_d), _p(kp_s), _p(theta),
+                                                _p(control_params), _p(bg_param), _p(source), _p(ws), _p(g_kd), _p(g_ks),
+                                                _p(g_bg) if bg_param is not None else None,
+                                                _p(g_src) if need_source else None,
+                                                B, G, C, h, w, variance, _stream()), "mrfa_tps_motion_prior_bwd")
+    return g_kd, g_ks, g_bg, g_src
+
+
+@tps_prior_bwd.register_fake
+def _(grad_motions, grad_hg, kp_d, kp_s, theta, control_params, bg_param, source, variance, need_source):
+    e = source.new_empty(0)
+    return (torch.empty_like(kp_d), torch.empty_like(kp_s), torch.empty_like(bg_param) if bg_param is not None else e,
+            torch.empty_like(source) if need_source else e)
+
+
+def _tpsp_setup(ctx, inputs, output):
+    kp_d, kp_s, bg_param, source, variance = inputs
+    ctx.save_for_backward(kp_d, kp_s, bg_param, source, output[2], output[3])
+    ctx.variance = variance
+    ctx.hg_shape = tuple(output[1].shape)
+    ctx.mark_non_differentiable(output[2], output[3])
+
+
+def _tpsp_backward(ctx, g_motions, g_hg, _g_theta, _g_params):
+    kp_d, kp_s, bg_param, source, theta, params = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    if g_hg is None:
+        g_hg = torch.zeros(ctx.hg_shape, device=source.device, dtype=source.dtype)
+    g_kd, g_ks, g_bg, g_src = torch.ops.mrfa.tps_prior_bwd(g_motions, g_hg, kp_d, kp_s, theta, params, bg_param, source,
+                                                           ctx.variance, bool(need[3]))
+    return (g_kd if need[0] else None, g_ks if need[1] else None, g_bg if (need[2] and bg_param is not None) else None,
+            g_src if need[3] else None, None)
+
+
+tps_prior.register_autograd(_tpsp_backward, setup_context=_tpsp_setup)
 
 
 # ------------------------------------------------------------------------------------------

@@ -26,16 +26,6 @@ def _dropout_softmax(X, P):
     return X_exp / (X_exp.sum(dim=1, keepdim=True) + 1e-6)
 
 
-def _needs_grad(*tensors):
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
-
-
-def _affine_bg(ident, bg_param, B):
-    hom = torch.cat([ident, torch.ones_like(ident[..., :1])], dim=-1)
-    hom = torch.matmul(bg_param.view(B, 1, 1, 1, 3, 3), hom.unsqueeze(-1)).squeeze(-1)
-    return hom[..., :2] / hom[..., 2:3]
-
-
 def _combine(motions, weights):
     """deformation = sum_k weights[:,k] * motions[:,k]  (dense_motion.py:132-136, :292-295)."""
     return (motions * weights.unsqueeze(-1)).sum(dim=1)
@@ -78,35 +68,10 @@ class DenseMotionNetwork(nn.Module):
         jd, js = kp_driving.get("jacobian"), kp_source.get("jacobian")
         if jd is None or js is None:
             jd = js = None
-        if _needs_grad(kp_driving["kp"], kp_source["kp"], jd, js, bg_param, source_image):
-            return self._prior_differentiable(source_image, kp_driving["kp"], kp_source["kp"], jd, js, bg_param)
+        # differentiable: mrfa::dense_motion_prior carries an autograd formula whose backward is one fused pass
+        # (csrc/motion_bwd.cu) -- key-points, Jacobians, background affine and the source all receive gradients
         return torch.ops.mrfa.dense_motion_prior(kp_driving["kp"], kp_source["kp"], jd, js, bg_param, source_image,
                                                  float(self.kp_variance))
-
-    def _prior_differentiable(self, source, kp_d, kp_s, jd, js, bg_param):
-        """Training path (dense_motion.py:36-85 composed from differentiable pieces): the heat-maps
-        and the K+1 warps still run on the kernels (mrfa::kp2gaussian, mrfa::grid_sample have
-        autograd formulas); the tiny affine algebra is plain tensor code."""
-        from . import ops
-        B, C, h, w = source.shape
-        K = self.num_kp
-        heat = torch.ops.mrfa.kp2gaussian(kp_d, None, h, w, float(self.kp_variance)) \
-            - torch.ops.mrfa.kp2gaussian(kp_s, None, h, w, float(self.kp_variance))
-        heat = torch.cat([torch.zeros_like(heat[:, :1]), heat], dim=1)
-        ident = ops.make_coordinate_grid_cuda(h, w, source.device).view(1, 1, h, w, 2)
-        local = ident - kp_d.view(B, K, 1, 1, 2)
-        if jd is not None:
-            J = torch.matmul(js, torch.inverse(jd))
-            local = torch.matmul(J.view(B, K, 1, 1, 2, 2), local.unsqueeze(-1)).squeeze(-1)
-        moved = local + kp_s.view(B, K, 1, 1, 2)
-        bg = ident.expand(B, 1, h, w, 2)
-        if bg_param is not None:
-            bg = _affine_bg(bg, bg_param, B)
-        motions = torch.cat([bg, moved], dim=1).contiguous()
-        deformed = torch.ops.mrfa.grid_sample(source, motions.view(B * (K + 1), h, w, 2), _lib.COORD_NORM_ACF,
-                                              _lib.PAD_ZEROS, False, K + 1).view(B, K + 1, C, h, w)
-        hg_input = torch.cat([heat.unsqueeze(2), deformed], dim=2).view(B, (K + 1) * (C + 1), h, w)
-        return motions, hg_input
 
     def create_heatmap_representations(self, source_image, kp_driving, kp_source):
         B, C, h, w = source_image.shape
@@ -166,43 +131,10 @@ class TPSDenseMotionNetwork(nn.Module):
         self.kp_variance = kp_variance
 
     def _prior(self, source_image, kp_driving, kp_source, bg_param):
-        B = source_image.shape[0]
-        kp_1 = kp_driving["kp"].view(B, -1, 5, 2)
-        kp_2 = kp_source["kp"].view(B, -1, 5, 2)
-        if _needs_grad(kp_driving["kp"], kp_source["kp"], bg_param, source_image):
-            return self._prior_differentiable(source_image, kp_driving["kp"], kp_source["kp"], kp_1, kp_2, bg_param)
-        theta, params = torch.ops.mrfa.tps_solve(kp_1, kp_2)
-        return torch.ops.mrfa.tps_motion_prior(kp_driving["kp"], kp_source["kp"], theta, params, bg_param,
-                                               source_image, float(self.kp_variance))
-
-    def _prior_differentiable(self, source, kp_d, kp_s, kp_1, kp_2, bg_param):
-        """Training path (dense_motion.py:200-243, util.py:355-410) from differentiable pieces."""
-        from . import ops
-        B, C, h, w = source.shape
-        G, n = kp_1.shape[1], kp_1.shape[2]
-        heat = torch.ops.mrfa.kp2gaussian(kp_d, None, h, w, float(self.kp_variance)) \
-            - torch.ops.mrfa.kp2gaussian(kp_s, None, h, w, float(self.kp_variance))
-        heat = torch.cat([torch.zeros_like(heat[:, :1]), heat], dim=1)
-        Kmat = torch.norm(kp_1[:, :, :, None] - kp_1[:, :, None, :], dim=4, p=2) ** 2
-        Kmat = Kmat * torch.log(Kmat + 1e-9)
-        kp1p = torch.cat([kp_1, torch.ones_like(kp_1[..., :1])], 3)
-        L = torch.cat([torch.cat([Kmat, kp1p.permute(0, 1, 3, 2)], 2),
-                       torch.cat([kp1p, torch.zeros(B, G, 3, 3, device=source.device)], 2)], 3)
-        L = L + torch.eye(n + 3, device=source.device).expand(L.shape) * 0.01
-        param = torch.linalg.solve(L, torch.cat([kp_2, torch.zeros(B, G, 3, 2, device=source.device)], 2))
-        theta, weights = param[:, :, n:, :].permute(0, 1, 3, 2), param[:, :, :n, :]
-        pts = ops.make_coordinate_grid_cuda(h, w, source.device).view(1, h * w, 2)
-        aff = torch.matmul(theta[..., :2], pts.permute(0, 2, 1)) + theta[..., 2:]
-        d2 = ((pts.view(1, 1, 1, -1, 2) - kp_1.view(B, G, -1, 1, 2)) ** 2).sum(-1)
-        rbf = torch.matmul((d2 * torch.log(d2 + 1e-9)).permute(0, 1, 3, 2), weights)
-        moved = (aff.permute(0, 1, 3, 2) + rbf).view(B, G, h, w, 2)
-        bg = pts.view(1, 1, h, w, 2).expand(B, 1, h, w, 2)
-        if bg_param is not None:
-            bg = _affine_bg(bg, bg_param, B)
-        motions = torch.cat([bg, moved], dim=1).contiguous()
-        deformed = torch.ops.mrfa.grid_sample(source, motions.view(B * (G + 1), h, w, 2), _lib.COORD_NORM_ACT,
-                                              _lib.PAD_ZEROS, False, G + 1).view(B, G + 1, C, h, w)
-        hg_input = torch.cat([heat, deformed.reshape(B, -1, h, w)], dim=1)
+        # solve + synthesis as one op; its backward reduces the motion / heat-map / warp gradients per transformation
+        # and runs the adjoint 8x8 solve in fp64 (csrc/motion_bwd.cu)
+        motions, hg_input, _, _ = torch.ops.mrfa.tps_prior(kp_driving["kp"], kp_source["kp"], bg_param, source_image,
+                                                           float(self.kp_variance))
         return motions, hg_input
 
     def create_heatmap_representations(self, source_image, kp_driving, kp_source):

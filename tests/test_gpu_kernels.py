@@ -574,6 +574,150 @@ def test_tps_kernels(golden):
     close(tps.transform_frame(small), O.tps_transformations(d["tps_kp_d"], d["tps_kp_s"], 16, 16)[:, 1:], 2e-5)
 
 
+def _grad_close(got, ref, rel=2e-4):
+    """Gradients that are sums over the h*w plane: |got - ref| <= rel * max|ref| (fp32 summation-order noise)."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    scale = float(ref.abs().max()) + 1e-12
+    err = float((got - ref).abs().max())
+    assert err <= rel * scale, f"max |err| {err:.3e} vs scale {scale:.3e}"
+
+
+def _leaf(t):
+    return t.detach().clone().requires_grad_(True)
+
+
+@pytest.mark.parametrize("use_jac,use_bg,src_grad", [(True, True, True), (False, False, True), (True, False, False),
+                                                     (False, True, False)])
+def test_dense_motion_prior_backward(use_jac, use_bg, src_grad):
+    """Fused backward of the FOMM / MTIA prior synthesis (csrc/motion_bwd.cu) against CPU autograd through the oracle's
+    restatement of dense_motion.py:36-85 (heat-maps, sparse motions, deformed sources), non-square map."""
+    import synthetic_inputs as syn
+    mb()
+    B, K, C, h, w = 3, 10, 3, 24, 20
+    g = torch.Generator().manual_seed(11)
+    kp_s0, kp_d0 = syn.keypoints(B, K, seed=4)
+    bg0 = syn.bg_affine(B, seed=4)
+    src0 = torch.rand(B, C, h, w, generator=g)
+    w_hg = torch.randn(B, (K + 1) * (C + 1), h, w, generator=g)
+    w_mo = torch.randn(B, K + 1, h, w, 2, generator=g)
+
+    def run(dev):
+        t = {"kd": _leaf(kp_d0["kp"].to(dev)), "ks": _leaf(kp_s0["kp"].to(dev)), "src": src0.detach().clone().to(dev).requires_grad_(src_grad)}
+        if use_jac:
+            t["jd"], t["js"] = _leaf(kp_d0["jacobian"].to(dev)), _leaf(kp_s0["jacobian"].to(dev))
+        if use_bg:
+            t["bg"] = _leaf(bg0.to(dev))
+        if dev == "cpu":
+            kd = {"kp": t["kd"]}
+            ks = {"kp": t["ks"]}
+            if use_jac:
+                kd["jacobian"], ks["jacobian"] = t["jd"], t["js"]
+            heat = TP.kp2gaussian(t["kd"], (h, w), 0.01) - TP.kp2gaussian(t["ks"], (h, w), 0.01)
+            heat = torch.cat([torch.zeros_like(heat[:, :1]), heat], dim=1).unsqueeze(2)
+            motions = TP.DenseMotionOracle.sparse_motions(None, h, w, kd, ks, t.get("bg"))
+            rep = t["src"][:, None].expand(B, K + 1, -1, h, w).reshape(B * (K + 1), -1, h, w)
+            deformed = F.grid_sample(rep, motions.view(B * (K + 1), h, w, 2), align_corners=False).view(B, K + 1, -1, h, w)
+            hg = torch.cat([heat, deformed], dim=2).view(B, -1, h, w)
+        else:
+            motions, hg = torch.ops.mrfa.dense_motion_prior(t["kd"], t["ks"], t.get("jd"), t.get("js"), t.get("bg"), t["src"], 0.01)
+        ((hg * w_hg.to(dev)).sum() + (motions * w_mo.to(dev)).sum()).backward()
+        return t, motions, hg
+
+    ref, mo_r, hg_r = run("cpu")
+    got, mo_g, hg_g = run(DEV)
+    close(mo_g, mo_r, 2e-5)
+    close(hg_g, hg_r, 2e-5)
+    for k in ref:
+        if ref[k].grad is None:
+            assert got[k].grad is None
+            continue
+        _grad_close(got[k].grad, ref[k].grad)
+
+
+@pytest.mark.parametrize("use_bg,src_grad", [(True, True), (False, False)])
+def test_tps_prior_backward(use_bg, src_grad):
+    """Fused backward of the thin-plate-spline prior (motion / heat-map / warp gradients + adjoint 8x8 solve in fp64)
+    against fp64 CPU autograd through the oracle's restatement of dense_motion.py:200-243 / util.py:355-410."""
+    import synthetic_inputs as syn
+    mb()
+    B, G, C, h, w = 2, 10, 3, 20, 24
+    g = torch.Generator().manual_seed(12)
+    kd0 = (torch.rand(B, G * 5, 2, generator=g) * 1.6 - 0.8)
+    ks0 = kd0 + 0.05 * torch.randn(B, G * 5, 2, generator=g)
+    bg0 = syn.bg_affine(B, seed=5)
+    src0 = torch.rand(B, C, h, w, generator=g)
+    w_hg = torch.randn(B, G * 5 + 1 + (G + 1) * C, h, w, generator=g)
+    w_mo = torch.randn(B, G + 1, h, w, 2, generator=g)
+
+    # fp64 reference: the reference formula evaluated in double (its own fp32 inverse carries ~1e-4 of round-off into
+    # these gradients; the kernel solves in fp64)
+    dt = torch.float64
+    kd, ks = _leaf(kd0.to(dt)), _leaf(ks0.to(dt))
+    bg = _leaf(bg0.to(dt)) if use_bg else None
+    src = src0.to(dt).requires_grad_(src_grad)
+    grid = TP.make_coordinate_grid((h, w), dtype=dt)
+    diff_d = grid.view(1, 1, h, w, 2) - kd.view(B, -1, 1, 1, 2)
+    diff_s = grid.view(1, 1, h, w, 2) - ks.view(B, -1, 1, 1, 2)
+    heat = torch.exp(-0.5 * (diff_d ** 2).sum(-1) / 0.01) - torch.exp(-0.5 * (diff_s ** 2).sum(-1) / 0.01)
+    heat = torch.cat([torch.zeros_like(heat[:, :1]), heat], dim=1)
+    kp_1, kp_2 = kd.view(B, G, 5, 2), ks.view(B, G, 5, 2)
+    Kmat = torch.norm(kp_1[:, :, :, None] - kp_1[:, :, None, :], dim=4, p=2) ** 2
+    Kmat = Kmat * torch.log(Kmat + 1e-9)
+    kp1p = torch.cat([kp_1, torch.ones(B, G, 5, 1, dtype=dt)], 3)
+    L = torch.cat([torch.cat([Kmat, kp1p.permute(0, 1, 3, 2)], 2), torch.cat([kp1p, torch.zeros(B, G, 3, 3, dtype=dt)], 2)], 3)
+    L = L + torch.eye(8, dtype=dt).expand(L.shape) * float(np.float32(0.01))
+    param = torch.matmul(torch.inverse(L), torch.cat([kp_2, torch.zeros(B, G, 3, 2, dtype=dt)], 2))
+    theta, weights = param[:, :, 5:, :].permute(0, 1, 3, 2), param[:, :, :5, :]
+    pts = grid.view(1, h * w, 2)
+    aff = torch.matmul(theta[..., :2], pts.permute(0, 2, 1)) + theta[..., 2:]
+    d2 = ((pts.view(1, 1, 1, -1, 2) - kp_1.view(B, G, -1, 1, 2)) ** 2).sum(-1)
+    rbf = torch.matmul((d2 * torch.log(d2 + 1e-9)).permute(0, 1, 3, 2), weights)
+    moved = (aff.permute(0, 1, 3, 2) + rbf).view(B, G, h, w, 2)
+    bgm = grid.view(1, 1, h, w, 2).repeat(B, 1, 1, 1, 1)
+    if use_bg:
+        hom = torch.cat([bgm, torch.ones_like(bgm[..., :1])], dim=-1)
+        hom = torch.matmul(bg.view(B, 1, 1, 1, 3, 3), hom.unsqueeze(-1)).squeeze(-1)
+        bgm = hom[..., :2] / hom[..., 2:3]
+    motions = torch.cat([bgm, moved], dim=1)
+    rep = src[:, None].expand(B, G + 1, -1, h, w).reshape(B * (G + 1), -1, h, w)
+    deformed = F.grid_sample(rep, motions.view(B * (G + 1), h, w, 2), align_corners=True).view(B, G + 1, -1, h, w)
+    hg = torch.cat([heat, deformed.reshape(B, -1, h, w)], dim=1)
+    ((hg * w_hg.to(dt)).sum() + (motions * w_mo.to(dt)).sum()).backward()
+
+    kd_g, ks_g = _leaf(kd0.to(DEV)), _leaf(ks0.to(DEV))
+    bg_g = _leaf(bg0.to(DEV)) if use_bg else None
+    src_g = src0.to(DEV).requires_grad_(src_grad)
+    mo_g, hg_g, _, _ = torch.ops.mrfa.tps_prior(kd_g, ks_g, bg_g, src_g, 0.01)
+    ((hg_g * w_hg.to(DEV)).sum() + (mo_g * w_mo.to(DEV)).sum()).backward()
+    close(mo_g, motions, 1e-4)
+    close(hg_g, hg, 2e-4)
+    # the bilinear-sample derivative is piecewise constant in the position: an fp32 position that rounds across a pixel
+    # boundary flips one tap pair, so the warp part of the key-point gradients carries ~1e-3 of the fp32 forward's noise
+    _grad_close(kd_g.grad, kd.grad, 2e-3)
+    _grad_close(ks_g.grad, ks.grad, 2e-3)
+    if use_bg:
+        _grad_close(bg_g.grad, bg.grad, 2e-3)
+    if src_grad:
+        _grad_close(src_g.grad, src.grad, 2e-3)
+    else:
+        assert src_g.grad is None
+
+
+def test_kp2gaussian_backward():
+    """d kp of util.kp2gaussian through the reduction kernel, and the pos_embedding gradient (raft.py:177-178)."""
+    mb()
+    g = torch.Generator().manual_seed(13)
+    kp0 = torch.rand(4, 10, 2, generator=g) * 1.6 - 0.8
+    add0 = 0.02 * torch.randn(1, 10, 12, 18, generator=g)
+    wgt = torch.randn(4, 10, 12, 18, generator=g)
+    kp, add = _leaf(kp0), _leaf(add0)
+    ((TP.kp2gaussian(kp, (12, 18), 0.1) + add) * wgt).sum().backward()
+    kp_g, add_g = _leaf(kp0.to(DEV)), _leaf(add0.to(DEV))
+    (torch.ops.mrfa.kp2gaussian(kp_g, add_g, 12, 18, 0.1) * wgt.to(DEV)).sum().backward()
+    _grad_close(kp_g.grad, kp.grad)
+    _grad_close(add_g.grad, add.grad)
+
+
 def test_dense_motion_networks_forward(golden):
     import synthetic_inputs as syn
     m, d = mb(), golden("prior_motion")
