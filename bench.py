@@ -331,13 +331,21 @@ def train_step_bench(world, rank, local, dev, batch, size, steps, warm):
     model.decoder.channels_last_()
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)                     # train.py:43
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)   # train.py:45-48
+        # train.py:45-48 passes find_unused_parameters=True; static_graph lets the reducer record the (fixed) set of unused
+        # parameters once instead of walking the autograd graph every step, gradient_as_bucket_view drops the bucket copy
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                          static_graph=True, gradient_as_bucket_view=True)
     opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.5, 0.999))
     src, drv = (t.to(dev) for t in syn.frame_pairs(batch, size, seed=rank))
-    kp_s, kp_d = ({k: v.to(dev) for k, v in d.items()} for d in syn.keypoints(batch, 10, seed=rank))
+    # the key-points carry gradients like the jointly trained detector's outputs do (model.py:196-201): the backward runs
+    # through the fused prior-motion / heat-map backward kernels
+    kp_s, kp_d = ({k: v.to(dev).requires_grad_(True) for k, v in d.items()} for d in syn.keypoints(batch, 10, seed=rank))
 
     def step():
         opt.zero_grad(set_to_none=True)
+        for d in (kp_s, kp_d):
+            for v in d.values():
+                v.grad = None
         loss = (model(src, kp_s, kp_d) - drv).abs().mean()
         loss.backward()
         opt.step()
@@ -563,6 +571,7 @@ def run_ours(args):
                 e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
         klist.append(e)
     ours_ms = sum(k["total_ms"] for k in kernels.values())
+    hot_ms = sum(k["total_ms"] for k in hot_kernels.values())
     # roofline: the dominant kernel of the hot path proper; the kernels of the
     # "next" rows 8(f) (fused elementwise helpers, small-channel convolution, cat) are listed in kernels[] only
     hot = [k for k in klist if k["kernel"] in HOT_PATH]
@@ -603,6 +612,13 @@ def run_ours(args):
             "kernels_note": "hot-path rows (SURVEY 8a) are timed inside the timed region; the other rows come from a "
                             f"second, fully instrumented pass of the same {args.steps} steps ({instrumented_ms / args.steps:.2f} ms/step)",
             "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
+            # two throughput tiers -- the SURVEY 8(a) kernels alone (K1-K9: correlation pack + volume, lookups,
+            # feature warps, prior-motion synthesis, grids), summed from the CUDA events of the timed region on rank 0 and
+            # scaled by the world size, and the end-to-end refinement forward (`value`, cuDNN convolutions included)
+            "tiers": {"hot_path_only": {"ms_per_step": round(hot_ms / args.steps, 4),
+                                        "pairs_per_s": round(B * world / (hot_ms / args.steps) * 1e3, 1) if hot_ms > 0 else None,
+                                        "kernels": sorted(hot_kernels)},
+                      "refinement_forward": {"ms_per_step": round(step_ms, 4), "pairs_per_s": round(pairs / (dev_ms / 1e3), 1)}},
             "recon_l1_mean": recon_l1_mean, "peaks": pk}
     if others is not None:
         line["other_configs"] = others

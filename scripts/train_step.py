@@ -61,16 +61,20 @@ if not a.nchw:
     model.decoder.channels_last_()
 if world > 1:
     model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-    model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                      static_graph=True, gradient_as_bucket_view=True)
 opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.5, 0.999))
 src, drv = (t.to(dev) for t in syn.frame_pairs(a.batch, a.size, seed=rank))
 kp_s, kp_d = syn.keypoints(a.batch, 10, seed=rank)
-kp_s = {k: v.to(dev) for k, v in kp_s.items()}
-kp_d = {k: v.to(dev) for k, v in kp_d.items()}
+kp_s = {k: v.to(dev).requires_grad_(True) for k, v in kp_s.items()}     # live key-point gradients (model.py:196-201)
+kp_d = {k: v.to(dev).requires_grad_(True) for k, v in kp_d.items()}
 
 
 def step():
     opt.zero_grad(set_to_none=True)
+    for d in (kp_s, kp_d):
+        for v in d.values():
+            v.grad = None
     out = model(src, kp_s, kp_d)
     loss = (out - drv).abs().mean()
     loss.backward()
