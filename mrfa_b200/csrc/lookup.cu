@@ -205,57 +205,90 @@ struct LookupSmem {
   alignas(16) float outs[kQPB * kOut];
   alignas(16) uint32_t patch[kQPB * kPatchStride];                 // per query: [level][row 0..7][8 words = tile columns tx, tx+1 as loaded]
   float frac[2][kQPB * kFracStride];
-  alignas(16) int org[2][kQPB][4];                     // footprint origin (x0, y0) per level
+  // per (query, level): {element offset of tile column tx0 / tx0 + 1 inside a tile row (-1: not needed or outside the
+  // map), footprint origin y0, footprint origin x0}; dead queries carry y0 = -2^20 so every row fails the range test
+  alignas(16) int4 org[2][kQPB][2];
 };
+
+// x / d for the launch-constant divisor d = size - 1 with rcp = RN(1 / d): q0 = RN(x * rcp), r = x - q0 * d (exact in
+// one FMA), q = RN(q0 + r * rcp) is the correctly rounded quotient (Markstein) -- the same bits as __fdiv_rn for every
+// finite x that is not denormal-small (those end as -1 + tiny either way) without the reciprocal refinement and the
+// slow-path check of the IEEE division sequence; non-finite x gives NaN instead of inf, both rejected by the |p| < 1e8
+// test below.  (Checked against the correctly rounded quotient on 1.1e8 coordinates x divisors on the host.)
+__device__ __forceinline__ float div_by_const(float x, float d, float rcp) {
+  const float q0 = __fmul_rn(x, rcp);
+  const float r = __fmaf_rn(-q0, d, x);
+  return __fmaf_rn(r, rcp, q0);
+}
+// to_pixel<MRFA_COORD_PIXEL> with the division above
+__device__ __forceinline__ float to_pixel_pix(float g, float size_m1, float rcp) {
+  g = __fsub_rn(div_by_const(__fmul_rn(2.f, g), size_m1, rcp), 1.f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), size_m1);
+}
 
 template <int R>
 __device__ __forceinline__ void lookup_geometry(LookupSmem<R>& sm, int buf, const float* __restrict__ coords, int b, int q0,
                                                 int Q, int H, int W) {
-  constexpr int n = 2 * R + 1;
+  constexpr int n = 2 * R + 1, F = n + 1;
   const int t = threadIdx.x;                         // 128 threads = 32 queries x 2 levels x 2 axes
   const int qi = t >> 2, lvl = (t >> 1) & 1, axis = t & 1;
   const int q = q0 + qi;
-  if (q >= Q) return;
+  int* o = reinterpret_cast<int*>(&sm.org[buf][qi][lvl]);
+  if (q >= Q) {
+    if (axis) o[2] = -(1 << 20); else { o[0] = -1; o[1] = -1; o[3] = 0; }
+    return;
+  }
   const float c = __ldg(coords + ((int64_t)b * 2 + axis) * Q + q);
   const int size = (axis ? H : W) >> lvl;
+  const float sm1 = (float)(size - 1), rcp = __frcp_rn(sm1);
   const float cs = __fmul_rn(c, lvl ? 0.5f : 1.f);   // coords / 2**lvl (raft.py:34), exact
-  const float pc = to_pixel<MRFA_COORD_PIXEL>(cs, size);
+  float* f = sm.frac[buf] + qi * kFracStride + (lvl * 2 + axis) * 7;
+  float pa[n];
+#pragma unroll
+  for (int a = 0; a < n; ++a) pa[a] = to_pixel_pix(__fadd_rn(cs, (float)(a - R)), sm1, rcp);
+  const float pc = pa[R];                            // tap R adds 0: the window centre itself
   const bool fin = fabsf(pc) < 1e8f;
   const int base = fin ? (int)floorf(pc) - R : -(1 << 20);
-  sm.org[buf][qi][2 * lvl + axis] = base;
-  float* f = sm.frac[buf] + qi * kFracStride + (lvl * 2 + axis) * 7;
 #pragma unroll
-  for (int a = 0; a < n; ++a) {
-    const float pa = to_pixel<MRFA_COORD_PIXEL>(__fadd_rn(cs, (float)(a - R)), size);
-    f[a] = fin ? pa - (float)(base + a) : 0.f;
+  for (int a = 0; a < n; ++a) f[a] = fin ? pa[a] - (float)(base + a) : 0.f;
+  if (axis) {
+    o[2] = base;
+  } else {
+    // tile columns tx0 = floor(x0 / 8) and tx0 + 1 (the second only when the footprint crosses an 8-column boundary):
+    // element offset of the tile inside its tile row (include/mrfa_b200.h "Map layouts": level 0 in 2 x 2 super-tiles)
+    const int tiles_w = size >> 3, tx0 = base >> 3;   // arithmetic shift: floor for negative origins
+    const bool two = (base & 7) + F > 8;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int tx = tx0 + half;
+      const bool ok = ((unsigned)tx < (unsigned)tiles_w) & ((half == 0) | two);
+      o[half] = ok ? (lvl ? tx << 5 : ((tx >> 1) << 7) + ((tx & 1) << 5)) : -1;
+    }
+    o[3] = base;
   }
 }
 
 template <int R>
 __device__ __forceinline__ void lookup_issue_loads(const LookupSmem<R>& sm, int buf, uint4 (&v)[kGroupT],
                                                    const __nv_bfloat16* __restrict__ level0,
-                                                   const __nv_bfloat16* __restrict__ level1, int b, int q0, int Q, int H,
+                                                   const __nv_bfloat16* __restrict__ level1, int b, int q0, int H,
                                                    int W, int64_t map_batch_stride, int64_t row_offset) {
   constexpr int F = 2 * R + 2;
   constexpr int kWarps = kLookupThreads / 32;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int lvl = lane >> 4, r = (lane >> 1) & 7, half = lane & 1;
-  const int Hl = H >> lvl, tiles_w = (W >> lvl) >> 3;
-  const int map_elems = Hl * (W >> lvl);
+  const int Hl = (r < F) ? (H >> lvl) : 0, tiles_w = (W >> lvl) >> 3;       // footprint rows past F never load
+  const int map_elems = (H >> lvl) * (W >> lvl);
+  // tile-row pitch and row-in-tile terms of the map offset: level 0 rows of 16 x 8-pixel super-tiles, level 1 rows of tiles
+  const int shift = lvl ? 2 : 3, pitch = lvl ? tiles_w << 5 : tiles_w << 6, mid = lvl ? 0 : 64;
   // map of query (b, q0 + warp) on this lane's level; the other queries of the warp are 4 maps apart
   const __nv_bfloat16* base = (lvl ? level1 : level0) + ((int64_t)b * map_batch_stride + row_offset + q0 + warp) * map_elems;
 #pragma unroll
   for (int g = 0; g < kGroupT; ++g) {
-    const int qi = warp + g * kWarps;
-    const int2 o = *reinterpret_cast<const int2*>(&sm.org[buf][qi][2 * lvl]);
-    const int y = o.y + r, tx = (o.x >> 3) + half;          // arithmetic shift: floor for negative origins
-    // the second tile column is only needed when the footprint crosses an 8-column boundary
-    const bool ok = (q0 + qi < Q) & (r < F) & ((unsigned)y < (unsigned)Hl) & ((unsigned)tx < (unsigned)tiles_w) &
-                    ((half == 0) | ((o.x & 7) + F > 8));
-    // tile index inside the map (include/mrfa_b200.h "Map layouts"): level 0 in 2 x 2 super-tiles, level 1 plain
-    const int t0 = (((y >> 3) * (tiles_w >> 1) + (tx >> 1)) << 2) + (((y >> 2) & 1) << 1) + (tx & 1);
-    const int t1 = (y >> 2) * tiles_w + tx;
-    const int off = ((lvl ? t1 : t0) << 5) + ((y & 3) << 3) + g * (kWarps * map_elems);
+    const int4 o = sm.org[buf][warp + g * kWarps][lvl];
+    const int y = o.z + r, xo = half ? o.y : o.x;
+    const bool ok = ((unsigned)y < (unsigned)Hl) & (xo >= 0);
+    const int off = (y >> shift) * pitch + (((y >> 2) & 1) ? mid : 0) + ((y & 3) << 3) + xo + g * (kWarps * map_elems);
     v[g] = make_uint4(0u, 0u, 0u, 0u);
     if (ok) v[g] = __ldg(reinterpret_cast<const uint4*>(base + off));
   }
@@ -274,21 +307,22 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
   __shared__ LookupSmem<R> sm;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // groups of 32 queries, numbered sample-major; (b, gi) advance by the grid size without 64-bit divisions
   const int groups_per_b = (Q + kQPB - 1) / kQPB;
-  const int64_t total = (int64_t)B * groups_per_b;
-  int64_t grp = blockIdx.x;
+  const int total = B * groups_per_b;                        // < 2^31 (checked by the launcher)
+  int grp = blockIdx.x;
   if (grp >= total) return;
+  const int step_b = gridDim.x / groups_per_b, step_g = gridDim.x - step_b * groups_per_b;
+  int b = grp / groups_per_b, gi = grp - b * groups_per_b;
 
   uint4 v[kGroupT];
   int buf = 0;
-  {
-    const int b = (int)(grp / groups_per_b), q0 = (int)(grp - (int64_t)b * groups_per_b) * kQPB;
-    lookup_geometry<R>(sm, 0, coords, b, q0, Q, H, W);
-    __syncthreads();
-    lookup_issue_loads<R>(sm, 0, v, level0, level1, b, q0, Q, H, W, map_batch_stride, row_offset);
-  }
+  lookup_geometry<R>(sm, 0, coords, b, gi * kQPB, Q, H, W);
+  __syncthreads();
+  lookup_issue_loads<R>(sm, 0, v, level0, level1, b, gi * kQPB, H, W, map_batch_stride, row_offset);
   for (; grp < total; grp += gridDim.x, buf ^= 1) {
-    const int b = (int)(grp / groups_per_b), q0 = (int)(grp - (int64_t)b * groups_per_b) * kQPB;
+    const int q0 = gi * kQPB;
+    const int cur_b = b;
     // ---- park the gathered tile rows as loaded (packed bf16): word (level*64 + row*8 + half*4 + i) == lane*4 + i
 #pragma unroll
     for (int g = 0; g < kGroupT; ++g) {
@@ -303,11 +337,12 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
       }
     }
     // ---- geometry + loads of the next group: in flight while this group is evaluated and written
-    const int64_t nxt = grp + gridDim.x;
-    const int nb = (int)(nxt / groups_per_b), nq0 = (int)(nxt - (int64_t)nb * groups_per_b) * kQPB;
-    if (nxt < total) lookup_geometry<R>(sm, buf ^ 1, coords, nb, nq0, Q, H, W);
+    const bool more = grp + (int)gridDim.x < total;
+    b += step_b; gi += step_g;
+    if (gi >= groups_per_b) { gi -= groups_per_b; ++b; }
+    if (more) lookup_geometry<R>(sm, buf ^ 1, coords, b, gi * kQPB, Q, H, W);
     __syncthreads();                                  // patches of this group and geometry of the next are visible
-    if (nxt < total) lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, nb, nq0, Q, H, W, map_batch_stride, row_offset);
+    if (more) lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, b, gi * kQPB, H, W, map_batch_stride, row_offset);
     // ---- evaluate: lane = query, warp = (level, half of the window columns).  Window column a reads elements dx + a and
     //      dx + a + 1 of every patch row (dx = x0 & 7: where the footprint starts inside the two loaded tile columns); each
     //      bf16 is widened with one PRMT whose selector depends on the element's parity.
@@ -317,7 +352,7 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
       const uint32_t* pq = sm.patch + lane * kPatchStride + lvl * 64;
       const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 14;
       float* oq = sm.outs + lane * kOut + lvl * NN;
-      const int dx = sm.org[buf][lane][2 * lvl] & 7;
+      const int dx = sm.org[buf][lane][lvl].w & 7;
       const int kx = lane >> 3;
       float fy[n];
 #pragma unroll
@@ -352,14 +387,14 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
     const int nq = min(kQPB, Q - q0);
     if (out_channels_last) {
       // the group's outputs are one contiguous run of nq * 2*n*n floats, in shared memory as in global memory
-      float* dst = out + ((int64_t)b * Q + q0) * kOut;
+      float* dst = out + ((int64_t)cur_b * Q + q0) * kOut;
       // float4 copies when the run starts 16-byte aligned (always for even Q); the remainder / unaligned case is scalar
       const int total4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? nq * kOut / 4 : 0;
       for (int f4 = threadIdx.x; f4 < total4; f4 += kLookupThreads)
         reinterpret_cast<float4*>(dst)[f4] = reinterpret_cast<const float4*>(sm.outs)[f4];
       for (int e = total4 * 4 + threadIdx.x; e < nq * kOut; e += kLookupThreads) dst[e] = sm.outs[e];
     } else if (lane < nq) {
-      float* dst = out + (int64_t)b * kOut * Q + q0 + lane;
+      float* dst = out + (int64_t)cur_b * kOut * Q + q0 + lane;
       for (int k = warp; k < kOut; k += kWarps) dst[(int64_t)k * Q] = sm.outs[lane * kOut + k];
     }
     // the next iteration's patch stores only touch sm.patch (last read before the barrier above); sm.outs is rewritten
@@ -495,6 +530,7 @@ static int launch_lookup_fwd_tiled(const void* l0, const void* l1, const float* 
                                    int W, int64_t mbs, int64_t ro, int radius, int ocl, cudaStream_t st) {
   // persistent blocks: each walks groups of 32 queries with the next group's loads in flight
   const int64_t groups = (int64_t)B * cdiv64(Q, kQPB);
+  if (groups >= ((int64_t)1 << 31) - 4096) return MRFA_E_SHAPE;   // 32-bit group counters (+ one grid stride) in the kernel
   const int64_t cap = (int64_t)148 * kTiledBlocksPerSM;
   const unsigned g = (unsigned)(groups < cap ? groups : cap);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(l0);
