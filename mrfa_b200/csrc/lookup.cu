@@ -294,6 +294,49 @@ __device__ __forceinline__ void lookup_issue_loads(const LookupSmem<R>& sm, int 
   }
 }
 
+// Horizontal interpolations of one patch row: h[a] = e[dx + a] * (1 - fx[a]) + e[dx + a + 1] * fx[a].
+template <int R>
+__device__ __forceinline__ void lookup_hrow(const uint32_t* __restrict__ pr, int w0, uint32_t sh, int kx,
+                                            const float (&fx)[2 * R + 1], const float (&wx0)[2 * R + 1],
+                                            float (&h)[2 * R + 1]) {
+  constexpr int n = 2 * R + 1, NP = (n + 2) / 2;       // NP aligned pairs hold elements dx .. dx + n
+  uint32_t w[NP + 1];
+#pragma unroll
+  for (int i = 0; i <= NP; ++i) w[i] = pr[(w0 + i) ^ kx];            // chunk-permuted word positions (see kPatchStride)
+  float e[2 * NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const uint32_t p = __funnelshift_r(w[i], w[i + 1], sh);          // elements dx + 2i (low half), dx + 2i + 1 (high half)
+    e[2 * i] = __uint_as_float(p << 16);
+    e[2 * i + 1] = __uint_as_float(p & 0xffff0000u);
+  }
+#pragma unroll
+  for (int a = 0; a < n; ++a) h[a] = fmaf(e[a + 1], fx[a], e[a] * wx0[a]);
+}
+
+// Output rows [B0, B1) of one level for the lane's query (same operation order as the column-wise form it replaced).
+template <int R, int B0, int B1>
+__device__ __forceinline__ void lookup_eval_rows(const uint32_t* __restrict__ pq, const float* __restrict__ fq,
+                                                 float* __restrict__ oq, int dx, int kx) {
+  constexpr int n = 2 * R + 1;
+  const int w0 = dx >> 1;
+  const uint32_t sh = (dx & 1) * 16;
+  float fx[n], wx0[n];
+#pragma unroll
+  for (int a = 0; a < n; ++a) { fx[a] = fq[a]; wx0[a] = 1.f - fx[a]; }
+  float h[2][n];
+  lookup_hrow<R>(pq + B0 * 8, w0, sh, kx, fx, wx0, h[0]);
+#pragma unroll
+  for (int bb = B0; bb < B1; ++bb) {
+    float (&hp)[n] = h[(bb - B0) & 1];
+    float (&hn)[n] = h[(bb - B0 + 1) & 1];
+    lookup_hrow<R>(pq + (bb + 1) * 8, w0, sh, kx, fx, wx0, hn);
+    const float fy = fq[7 + bb], wy0 = 1.f - fy;
+#pragma unroll
+    for (int a = 0; a < n; ++a) oq[a * n + bb] = fmaf(hn[a], fy, hp[a] * wy0);
+  }
+}
+
 template <int R>
 __global__ void __launch_bounds__(kLookupThreads)
 corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __nv_bfloat16* __restrict__ level1,
@@ -343,44 +386,19 @@ corr_lookup_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ level0, const __n
     if (more) lookup_geometry<R>(sm, buf ^ 1, coords, b, gi * kQPB, Q, H, W);
     __syncthreads();                                  // patches of this group and geometry of the next are visible
     if (more) lookup_issue_loads<R>(sm, buf ^ 1, v, level0, level1, b, gi * kQPB, H, W, map_batch_stride, row_offset);
-    // ---- evaluate: lane = query, warp = (level, half of the window columns).  Window column a reads elements dx + a and
-    //      dx + a + 1 of every patch row (dx = x0 & 7: where the footprint starts inside the two loaded tile columns); each
-    //      bf16 is widened with one PRMT whose selector depends on the element's parity.
+    // ---- evaluate: lane = query, warp = (level, half of the window rows).  Row-wise: the words holding elements
+    //      dx .. dx + n of a patch row (dx = x0 & 7: where the footprint starts inside the two loaded tile columns) are
+    //      fetched once, aligned by one funnel shift per word pair, widened, and give the n horizontal interpolations of
+    //      that row; two consecutive rows give a row of outputs.
     {
-      const int lvl = warp >> 1, ahalf = warp & 1;
-      const int a_begin = ahalf ? (n + 1) / 2 : 0, a_end = ahalf ? n : (n + 1) / 2;
+      const int lvl = warp >> 1;
       const uint32_t* pq = sm.patch + lane * kPatchStride + lvl * 64;
       const float* fq = sm.frac[buf] + lane * kFracStride + lvl * 14;
       float* oq = sm.outs + lane * kOut + lvl * NN;
       const int dx = sm.org[buf][lane][lvl].w & 7;
-      const int kx = lane >> 3;
-      float fy[n];
-#pragma unroll
-      for (int bb = 0; bb < n; ++bb) fy[bb] = fq[7 + bb];
-#pragma unroll 1
-      for (int a = a_begin; a < a_end; ++a) {
-        const int e0 = dx + a;
-        const bool odd = e0 & 1;
-        const uint32_t* pa = pq + ((e0 >> 1) ^ kx);          // word holding element e0 / the next word (chunk-permuted)
-        const uint32_t* pb = pq + (((e0 >> 1) + 1) ^ kx);
-        const uint32_t sel0 = odd ? 0x3244u : 0x1044u;     // element e0: high / low half of word A -> fp32
-        const uint32_t sel1 = odd ? 0x1044u : 0x3244u;     // element e0 + 1: low half of word B / high half of word A
-        const float fx = fq[a];
-        const float wx0 = 1.f - fx;
-        float hprev;
-        {
-          const uint32_t wa = pa[0], wb = pb[0];
-          hprev = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx, __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
-        }
-#pragma unroll
-        for (int bb = 0; bb < n; ++bb) {
-          const uint32_t wa = pa[(bb + 1) * 8], wb = pb[(bb + 1) * 8];
-          const float hnext = fmaf(__uint_as_float(__byte_perm(odd ? wb : wa, 0u, sel1)), fx,
-                                   __uint_as_float(__byte_perm(wa, 0u, sel0)) * wx0);
-          oq[a * n + bb] = fmaf(hnext, fy[bb], hprev * (1.f - fy[bb]));
-          hprev = hnext;
-        }
-      }
+      constexpr int nb0 = (n + 1) / 2;
+      if (warp & 1) lookup_eval_rows<R, nb0, n>(pq, fq, oq, dx, lane >> 3);
+      else lookup_eval_rows<R, 0, nb0>(pq, fq, oq, dx, lane >> 3);
     }
     __syncthreads();
     // ---- write out
