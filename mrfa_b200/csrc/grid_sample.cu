@@ -81,6 +81,67 @@ grid_sample_fwd_kernel(const float* __restrict__ in, const float* __restrict__ g
   }
 }
 
+// Few-channel NCHW maps (C <= 4: the full-resolution image warp raft.py:302, C = 3).  With so few channels the generic
+// kernel above is bound by the latency of its dependent load chain (grid value -> taps -> store: ncu showed 14 % of the
+// DRAM peak at 47 % occupancy), not by bytes: each thread here owns kFewPix pixels 128 apart (lanes stay on consecutive
+// pixels, so grid loads, taps and stores coalesce as before) and issues all grid loads, then all 4 * C * kFewPix tap
+// loads, before the first use -- four times the bytes in flight per thread.
+constexpr int kFewPix = 4;
+constexpr int kFewThreads = 128;
+
+template <int MODE, int PAD, bool ADD_ID, int CC>
+__global__ void __launch_bounds__(kFewThreads)
+grid_sample_fwd_fewc_kernel(const float* __restrict__ in, const float* __restrict__ grid, mrfa_grid_strides_t gs,
+                            float* __restrict__ out, int H, int W, int Ho, int Wo, FastDiv wo_div, int in_batch_div) {
+  const int HoWo = Ho * Wo;
+  const int n = blockIdx.y;                            // one sample per grid row: no division by the plane size
+  const int p0 = blockIdx.x * (kFewThreads * kFewPix) + threadIdx.x;
+  const int HW = H * W;
+  float gx[kFewPix], gy[kFewPix];
+  int nn[kFewPix], pp[kFewPix], xx[kFewPix], yy[kFewPix];
+#pragma unroll
+  for (int j = 0; j < kFewPix; ++j) {
+    const int pj = p0 + j * kFewThreads;
+    const bool live = pj < HoWo;
+    const int p = live ? pj : 0;
+    nn[j] = live ? n : -1; pp[j] = p;
+    yy[j] = (int)fast_div((uint32_t)p, wo_div); xx[j] = p - yy[j] * Wo;
+    const float* g = grid + n * gs.sn + yy[j] * gs.sy + xx[j] * gs.sx;
+    gx[j] = __ldg(g); gy[j] = __ldg(g + gs.sc);
+  }
+  Taps t[kFewPix];
+#pragma unroll
+  for (int j = 0; j < kFewPix; ++j) {
+    float vx = gx[j], vy = gy[j], mx, my;
+    if (ADD_ID) { vx = __fadd_rn(vx, (float)xx[j]); vy = __fadd_rn(vy, (float)yy[j]); }
+    t[j] = make_taps(source_index<MODE, PAD>(vx, W, &mx), source_index<MODE, PAD>(vy, H, &my), H, W);
+  }
+  float v[kFewPix][CC][4];
+#pragma unroll
+  for (int j = 0; j < kFewPix; ++j) {
+    const float* src = in + (int64_t)(n / in_batch_div) * CC * HW;
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      const float* s = src + c * HW;
+      v[j][c][0] = __ldg(s + t[j].o_nw); v[j][c][1] = __ldg(s + t[j].o_ne);
+      v[j][c][2] = __ldg(s + t[j].o_sw); v[j][c][3] = __ldg(s + t[j].o_se);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kFewPix; ++j) {
+    if (nn[j] < 0) continue;
+    float* dst = out + (int64_t)nn[j] * CC * HoWo + pp[j];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      float acc = v[j][c][0] * t[j].w_nw;                 // same evaluation order as the generic kernel (and ATen)
+      acc = fmaf(v[j][c][1], t[j].w_ne, acc);
+      acc = fmaf(v[j][c][2], t[j].w_sw, acc);
+      acc = fmaf(v[j][c][3], t[j].w_se, acc);
+      dst[(int64_t)c * HoWo] = acc;
+    }
+  }
+}
+
 // refined warp (pixel flow + identity) and coarse warp (normalised prior grid, a.c.=False)
 // of the same feature map: the feature tile is pulled through L1/L2 once for both outputs.
 __global__ void __launch_bounds__(kThreads)
@@ -788,6 +849,18 @@ static int launch_bwd_nhwc(const float* go, const float* in, const float* grid, 
 template <int MODE, int PAD>
 static int launch_fwd(const float* in, const float* grid, mrfa_grid_strides_t gs, float* out, int N, int C, int H,
                       int W, int Ho, int Wo, int div, int add_id, cudaStream_t st) {
+  if (C <= 4 && N <= 65535 && (int64_t)N * Ho * Wo >= (1 << 16)) {        // few channels, many pixels: the latency-hiding variant
+    const dim3 gb((unsigned)cdiv64((int64_t)Ho * Wo, kFewThreads * kFewPix), (unsigned)N);
+    const FastDiv wd = make_fastdiv((uint32_t)Wo);
+#define MRFA_FEWC(CC)                                                                                                    \
+  case CC:                                                                                                               \
+    if (add_id) grid_sample_fwd_fewc_kernel<MODE, PAD, true, CC><<<gb, kFewThreads, 0, st>>>(in, grid, gs, out, H, W, Ho, Wo, wd, div); \
+    else grid_sample_fwd_fewc_kernel<MODE, PAD, false, CC><<<gb, kFewThreads, 0, st>>>(in, grid, gs, out, H, W, Ho, Wo, wd, div);       \
+    break;
+    switch (C) { MRFA_FEWC(1) MRFA_FEWC(2) MRFA_FEWC(3) MRFA_FEWC(4) }
+#undef MRFA_FEWC
+    return MRFA_LAUNCH_RESULT();
+  }
   dim3 g((unsigned)cdiv64((int64_t)N * Ho * Wo, kWarpPix), (unsigned)cdiv64(C, kCPT * (kThreads / kWarpPix)));
   if (add_id) grid_sample_fwd_kernel<MODE, PAD, true><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);
   else grid_sample_fwd_kernel<MODE, PAD, false><<<g, kThreads, 0, st>>>(in, grid, gs, out, N, C, H, W, Ho, Wo, div);

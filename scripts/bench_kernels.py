@@ -200,6 +200,19 @@ with torch.no_grad():
                 report(f"stock_grid_sample[C={Cc} R={R}]", ms, 4 * (2 * elems + 2 * B * R * R))
             del feat
 
+if want("image_warp"):
+    # the full-resolution image warp (raft.py:302): NCHW, 3 channels
+    img = torch.rand(B, 3, S, S, device=dev)
+    flow = F.interpolate(torch.randn(B, 2, S // 8, S // 8, device=dev) * 3.0, size=(S, S), mode="bilinear", align_corners=True)
+    ms = timeit(lambda: mrfa_b200.warp_by_flow(img, flow))
+    report(f"grid_sample_fwd[image warp, nchw C=3 R={S}]", ms, 4 * (2 * img.numel() + 2 * B * S * S))
+    if a.stock:
+        g = (flow + mrfa_b200.coords_grid(B, S, S, dev)).permute(0, 2, 3, 1)
+        gn = torch.stack([2 * g[..., 0] / (S - 1) - 1, 2 * g[..., 1] / (S - 1) - 1], -1)
+        ms = timeit(lambda: F.grid_sample(img, gn, align_corners=True))
+        report(f"stock_grid_sample[image warp, C=3 R={S}]", ms, 4 * (2 * img.numel() + 2 * B * S * S))
+    del img, flow
+
 if want("bwd"):
     # backward kernels of the training-step configuration (B = 16 per GPU)
     Bt = min(B, 16)

@@ -45,6 +45,21 @@ with torch.no_grad():
         for _ in range(a.reps):
             torch.ops.mrfa.dual_warp(feat, flow, prior)
             mrfa_b200.warp_by_flow(feat, flow)
+    if want("image"):
+        # the full-resolution image warp (raft.py:302): NCHW, 3 channels -> grid_sample_fwd_fewc_kernel; stock op beside it
+        img = torch.rand(B, 3, 256, 256, device=dev)
+        flow = F.interpolate(torch.randn(B, 2, 32, 32, device=dev) * 3.0, size=(256, 256), mode="bilinear", align_corners=True)
+        g = (flow + mrfa_b200.coords_grid(B, 256, 256, dev)).permute(0, 2, 3, 1)
+        gn = torch.stack([2 * g[..., 0] / 255 - 1, 2 * g[..., 1] / 255 - 1], -1)
+        for _ in range(a.reps):
+            mrfa_b200.warp_by_flow(img, flow)
+            F.grid_sample(img, gn, align_corners=True)
+    if want("prior"):
+        import synthetic_inputs as syn
+        kp_s, kp_d = ({k: v.to(dev) for k, v in d.items()} for d in syn.keypoints(B, 10, seed=0))
+        src = torch.rand(B, 3, 64, 64, device=dev)
+        for _ in range(a.reps):
+            torch.ops.mrfa.dense_motion_prior(kp_d["kp"], kp_s["kp"], kp_d["jacobian"], kp_s["jacobian"], None, src, 0.01)
 if want("bwd"):
     Bt = 16
     q = torch.randn(Bt, C, h, w, device=dev).contiguous(memory_format=torch.channels_last)

@@ -111,6 +111,28 @@ def test_feature_warp_shapes(C, R):
     close(b, F.grid_sample(feat, grid, align_corners=False))
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 4])
+def test_few_channel_image_warp(C):
+    """Few-channel NCHW maps with many pixels (the full-resolution image warp, raft.py:302) take the four-pixels-per-thread
+    kernel: ragged pixel count, every convention, some taps outside the image, a shared input for several grids."""
+    m = mb()
+    torch.manual_seed(100 + C)
+    B, R, S = 3, 150, 151                              # 3 * 150 * 151 pixels: above the switch point, not a multiple of 512
+    img = torch.rand(B, C, R, S)
+    flow = torch.randn(B, 2, R, S) * 3.0
+    ident = TP.coords_grid(B, R, S)
+    ref = TP.bilinear_sampler(img, (flow + ident).permute(0, 2, 3, 1))
+    close(m.warp_by_flow(img.to(DEV), flow.to(DEV)), ref)
+    grid = TP.make_coordinate_grid((R, S))[None].repeat(B, 1, 1, 1) + torch.randn(B, R, S, 2) * 0.1
+    close(m.grid_sample(img.to(DEV), grid.to(DEV)), F.grid_sample(img, grid, align_corners=False))
+    close(m.grid_sample(img.to(DEV), grid.to(DEV), align_corners=True), F.grid_sample(img, grid, align_corners=True))
+    close(torch.ops.mrfa.grid_sample(img.to(DEV), grid.to(DEV), 0, 1, False, 1),
+          F.grid_sample(img, grid, padding_mode="reflection", align_corners=False))
+    # one input for three grids (in_batch_div): the fused `.repeat` of dense_motion.py:80-81
+    got = torch.ops.mrfa.grid_sample(img[:1].to(DEV), grid.to(DEV), 0, 0, False, 3)
+    close(got, F.grid_sample(img[:1].expand(3, -1, -1, -1), grid, align_corners=False))
+
+
 def test_warp_edge_cases():
     m = mb()
     feat = torch.randn(1, 2, 4, 4, device=DEV)
