@@ -74,5 +74,19 @@ if want("bwd"):
     for _ in range(a.reps):
         out = mrfa_b200.warp_by_flow(feat, flow)
         out.backward(torch.ones_like(out))
+    # lookup backward: volume gradients accumulated into the pyramid's fp32 buffers + coordinate gradients
+    pyr = mrfa_b200.CorrPyramid(q.detach().requires_grad_(), k.detach().requires_grad_(), C ** -0.5)
+    cflow = F.interpolate(torch.randn(Bt, 2, 8, 8, device=dev) * 3.0, size=(h, w), mode="bilinear", align_corners=True)
+    coords = (cflow + mrfa_b200.coords_grid(Bt, h, w, dev)).requires_grad_()
+    for _ in range(a.reps):
+        o = pyr.block(0)(coords, True)
+        o.backward(torch.ones_like(o), retain_graph=True)
+    # prior-motion synthesis backward (key-points, Jacobians and source carry gradients)
+    import synthetic_inputs as syn
+    kp_s, kp_d = ({kk: v.to(dev).requires_grad_() for kk, v in d.items()} for d in syn.keypoints(Bt, 10, seed=0))
+    src = torch.rand(Bt, 3, 64, 64, device=dev, requires_grad=True)
+    for _ in range(a.reps):
+        mo, hg = torch.ops.mrfa.dense_motion_prior(kp_d["kp"], kp_s["kp"], kp_d["jacobian"], kp_s["jacobian"], None, src, 0.01)
+        (mo.sum() + hg.sum()).backward()
 torch.cuda.synchronize()
 print("done")
