@@ -210,17 +210,7 @@ struct LookupSmem {
   alignas(16) int4 org[2][kQPB][2];
 };
 
-// x / d for the launch-constant divisor d = size - 1 with rcp = RN(1 / d): q0 = RN(x * rcp), r = x - q0 * d (exact in
-// one FMA), q = RN(q0 + r * rcp) is the correctly rounded quotient (Markstein) -- the same bits as __fdiv_rn for every
-// finite x that is not denormal-small (those end as -1 + tiny either way) without the reciprocal refinement and the
-// slow-path check of the IEEE division sequence; non-finite x gives NaN instead of inf, both rejected by the |p| < 1e8
-// test below.  (Checked against the correctly rounded quotient on 1.1e8 coordinates x divisors on the host.)
-__device__ __forceinline__ float div_by_const(float x, float d, float rcp) {
-  const float q0 = __fmul_rn(x, rcp);
-  const float r = __fmaf_rn(-q0, d, x);
-  return __fmaf_rn(r, rcp, q0);
-}
-// to_pixel<MRFA_COORD_PIXEL> with the division above
+// to_pixel<MRFA_COORD_PIXEL> with div_by_const (common.cuh): the divisor size - 1 is constant per (level, axis)
 __device__ __forceinline__ float to_pixel_pix(float g, float size_m1, float rcp) {
   g = __fsub_rn(div_by_const(__fmul_rn(2.f, g), size_m1, rcp), 1.f);
   return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), size_m1);

@@ -38,25 +38,30 @@ __device__ __forceinline__ void sample_source(const float* __restrict__ src, flo
   }
 }
 
-// one thread per (b, k, y, x), k in [0, K]; k == 0 is the background channel.  A block covers 256 pixels of ONE (b, k)
-// (grid.y = b * (K+1) + k): the per-key-point algebra -- J = jac_s * inverse(jac_d) with its four IEEE divisions, the
-// key-point coordinates -- is evaluated once per block into shared memory instead of once per pixel.
+// One thread per (b, y, x) walking k = 0 .. K (k == 0 is the background channel); a block covers 128 pixels of ONE sample.
+// The per-key-point algebra -- J = jac_s * inverse(jac_d) with its four IEEE divisions, the key-point coordinates -- is
+// evaluated once per block into shared memory (thread k owns key-point k); the identity-grid value of the pixel, its
+// two IEEE divisions and the reciprocal of the variance are evaluated once per thread instead of once per (k, pixel)
+// (round 2: the one-thread-per-(b,k,pixel) form issued 425 instructions per thread, 60 % issue-bound at 3 % of DRAM).
 struct PriorKp {
   float kdx, kdy, ksx, ksy, j00, j01, j10, j11;
 };
+constexpr int kPriorThreads = 128;
+constexpr int kPriorMaxK = 64;                       // key-points held in shared memory per sample
 
-__global__ void __launch_bounds__(256)
+template <int CT>                                    // CT > 0: compile-time channel count (3), 0: runtime C
+__global__ void __launch_bounds__(kPriorThreads)
 dense_motion_prior_kernel(const float* __restrict__ kp_d, const float* __restrict__ kp_s,
                           const float* __restrict__ jac_d, const float* __restrict__ jac_s,
                           const float* __restrict__ bg_param, const float* __restrict__ source,
                           float* __restrict__ motions, float* __restrict__ hg_input,
-                          int B, int K, int C, int h, int w, float variance) {
-  __shared__ PriorKp sk;
+                          int B, int K, int Crt, int h, int w, float variance) {
+  __shared__ PriorKp sk[kPriorMaxK];
+  const int C = CT > 0 ? CT : Crt;
   const int hw = h * w;
-  const int bk = blockIdx.y;
-  const int b = bk / (K + 1), k = bk - b * (K + 1);
-  if (threadIdx.x == 0 && k > 0) {
-    const int kk = b * K + (k - 1);
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += kPriorThreads) {
+    const int kk = b * K + k;
     PriorKp p;
     p.kdx = __ldg(kp_d + 2 * kk); p.kdy = __ldg(kp_d + 2 * kk + 1);
     p.ksx = __ldg(kp_s + 2 * kk); p.ksy = __ldg(kp_s + 2 * kk + 1);
@@ -74,38 +79,67 @@ dense_motion_prior_kernel(const float* __restrict__ kp_d, const float* __restric
       p.j10 = __fadd_rn(__fmul_rn(s10, i00), __fmul_rn(s11, i10));
       p.j11 = __fadd_rn(__fmul_rn(s10, i01), __fmul_rn(s11, i11));
     }
-    sk = p;
+    sk[k] = p;
   }
   __syncthreads();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.x * kPriorThreads + threadIdx.x;
   if (r >= hw) return;
-  const int64_t i = (int64_t)bk * hw + r;
   const int y = r / w, x = r - y * w;
   const float gx = norm_coord(x, w), gy = norm_coord(y, h);
+  const float rvar = __frcp_rn(variance);
+  const float* src = source + (int64_t)b * C * hw;
+  float2* mo = reinterpret_cast<float2*>(motions) + (int64_t)b * (K + 1) * hw + r;
+  float* dst = hg_input + (int64_t)b * (K + 1) * (C + 1) * hw + r;
 
-  float heat = 0.f;
-  float2 m;
-  if (k == 0) {
-    m = bg_param ? bg_affine(bg_param + 9 * b, gx, gy) : make_float2(gx, gy);
-  } else {
-    const PriorKp p = sk;
-    float cx = __fsub_rn(gx, p.kdx), cy = __fsub_rn(gy, p.kdy);
-    {
-      const float sx = __fsub_rn(gx, p.ksx), sy = __fsub_rn(gy, p.ksy);
-      const float dd = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), ds = __fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
-      heat = __fsub_rn(expf(__fdiv_rn(__fmul_rn(-0.5f, dd), variance)), expf(__fdiv_rn(__fmul_rn(-0.5f, ds), variance)));
+#pragma unroll 2
+  for (int k = 0; k <= K; ++k) {
+    float heat = 0.f;
+    float2 m;
+    if (k == 0) {
+      m = bg_param ? bg_affine(bg_param + 9 * b, gx, gy) : make_float2(gx, gy);
+    } else {
+      const PriorKp p = sk[k - 1];
+      float cx = __fsub_rn(gx, p.kdx), cy = __fsub_rn(gy, p.kdy);
+      {
+        const float sx = __fsub_rn(gx, p.ksx), sy = __fsub_rn(gy, p.ksy);
+        const float dd = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), ds = __fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
+        // exp((-0.5 * s) / variance), util.py:85: the quotient through div_by_const (same bits as the IEEE division)
+        heat = __fsub_rn(expf(div_by_const(__fmul_rn(-0.5f, dd), variance, rvar)),
+                         expf(div_by_const(__fmul_rn(-0.5f, ds), variance, rvar)));
+      }
+      if (jac_d != nullptr) {
+        const float nx = __fadd_rn(__fmul_rn(p.j00, cx), __fmul_rn(p.j01, cy));
+        const float ny = __fadd_rn(__fmul_rn(p.j10, cx), __fmul_rn(p.j11, cy));
+        cx = nx; cy = ny;
+      }
+      m = make_float2(__fadd_rn(cx, p.ksx), __fadd_rn(cy, p.ksy));
     }
-    if (jac_d != nullptr) {
-      const float nx = __fadd_rn(__fmul_rn(p.j00, cx), __fmul_rn(p.j01, cy));
-      const float ny = __fadd_rn(__fmul_rn(p.j10, cx), __fmul_rn(p.j11, cy));
-      cx = nx; cy = ny;
+    mo[(int64_t)k * hw] = m;
+    float* dk = dst + (int64_t)k * (C + 1) * hw;
+    dk[0] = heat;
+    const Taps t = make_taps(to_pixel<MRFA_COORD_NORM_ACF>(m.x, w), to_pixel<MRFA_COORD_NORM_ACF>(m.y, h), h, w);
+#pragma unroll
+    for (int c = 0; c < (CT > 0 ? CT : 1); ++c) {
+      if (CT > 0) {
+        const float* s = src + c * hw;
+        float acc = __ldg(s + t.o_nw) * t.w_nw;
+        acc = fmaf(__ldg(s + t.o_ne), t.w_ne, acc);
+        acc = fmaf(__ldg(s + t.o_sw), t.w_sw, acc);
+        acc = fmaf(__ldg(s + t.o_se), t.w_se, acc);
+        dk[(c + 1) * hw] = acc;
+      }
     }
-    m = make_float2(__fadd_rn(cx, p.ksx), __fadd_rn(cy, p.ksy));
+    if (CT == 0) {
+      for (int c = 0; c < C; ++c) {
+        const float* s = src + (int64_t)c * hw;
+        float acc = __ldg(s + t.o_nw) * t.w_nw;
+        acc = fmaf(__ldg(s + t.o_ne), t.w_ne, acc);
+        acc = fmaf(__ldg(s + t.o_sw), t.w_sw, acc);
+        acc = fmaf(__ldg(s + t.o_se), t.w_se, acc);
+        dk[(int64_t)(c + 1) * hw] = acc;
+      }
+    }
   }
-  reinterpret_cast<float2*>(motions)[i] = m;
-  float* dst = hg_input + (int64_t)bk * (C + 1) * hw;
-  dst[r] = heat;
-  sample_source<MRFA_COORD_NORM_ACF>(source + (int64_t)b * C * hw, dst + hw, C, h, w, m, r);
 }
 
 // ---- thin-plate splines ---------------------------------------------------------------------
@@ -299,10 +333,14 @@ extern "C" int mrfa_dense_motion_prior(const float* kp_d, const float* kp_s, con
   MRFA_CHECK_ARG((jac_d == nullptr) == (jac_s == nullptr));
   MRFA_CHECK_ARG(B >= 0 && K > 0 && C > 0 && h > 1 && w > 1 && variance > 0.f);
   if (B == 0) return 0;
-  MRFA_CHECK_SHAPE((int64_t)B * (K + 1) <= 65535 && (int64_t)h * w < ((int64_t)1 << 31));
-  const dim3 grid((unsigned)cdiv64((int64_t)h * w, 256), (unsigned)(B * (K + 1)));
-  dense_motion_prior_kernel<<<grid, 256, 0, as_stream(stream)>>>(
-      kp_d, kp_s, jac_d, jac_s, bg_param, source, motions, hg_input, B, K, C, h, w, variance);
+  MRFA_CHECK_SHAPE(B <= 65535 && K <= kPriorMaxK && (int64_t)h * w * (C + 1) < ((int64_t)1 << 31));
+  const dim3 grid((unsigned)cdiv64((int64_t)h * w, kPriorThreads), (unsigned)B);
+  if (C == 3)
+    dense_motion_prior_kernel<3><<<grid, kPriorThreads, 0, as_stream(stream)>>>(
+        kp_d, kp_s, jac_d, jac_s, bg_param, source, motions, hg_input, B, K, C, h, w, variance);
+  else
+    dense_motion_prior_kernel<0><<<grid, kPriorThreads, 0, as_stream(stream)>>>(
+        kp_d, kp_s, jac_d, jac_s, bg_param, source, motions, hg_input, B, K, C, h, w, variance);
   return MRFA_LAUNCH_RESULT();
 }
 
