@@ -63,7 +63,7 @@ for r in data:
     lines.append("| `%s` | %s | %.4f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %.1f | %.1f |" % (
         short(r[C["name"]]), grid, num(r, "time", "ms"), rd, wr, num(r, "dram"), num(r, "l1"), num(r, "l2"), num(r, "occ"),
         int(num(r, "regs")) if num(r, "regs") == num(r, "regs") else 0, num(r, "sm"), num(r, "tensor")))
-    key = re.sub(r"(_nhwc|_nchw)?(_run|_q|_v4|_scalar|_tma|_2sm|_tiled|_tiled_rows|_s4k13)*_kernel.*", "", short(r[C["name"]]).split("<")[0])
+    key = re.sub(r"(_nhwc|_nchw)?(_run|_q|_v4|_scalar|_tma|_2sm|_tiled|_tiled_rows|_s4k13|_fewc|_finish)*_kernel.*", "", short(r[C["name"]]).split("<")[0])
     # the names bench.py's KernelTimer uses (ops.py `_timed`): one entry per C-ABI call, whatever kernels it launches
     key = {"cast_bf16": "corr_pack", "avg_pool2x2": "avg_pool2x2_nhwc" if "nhwc" in r[C["name"]] else "avg_pool2x2",
            "occlusion_blend_subpixel": "occlusion_blend"}.get(key, key)
