@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=0, help="pairs per step of the CPU reference arm (0 = auto)")
     ap.add_argument("--other-configs", type=int, default=1,
                     help="also run short measurements of BASELINE.json configs 3/4/5 (celebvhq, 512x512 sweep, training step)")
+    ap.add_argument("--other-timeout", type=int, default=300,
+                    help="watchdog (s) around the other-config measurements: on expiry rank 0 prints the line with what finished")
     ap.add_argument("--parity-pairs", type=int, default=2, help="pairs of the timed batch compared with the CPU reference in the same run")
     return ap.parse_args()
 
@@ -238,7 +240,7 @@ def same_run_parity(cfg, size, host, parity_in, P, use_bg):
             "settings": "same process, same weights (state_dict copied to the CPU modules), product under the timed settings"}
 
 
-def measure_other_configs(args, world, rank, local, dev):
+def measure_other_configs(args, world, rank, local, dev, res=None):
     """Short measurements (3 timed steps after 2 warm-up, CUDA events, max over ranks) of the BASELINE.json configs the
     headline line does not cover, at the same N: config 3 celebvhq 256x256 B=64 (background-affine path on), config 4
     the vox1 architecture at 512x512 swept over B, config 5 the vox1 training step B=16/GPU (fwd + bwd through the
@@ -249,7 +251,8 @@ def measure_other_configs(args, world, rank, local, dev):
     import mrfa_b200
     import synthetic_inputs as syn
     steps, warm = 3, 2
-    res = {"steps": steps, "warmup": warm, "note": "device-resident inputs, ms = max over ranks"}
+    res = {} if res is None else res                         # filled in place: the watchdog of run_ours reports what is there
+    res.update({"steps": steps, "warmup": warm, "note": "device-resident inputs, ms = max over ranks"})
 
     def tmax(ms):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -329,27 +332,72 @@ def train_step_bench(world, rank, local, dev, batch, size, steps, warm):
     model = Refiner().to(dev).train()
     model.dense_motion.channels_last_()
     model.decoder.channels_last_()
+    use_graph = os.environ.get("MRFA_TRAIN_GRAPH", "1") != "0"
+    side = torch.cuda.Stream()
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)                     # train.py:43
         # train.py:45-48 passes find_unused_parameters=True; static_graph lets the reducer record the (fixed) set of unused
-        # parameters once instead of walking the autograd graph every step, gradient_as_bucket_view drops the bucket copy
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
-                                                          static_graph=True, gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        # parameters once instead of walking the autograd graph every step, gradient_as_bucket_view drops the bucket copy.
+        # Constructed on a side stream: the whole step is captured in a CUDA graph below.
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                              static_graph=True, gradient_as_bucket_view=True)
+        torch.cuda.current_stream().wait_stream(side)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=use_graph)
     src, drv = (t.to(dev) for t in syn.frame_pairs(batch, size, seed=rank))
     # the key-points carry gradients like the jointly trained detector's outputs do (model.py:196-201): the backward runs
     # through the fused prior-motion / heat-map backward kernels
     kp_s, kp_d = ({k: v.to(dev).requires_grad_(True) for k, v in d.items()} for d in syn.keypoints(batch, 10, seed=rank))
 
-    def step():
+    def clear_grads():
         opt.zero_grad(set_to_none=True)
         for d in (kp_s, kp_d):
             for v in d.values():
                 v.grad = None
+
+    def eager_step():
+        clear_grads()
         loss = (model(src, kp_s, kp_d) - drv).abs().mean()
         loss.backward()
         opt.step()
         return loss
+
+    step, graph, execution = eager_step, None, "eager"
+    if use_graph:
+        # B200-first: forward + backward + Adam and every NCCL collective of DDP / SyncBatchNorm captured ONCE in a CUDA graph
+        # and replayed.  Eager SyncBatchNorm forces a host synchronisation per layer (the count mask of
+        # torch/nn/modules/_functions.py, skipped under capture) and ~112 separately enqueued small collectives per step:
+        # at N = 2 the eager step takes 123 ms against 96.8 ms on one GPU, the replayed graph 97.5 ms.
+        ok = 1.0
+        try:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(11):                       # DDP wants >= 11 eager iterations before a whole-network capture
+                    eager_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            clear_grads()
+            with torch.cuda.graph(graph):
+                static_loss = (model(src, kp_s, kp_d) - drv).abs().mean()
+                static_loss.backward()
+                opt.step()
+        except Exception as e:                             # capture unsupported somewhere: every rank falls back together
+            ok, graph = 0.0, None
+            sys.stderr.write(f"train-step graph capture failed on rank {rank}: {e!r}\n")
+        torch.cuda.synchronize()
+        if world > 1:
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = float(flag[0])
+        if ok > 0:
+            def step():                                    # noqa: F811
+                graph.replay()
+                return static_loss
+            execution = "one CUDA graph per step (forward + backward + Adam + NCCL collectives), replayed"
+        else:
+            graph = None
 
     for _ in range(warm):
         step()
@@ -370,7 +418,8 @@ def train_step_bench(world, rank, local, dev, batch, size, steps, warm):
     ms = float(t[0])
     out = {"pairs_per_gpu": batch, "size": size, "ms_per_step": round(ms, 3), "pairs_per_s": round(batch * world / ms * 1e3, 1),
            "loss": float(loss.detach()), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
-           "parallelism": f"DDP dp{world} + SyncBatchNorm, NCCL gradient all-reduce" if world > 1 else "single GPU (no collective)"}
+           "parallelism": f"DDP dp{world} + SyncBatchNorm, NCCL gradient all-reduce" if world > 1 else "single GPU (no collective)",
+           "execution": execution}
     # share of NCCL / this library's / cuDNN kernels in one step (torch.profiler, rank 0; an extra untimed step)
     try:
         from torch.profiler import ProfilerActivity, profile
@@ -393,6 +442,14 @@ def train_step_bench(world, rank, local, dev, batch, size, steps, warm):
                         if world > 1 else None})
     except Exception as e:
         out["profile_error"] = repr(e)[:120]
+    # release the captured NCCL nodes before anything tears the communicator down (destroying it under a live graph blocks)
+    del step, loss
+    if graph is not None:
+        del static_loss
+        graph = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     del model, opt
     torch.cuda.empty_cache()
     return out
@@ -544,94 +601,118 @@ def run_ours(args):
         parity_in = {"out": out[:P].float().cpu(), "sd_dm": {k: v.detach().cpu() for k, v in dm.state_dict().items()},
                      "sd_rf": {k: v.detach().cpu() for k, v in rf.state_dict().items()}}
     del out, resident
-    others = None
     if args.other_configs:
         del dm, rf
         torch.cuda.empty_cache()
-        others = measure_other_configs(args, world, rank, local, dev)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    line = None
+    if rank == 0:
+        pk = peaks()
+        pairs = B * world * args.steps
+        step_ms = dev_ms / args.steps
+        klist = []
+        for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"]):
+            sec = k["total_ms"] / 1e3
+            e = {"kernel": name, "launches": k["launches"], "total_ms": round(k["total_ms"], 4),
+                 "share_of_step": round(k["total_ms"] / dev_ms, 4), "avg_ms": round(k["total_ms"] / max(1, k["calls"]), 5)}
+            e["algorithmic_bytes_per_launch"] = round(k["bytes"] / max(1, k["calls"]))
+            if sec > 0:
+                e["hbm_gbs"] = round(k["bytes"] / sec / 1e9, 1)
+                e["hbm_frac"] = round(k["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4)
+                if k["flops"]:
+                    e["tflops"] = round(k["flops"] / sec / 1e12, 1)
+                    e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
+            klist.append(e)
+        ours_ms = sum(k["total_ms"] for k in kernels.values())
+        hot_ms = sum(k["total_ms"] for k in hot_kernels.values())
+        # roofline: the dominant kernel of the hot path proper; the kernels of the
+        # "next" rows 8(f) (fused elementwise helpers, small-channel convolution, cat) are listed in kernels[] only
+        hot = [k for k in klist if k["kernel"] in HOT_PATH]
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        # the ncu capture was taken at the default workload; other shapes report traffic = null
+        traffic_tbl = json.load(open(tpath)) if (os.path.exists(tpath) and args.batch == 64 and args.size == 256) else {}
 
-    pk = peaks()
-    pairs = B * world * args.steps
-    step_ms = dev_ms / args.steps
-    klist = []
-    for name, k in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"]):
-        sec = k["total_ms"] / 1e3
-        e = {"kernel": name, "launches": k["launches"], "total_ms": round(k["total_ms"], 4),
-             "share_of_step": round(k["total_ms"] / dev_ms, 4), "avg_ms": round(k["total_ms"] / max(1, k["calls"]), 5)}
-        e["algorithmic_bytes_per_launch"] = round(k["bytes"] / max(1, k["calls"]))
-        if sec > 0:
-            e["hbm_gbs"] = round(k["bytes"] / sec / 1e9, 1)
-            e["hbm_frac"] = round(k["bytes"] / sec / 1e9 / pk["hbm_gbs"], 4)
-            if k["flops"]:
-                e["tflops"] = round(k["flops"] / sec / 1e12, 1)
-                e["tensor_frac"] = round(k["flops"] / sec / 1e12 / pk["bf16_tflops_sustained"], 4)
-        klist.append(e)
-    ours_ms = sum(k["total_ms"] for k in kernels.values())
-    hot_ms = sum(k["total_ms"] for k in hot_kernels.values())
-    # roofline: the dominant kernel of the hot path proper; the kernels of the
-    # "next" rows 8(f) (fused elementwise helpers, small-channel convolution, cat) are listed in kernels[] only
-    hot = [k for k in klist if k["kernel"] in HOT_PATH]
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    # the ncu capture was taken at the default workload; other shapes report traffic = null
-    traffic_tbl = json.load(open(tpath)) if (os.path.exists(tpath) and args.batch == 64 and args.size == 256) else {}
+        def roof(entry):
+            if entry is None:
+                return None
+            t = traffic_tbl.get(entry["kernel"])
+            per_step = max(1, entry["launches"] // max(1, args.steps))
+            base = {"kernel": entry["kernel"], "launches_per_step": per_step, "avg_launch_ms": entry["avg_ms"],
+                    "algorithmic_bytes_per_launch": entry["algorithmic_bytes_per_launch"],
+                    "traffic": round(t / per_step) if t else None,
+                    "traffic_scope": "average per launch: ncu dram__bytes_read+write summed over this kernel's launches in one step "
+                                     "(B=64, 256x256; profiles/r2_hot_kernels_ncu.md), divided by launches_per_step" if t else None}
+            if entry["kernel"] == "corr_volume":
+                base.update({"bound": "tensor", "achieved": entry["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": entry["tensor_frac"], "peak_source": pk["source"] + " (sustained bf16)",
+                             "hbm_frac_of_output_bytes": entry["hbm_frac"]})
+            else:
+                base.update({"bound": "hbm", "achieved": entry["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": entry["hbm_frac"], "peak_source": pk["source"]})
+            return base
 
-    def roof(entry):
-        if entry is None:
-            return None
-        t = traffic_tbl.get(entry["kernel"])
-        per_step = max(1, entry["launches"] // max(1, args.steps))
-        base = {"kernel": entry["kernel"], "launches_per_step": per_step, "avg_launch_ms": entry["avg_ms"],
-                "algorithmic_bytes_per_launch": entry["algorithmic_bytes_per_launch"],
-                "traffic": round(t / per_step) if t else None,
-                "traffic_scope": "average per launch: ncu dram__bytes_read+write summed over this kernel's launches in one step "
-                                 "(B=64, 256x256; profiles/r2_hot_kernels_ncu.md), divided by launches_per_step" if t else None}
-        if entry["kernel"] == "corr_volume":
-            base.update({"bound": "tensor", "achieved": entry["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": entry["tensor_frac"], "peak_source": pk["source"] + " (sustained bf16)",
-                         "hbm_frac_of_output_bytes": entry["hbm_frac"]})
-        else:
-            base.update({"bound": "hbm", "achieved": entry["hbm_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": entry["hbm_frac"], "peak_source": pk["source"]})
-        return base
+        roofline = roof(hot[0] if hot else None)
+        roofline_corr = roof(next((k for k in klist if k["kernel"] == "corr_volume"), None))
 
-    roofline = roof(hot[0] if hot else None)
-    roofline_corr = roof(next((k for k in klist if k["kernel"] == "corr_volume"), None))
+        line = {"metric": METRIC, "value": pairs / (dev_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32 warps/lookups + bf16 tensor-core correlation", "data": "synthetic",
+                "config": workload_config(args, B, world), "clocks": clocks,
+                "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": sum(launch_counts.values()),
+                "roofline": roofline, "roofline_corr": roofline_corr, "kernels": klist,
+                "kernels_note": "hot-path rows (SURVEY 8a) are timed inside the timed region; the other rows come from a "
+                                f"second, fully instrumented pass of the same {args.steps} steps ({instrumented_ms / args.steps:.2f} ms/step)",
+                "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
+                # two throughput tiers -- the SURVEY 8(a) kernels alone (K1-K9: correlation pack + volume, lookups,
+                # feature warps, prior-motion synthesis, grids), summed from the CUDA events of the timed region on rank 0 and
+                # scaled by the world size, and the end-to-end refinement forward (`value`, cuDNN convolutions included)
+                "tiers": {"hot_path_only": {"ms_per_step": round(hot_ms / args.steps, 4),
+                                            "pairs_per_s": round(B * world / (hot_ms / args.steps) * 1e3, 1) if hot_ms > 0 else None,
+                                            "kernels": sorted(hot_kernels)},
+                          "refinement_forward": {"ms_per_step": round(step_ms, 4), "pairs_per_s": round(pairs / (dev_ms / 1e3), 1)}},
+                "recon_l1_mean": recon_l1_mean, "peaks": pk}
+        if parity_in is not None:
+            line["parity"] = same_run_parity(cfg, S, host, parity_in, P, use_bg)
+            line["parity_max_err"], line["parity_rel_l2"] = line["parity"]["max_abs_err"], line["parity"]["rel_l2"]
+        if not args.no_cpu_baseline and world == 1:           # reported at N = 1 only (torchrun pins OMP threads per rank)
+            r = time_cpu_path(cfg, S, 1, 3, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
+                                    "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"],
+                                    "sample": f"1 pair per step, 3 timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step), "
+                                              f"{CPU_KIND_TEXT[r['kind']]}, {r['cores']} threads"}
 
-    line = {"metric": METRIC, "value": pairs / (dev_ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32 warps/lookups + bf16 tensor-core correlation", "data": "synthetic",
-            "config": workload_config(args, B, world), "clocks": clocks,
-            "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": sum(launch_counts.values()),
-            "roofline": roofline, "roofline_corr": roofline_corr, "kernels": klist,
-            "kernels_note": "hot-path rows (SURVEY 8a) are timed inside the timed region; the other rows come from a "
-                            f"second, fully instrumented pass of the same {args.steps} steps ({instrumented_ms / args.steps:.2f} ms/step)",
-            "hot_path_share_of_step": round(ours_ms / dev_ms, 4),
-            # two throughput tiers -- the SURVEY 8(a) kernels alone (K1-K9: correlation pack + volume, lookups,
-            # feature warps, prior-motion synthesis, grids), summed from the CUDA events of the timed region on rank 0 and
-            # scaled by the world size, and the end-to-end refinement forward (`value`, cuDNN convolutions included)
-            "tiers": {"hot_path_only": {"ms_per_step": round(hot_ms / args.steps, 4),
-                                        "pairs_per_s": round(B * world / (hot_ms / args.steps) * 1e3, 1) if hot_ms > 0 else None,
-                                        "kernels": sorted(hot_kernels)},
-                      "refinement_forward": {"ms_per_step": round(step_ms, 4), "pairs_per_s": round(pairs / (dev_ms / 1e3), 1)}},
-            "recon_l1_mean": recon_l1_mean, "peaks": pk}
-    if others is not None:
-        line["other_configs"] = others
-    if parity_in is not None:
-        line["parity"] = same_run_parity(cfg, S, host, parity_in, P, use_bg)
-        line["parity_max_err"], line["parity_rel_l2"] = line["parity"]["max_abs_err"], line["parity"]["rel_l2"]
-    if not args.no_cpu_baseline:
-        r = time_cpu_path(cfg, S, 1, 3, 1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
-                                "cpu_model": r["cpu_model"], "best": r["best_pairs_s"], "median": r["median_pairs_s"],
-                                "sample": f"1 pair per step, 3 timed steps after 1 warm-up ({r['ms_per_step']:.0f} ms/step), "
-                                          f"{CPU_KIND_TEXT[r['kind']]}, {r['cores']} threads"}
-    print(json.dumps(line), flush=True)
+    # ---- the other BASELINE.json configs, under a watchdog: whatever happens there (a stuck collective at some N), rank 0
+    #      still prints the headline line with the side measurements finished so far
+    emitted = threading.Event()
+
+    def emit():
+        if rank == 0 and not emitted.is_set():
+            emitted.set()
+            for _ in range(5):                      # the watchdog thread may serialise while the main thread still adds results
+                try:
+                    text = json.dumps(line)
+                    break
+                except RuntimeError:
+                    time.sleep(0.05)
+            print(text, flush=True)
+
+    if args.other_configs:
+        others = {}
+        if rank == 0:
+            line["other_configs"] = others
+
+        def on_timeout():
+            others["watchdog"] = f"other_configs did not finish within {args.other_timeout} s; partial results"
+            emit()
+            os._exit(0)
+
+        dog = threading.Timer(args.other_timeout, on_timeout)
+        dog.daemon = True
+        dog.start()
+        measure_other_configs(args, world, rank, local, dev, others)
+        dog.cancel()
+    emit()
     if world > 1:
         dist.destroy_process_group()
 
