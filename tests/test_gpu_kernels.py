@@ -760,6 +760,87 @@ def test_dense_motion_networks_forward(golden):
             close(out[k], d["tps_fwd_" + k], 2e-4)
 
 
+# ------------------------------------------------------------------ full-size properties (BASELINE.json config 2: B = 64)
+def test_full_size_correlation_and_lookup_properties():
+    """Size-independent properties at the benchmarked size (64 pairs, 64 x 64 maps, C = 256, 3.6 GB of volume):
+    scaling a factor by a power of two scales the bf16 volume bit-exactly; the driving-pooled rows are the average of the
+    basic rows they pool (pooling commutes with the contraction) within bf16 rounding; a lookup at integer coordinates
+    returns the stored volume entries (weights 1, 0, 0, 0 up to the coordinate round trip's last ulp) with zeros outside
+    the maps."""
+    m = mb()
+    torch.manual_seed(7)
+    B, C, h, w = 64, 256, 64, 64
+    q = torch.randn(B, C, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+    k = torch.randn(B, C, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        pyr = m.CorrPyramid(q, k, C ** -0.5)
+        pyr2 = m.CorrPyramid(q * 2.0, k, C ** -0.5)
+        assert torch.equal(pyr2.volume0.float(), pyr.volume0.float() * 2.0)
+        assert torch.equal(pyr2.volume1.float(), pyr.volume1.float() * 2.0)
+        del pyr2
+        # level-1 pooled driving rows (32 x 32 queries) of a few samples vs the mean of their four basic rows
+        off1 = m.ops.corr_row_offset(h, w, 1)
+        for b in (0, 17, 63):
+            basic = pyr.volume0[b, :h * w].float().view(h // 2, 2, w // 2, 2, h * w).mean(dim=(1, 3)).view(-1, h * w)
+            pooled = pyr.volume0[b, off1:off1 + h * w // 4].float()
+            rel_close(pooled, basic, 2e-2)                     # both sides rounded to bf16 separately
+        # integer coordinates: every window tap of query (y, x) is a stored cell
+        ys, xs = torch.meshgrid(torch.arange(h, device=DEV), torch.arange(w, device=DEV), indexing="ij")
+        shift = torch.randint(-6, 7, (B, 2, 1, 1), device=DEV)
+        coords = torch.stack([xs, ys]).float()[None] + shift.float()                    # (B,2,h,w), integer valued
+        out = pyr.block(0)(coords, True)                                              # NHWC (B,98,h,w)
+        # check three samples against the un-tiled maps
+        for b in (0, 31, 63):
+            sub = m.CorrPyramid(q[b:b + 1], k[b:b + 1], C ** -0.5)
+            assert torch.equal(sub.volume0, pyr.volume0[b:b + 1])                      # batch entries are independent
+            for lvl in (0, 1):
+                maps = sub.dense(0, lvl)[:, 0]                                          # (h*w, H_l, W_l) fp32 copies of the bf16 cells
+                Hl, Wl = h >> lvl, w >> lvl
+                cx = (coords[b, 0].view(-1) / 2 ** lvl)
+                cy = (coords[b, 1].view(-1) / 2 ** lvl)
+                integral = (cx == cx.floor()) & (cy == cy.floor())                     # level 1: only even coordinates are cell centres
+                for a, bb in ((0, 0), (3, 3), (6, 2), (1, 6)):
+                    x = cx.long() + a - 3
+                    y = cy.long() + bb - 3
+                    inside = (x >= 0) & (x < Wl) & (y >= 0) & (y < Hl)
+                    exp = torch.where(inside, maps[torch.arange(h * w, device=DEV), y.clamp(0, Hl - 1), x.clamp(0, Wl - 1)],
+                                      torch.zeros((), device=DEV))
+                    got = out[b, lvl * 49 + a * 7 + bb].reshape(-1)
+                    # not bit for bit: the replayed coordinate round trip returns x only to within an ulp (see the warp test)
+                    assert float((got[integral] - exp[integral]).abs().max()) <= 1e-4, (b, lvl, a, bb)
+
+
+def test_full_size_warp_identity_properties():
+    """Zero flow reproduces the feature map at every benchmarked level (B = 64), in both memory layouts, through the single
+    and the dual warp kernels and the few-channel image warp; a one-pixel integer shift is a shift with a zero border.
+    Not bit for bit: the kernels replay the reference's coordinate round trip x -> 2x/(W-1)-1 -> ((g+1)/2)(W-1)
+    (util.py:30-31 + grid_sample), which returns x only to within an ulp of the coordinate (1.5e-5 at x = 255): the blend
+    of two neighbouring N(0,1) values then moves by up to ~1e-4, exactly as in the reference."""
+    m = mb()
+    torch.manual_seed(8)
+    B = 64
+
+    def same(a, b):
+        assert float((a - b).abs().max()) <= 2e-4
+
+    with torch.no_grad():
+        for C, R in ((512, 8), (512, 32), (256, 64), (64, 256), (3, 256)):
+            feat = torch.randn(B, C, R, R, device=DEV)
+            zero = torch.zeros(B, 2, R, R, device=DEV)
+            prior = m.make_coordinate_grid((R, R), "torch.cuda.FloatTensor")[None].repeat(B, 1, 1, 1).contiguous()
+            layouts = [feat] if C % 4 else [feat, feat.contiguous(memory_format=torch.channels_last)]
+            for f in layouts:
+                same(m.warp_by_flow(f, zero), f)
+                if C % 4 == 0:
+                    same(torch.ops.mrfa.dual_warp(f, zero, prior)[0], f)
+                shift = zero.clone()
+                shift[:, 0] = 1.0                                                       # sample one pixel to the right
+                got = m.warp_by_flow(f, shift)
+                same(got[..., :-1], f[..., 1:])
+                assert float(got[..., -1].abs().max()) <= 2e-4
+            del feat, zero, prior
+
+
 # ------------------------------------------------------------------ channels-last (NHWC) paths
 @pytest.mark.parametrize("C,R", [(512, 8), (256, 64), (64, 128), (4, 19)])
 def test_feature_warp_channels_last(C, R):
