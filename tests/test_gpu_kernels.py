@@ -760,6 +760,46 @@ def test_dense_motion_networks_forward(golden):
             close(out[k], d["tps_fwd_" + k], 2e-4)
 
 
+# ------------------------------------------------------------------ seeded random shape sweep
+def test_random_shapes_warps_and_lookups():
+    """Ragged / odd shapes drawn from a seeded generator: every warp convention in both layouts against the stock ops the
+    reference calls, and row-major lookups of every radius against the oracle (non-square maps, window sizes 3..9, query
+    planes that are not multiples of the 32-query groups)."""
+    m = mb()
+    rng = np.random.default_rng(2024)
+    for _ in range(12):
+        B = int(rng.integers(1, 4))
+        C = int(rng.choice([1, 2, 3, 4, 5, 8, 12, 20, 36, 64]))
+        H, W = int(rng.integers(3, 41)), int(rng.integers(3, 41))
+        Ho, Wo = int(rng.integers(2, 37)), int(rng.integers(2, 37))
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        feat = torch.randn(B, C, H, W, generator=g)
+        grid = torch.rand(B, Ho, Wo, 2, generator=g) * 2.6 - 1.3                    # ~12 % of the samples leave the map
+        pix = torch.rand(B, Ho, Wo, 2, generator=g) * torch.tensor([W + 6.0, H + 6.0]) - 3.0
+        layouts = [feat.to(DEV)]
+        if C % 4 == 0:
+            layouts.append(feat.to(DEV).contiguous(memory_format=torch.channels_last))
+        for f in layouts:
+            close(m.grid_sample(f, grid.to(DEV)), F.grid_sample(feat, grid, align_corners=False))
+            close(m.grid_sample(f, grid.to(DEV), align_corners=True), F.grid_sample(feat, grid, align_corners=True))
+            close(m.grid_sample(f, grid.to(DEV), padding_mode="reflection"),
+                  F.grid_sample(feat, grid, padding_mode="reflection", align_corners=False), 2e-5)
+            close(m.bilinear_sampler(f, pix.to(DEV)), TP.bilinear_sampler(feat, pix))
+    for _ in range(8):
+        B = int(rng.integers(1, 3))
+        H, W = 2 * int(rng.integers(4, 20)), 2 * int(rng.integers(4, 20))
+        h1, w1 = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        radius = int(rng.integers(1, 5))
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        corr = torch.randn(B * h1 * w1, 1, H, W, generator=g)
+        coords = torch.rand(B, 2, h1, w1, generator=g) * torch.tensor([W + 8.0, H + 8.0]).view(1, 2, 1, 1) - 4.0
+        lv1 = F.avg_pool2d(corr, 2, stride=2)
+        exp = O.corr_lookup([corr.numpy(), lv1.numpy()], coords.numpy(), radius=radius)
+        blk = m.CorrBlock(corr.to(DEV), radius=radius)
+        close(blk(coords.to(DEV)), exp)
+        close(blk(coords.to(DEV), True), exp)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE.json config 2: B = 64)
 def test_full_size_correlation_and_lookup_properties():
     """Size-independent properties at the benchmarked size (64 pairs, 64 x 64 maps, C = 256, 3.6 GB of volume):
