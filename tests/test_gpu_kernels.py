@@ -800,6 +800,41 @@ def test_random_shapes_warps_and_lookups():
         close(blk(coords.to(DEV), True), exp)
 
 
+def test_random_shapes_warp_backward():
+    """Backward of the warps at ragged shapes in both layouts (the NHWC run-walk kernel pre-reduces its scatter-adds along a
+    row: odd widths, single rows and channel counts that do not fill a lane group) against fp64 autograd of the stock op.
+    Sample positions keep 0.02 px away from cell borders, where the bilinear derivative jumps."""
+    m = mb()
+    rng = np.random.default_rng(77)
+    for it in range(10):
+        B = int(rng.integers(1, 3))
+        C = int(rng.choice([1, 3, 4, 8, 12, 32, 64]))
+        H, W = int(rng.integers(2, 30)), int(rng.integers(2, 30))
+        Ho, Wo = int(rng.integers(1, 26)), int(rng.integers(1, 26))
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        feat = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+        pix = torch.rand(B, Ho, Wo, 2, generator=g, dtype=torch.float64) * torch.tensor([W + 3.0, H + 3.0]) - 1.5
+        frac = pix - pix.floor()
+        pix = pix.floor() + frac.clamp(0.02, 0.98)
+        act = bool(it % 2)
+        size = torch.tensor([float(W), float(H)], dtype=torch.float64)
+        grid = (2 * pix / (size - 1) - 1) if act else ((2 * pix + 1) / size - 1)        # normalised positions of `pix`
+        go = torch.randn(B, C, Ho, Wo, generator=g, dtype=torch.float64)
+        f64, g64 = feat.clone().requires_grad_(), grid.clone().requires_grad_()
+        F.grid_sample(f64, g64, align_corners=act).backward(go)
+        for cl in ([False, True] if C % 4 == 0 else [False]):
+            f32 = feat.float().to(DEV)
+            if cl:
+                f32 = f32.contiguous(memory_format=torch.channels_last)
+            f32 = f32.requires_grad_()
+            g32 = grid.float().to(DEV).requires_grad_()
+            m.grid_sample(f32, g32, align_corners=act).backward(go.float().to(DEV))
+            scale = float(f64.grad.abs().max()) + 1e-9
+            assert float((f32.grad.double().cpu() - f64.grad).abs().max()) <= 1e-4 * max(1.0, scale), (it, cl)
+            gs = float(g64.grad.abs().max()) + 1e-9
+            assert float((g32.grad.double().cpu() - g64.grad).abs().max()) <= 2e-3 * max(1.0, gs), (it, cl)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE.json config 2: B = 64)
 def test_full_size_correlation_and_lookup_properties():
     """Size-independent properties at the benchmarked size (64 pairs, 64 x 64 maps, C = 256, 3.6 GB of volume):
