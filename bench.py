@@ -466,8 +466,12 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL writes its banner / debug lines to stdout by default; stdout carries exactly one JSON line
+    # stdout carries exactly ONE JSON line: NCCL (version banner, NCCL_DEBUG lines) and other libraries write to file
+    # descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the line goes to a saved copy of the real stdout
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -695,7 +699,7 @@ def run_ours(args):
                     break
                 except RuntimeError:
                     time.sleep(0.05)
-            print(text, flush=True)
+            print(text, file=real_stdout, flush=True)
 
     if args.other_configs:
         others = {}
