@@ -84,6 +84,7 @@ S2D_FINAL = os.environ.get("MRFA_S2D_FINAL", "1") != "0"      # A/B switch for t
 S2D_BLOCK = 4
 HG_SUBPIXEL = os.environ.get("MRFA_HG_SUBPIXEL", "1") != "0"  # A/B switch for the hourglass sub-pixel up-blocks
 SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for mrfa::conv7x7_small
+FOLD_CB_BIAS = os.environ.get("MRFA_FOLD_CB_BIAS", "1") != "0"  # A/B switch: ChannelBlock2d bias folded into the ResBlock2d behind it
 
 
 def _small7_ok(conv: nn.Conv2d, x: torch.Tensor) -> bool:
@@ -211,6 +212,25 @@ class ResBlock2d(nn.Module):
         y = self.conv2(F.relu(self.norm2(y)))
         return y + x
 
+    def forward_prebias(self, t, bias):
+        """forward(t + bias[c]) without materialising the sum (inference fast path): the per-channel bias of the producing
+        convolution folds into the norm1 shift (relu(s (t + b) + h) = relu(s t + (s b + h))) and into the shift of the
+        closing residual pass (v + b2 + (t + b) = v + (b2 + b) + t), which saves one read + write of the whole map."""
+        n1, n2, c1, c2 = self.norm1, self.norm2, self.conv1, self.conv2
+        if not hasattr(self, "_prebias"):
+            self._prebias = _Cache()
+
+        def build():
+            s1, h1 = _bn_affine(n1)
+            return s1, s1 * bias + h1, c2.bias + bias
+
+        s1, h1b, b2b = self._prebias.get((n1.weight, n1.bias, n1.running_mean, n1.running_var, c2.bias, bias), build)
+        w, b = self._folded.get((c1.weight, c1.bias, n2.weight, n2.bias, n2.running_mean, n2.running_var), lambda: _fold(c1, n2))
+        a = torch.ops.mrfa.channel_affine(t, s1, h1b, None, 1)                          # norm1(t + bias) + relu
+        a = torch.cudnn_convolution_relu(a, w, b, c1.stride, c1.padding, c1.dilation, c1.groups)
+        a = F.conv2d(a, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+        return torch.ops.mrfa.channel_affine(a, None, b2b, t, 0)                        # + conv2 bias + (t + bias)
+
 
 class ChannelBlock2d(nn.Module):
     """BN -> ReLU -> conv halving the channel count (util.py:111-133)."""
@@ -229,6 +249,13 @@ class ChannelBlock2d(nn.Module):
             t = F.conv2d(t, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
             return torch.ops.mrfa.channel_affine(t, None, c1.bias, None, 0)
         return self.conv1(F.relu(self.norm1(x)))
+
+    def forward_nobias(self, x):
+        """(conv1(relu(norm1(x))) WITHOUT its bias, the bias): the ResBlock2d behind it absorbs the bias (forward_prebias)."""
+        n1, c1 = self.norm1, self.conv1
+        s1, h1 = self._pre.get((n1.weight, n1.bias, n1.running_mean, n1.running_var), lambda: _bn_affine(n1))
+        t = torch.ops.mrfa.channel_affine(x, s1, h1, None, 1)
+        return F.conv2d(t, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups), c1.bias
 
 
 class _HGEncoder(nn.Module):
@@ -398,9 +425,14 @@ class OcclusionAwareGenerator(nn.Module):
         if use_coarse:
             y = torch.cat([y, warp_f_c[0]], dim=1)
         for i in range(self.num_up_blocks):
-            if use_coarse:
-                y = self.channel_block[i](y)
-            y = self.resblock[i](y)
+            cb = self.channel_block[i]
+            if use_coarse and FOLD_CB_BIAS and cb.conv1.bias is not None and self.resblock[i].conv2.bias is not None:
+                t, cbias = cb.forward_nobias(y)                  # the ChannelBlock's bias pass folds into the ResBlock
+                y = self.resblock[i].forward_prebias(t, cbias)
+            else:
+                if use_coarse:
+                    y = cb(y)
+                y = self.resblock[i](y)
             up = self.up_blocks[i]
             if up.subpixel_ok(y) and warp_f[i + 1].is_contiguous(memory_format=torch.channels_last) \
                     and not warp_f[i + 1].is_contiguous():
