@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRFA_B200_ABI_VERSION 7
+#define MRFA_B200_ABI_VERSION 8
 
 #define MRFA_E_BADARG   (-1)   /* null pointer, non-positive extent, unsupported enum  */
 #define MRFA_E_SHAPE    (-2)   /* shape outside what the kernel is specialised for     */
@@ -280,6 +280,13 @@ int mrfa_corr_lookup_bwd(const float* grad_out, const void* level0, const void* 
 int mrfa_channel_affine(const float* x, const float* scale, const float* shift, const float* residual,
                         float* y, int64_t pixels, int C, int HW, int channels_last, int act,
                         mrfa_stream_t stream);
+
+/* generator.py:61-63 behind the space-to-depth final convolution (mrfa_occlusion_blend_subpixel with out_block r feeds a 3x3
+ * convolution with C*r*r outputs): pixel shuffle + bias + sigmoid + the last occlusion blend in one pass.
+ *   conv (B, H/r, W/r, C*r*r) NHWC, channel c*r*r + (Y%r)*r + X%r of block (Y/r, X/r) = pixel (Y,X) of plane c, no bias;
+ *   bias (C); a, y (B,C,H,W) NCHW; occ (B,1,H,W):  y = a * occ + sigmoid(conv + bias[c]) * (1 - occ).              */
+int mrfa_final_blend_s2d(const float* conv, const float* bias, const float* a, const float* occ, float* y, int B,
+                         int C, int H, int W, int r, mrfa_stream_t stream);
 
 /* Decoder occlusion blending generator.py:47,57: y = a * occ + b * (1 - occ) (b NULL: y = a * occ),
  * occ (N,1,H,W) broadcast over channels.  Same layouts as above.  y may alias a or b.        */

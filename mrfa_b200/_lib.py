@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrfa_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 COORD_NORM_ACF, COORD_NORM_ACT, COORD_PIXEL = 0, 1, 2
 PAD_ZEROS, PAD_REFLECTION = 0, 1
 TPS_L1, TPS_L2SQ = 0, 1
@@ -72,6 +72,7 @@ SIGNATURES = {
     "mrfa_cat2_nhwc": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_void_p]),
     "mrfa_flow_update": (c_int, [c_void_p] * 3 + [GridStrides] + [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "mrfa_flow_carry": (c_int, [c_void_p, GridStrides] + [c_void_p] * 8 + [c_int] * 3 + [c_float, c_int, c_void_p]),
+    "mrfa_final_blend_s2d": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "mrfa_occlusion_blend": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "mrfa_corr_lookup_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4
                              + [c_int64, c_int64, c_int, c_int, c_void_p]),

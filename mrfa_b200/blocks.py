@@ -84,6 +84,7 @@ S2D_FINAL = os.environ.get("MRFA_S2D_FINAL", "1") != "0"      # A/B switch for t
 S2D_BLOCK = 4
 HG_SUBPIXEL = os.environ.get("MRFA_HG_SUBPIXEL", "1") != "0"  # A/B switch for the hourglass sub-pixel up-blocks
 SMALL_CONV = os.environ.get("MRFA_SMALL_CONV", "1") != "0"    # A/B switch for mrfa::conv7x7_small
+FUSED_TAIL = os.environ.get("MRFA_FUSED_TAIL", "1") != "0"      # A/B switch: pixel shuffle + bias + sigmoid + last blend as one kernel
 FOLD_CB_BIAS = os.environ.get("MRFA_FOLD_CB_BIAS", "1") != "0"  # A/B switch: ChannelBlock2d bias folded into the ResBlock2d behind it
 
 
@@ -384,7 +385,7 @@ class OcclusionAwareGenerator(nn.Module):
         y = torch.sigmoid(self.final(y))
         return y * (1 - occlusion[-1]) + warp_img * occlusion[-1]
 
-    def _final_s2d(self, ys):
+    def _final_s2d(self, ys, fused_tail=None):
         """self.final (7x7, C -> 3, pad 3) on a 4x4 space-to-depth input (N, 16C, H/4, W/4): the same sums as a
         3x3 / pad 1 convolution with 48 outputs (weights re-indexed, taps outside the 7x7 window zero) followed by
         a pixel shuffle.  The library's 7x7 kernel tiles N = 3 outputs into a 64-wide tile (3.9 ms per batch of
@@ -412,6 +413,10 @@ class OcclusionAwareGenerator(nn.Module):
             return w2, c.bias.repeat_interleave(r * r).contiguous()
 
         w2, b2 = self._s2d.get((c.weight, c.bias), build)
+        if fused_tail is not None:
+            # pixel shuffle + bias + sigmoid + the last occlusion blend in one pass over the 48-channel convolution output
+            warp_img, occ = fused_tail
+            return torch.ops.mrfa.final_blend_s2d(F.conv2d(ys, w2, None, padding=1), c.bias, warp_img, occ, S2D_BLOCK)
         return F.pixel_shuffle(F.conv2d(ys, w2, b2, padding=1), S2D_BLOCK)
 
     def _decode_fast(self, warp_f, warp_img, occlusion, warp_f_c, coarse_cat=None):
@@ -440,6 +445,8 @@ class OcclusionAwareGenerator(nn.Module):
                 if last and s2d_final and warp_f[i + 1].shape[2] % S2D_BLOCK == 0 and warp_f[i + 1].shape[3] % S2D_BLOCK == 0:
                     # the last blend writes its result in 4x4 space-to-depth order for the final convolution
                     ys = torch.ops.mrfa.occlusion_blend_subpixel(warp_f[i + 1], up.forward_subpixel(y), occlusion[i + 1], S2D_BLOCK)
+                    if FUSED_TAIL and warp_img.is_contiguous():              # NCHW planes (the few-channel image warp's output)
+                        return self._final_s2d(ys, (warp_img, occlusion[-1]))
                     return blend(warp_img, torch.sigmoid(self._final_s2d(ys)), occlusion[-1])
                 buf = coarse_cat[i + 1] if (coarse_cat is not None and use_coarse and not last) else None
                 if buf is not None and buf.shape[1] == 2 * warp_f[i + 1].shape[1]:

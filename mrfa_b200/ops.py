@@ -891,6 +891,30 @@ def _(a, b, occ):
     return torch.empty_like(a)
 
 
+@torch.library.custom_op("mrfa::final_blend_s2d", mutates_args=(), device_types="cuda")
+def final_blend_s2d(conv: Tensor, bias: Tensor, a: Tensor, occ: Tensor, r: int) -> Tensor:
+    """a * occ + sigmoid(pixel_shuffle(conv, r) + bias[c]) * (1 - occ) in one pass (generator.py:61-63 behind the
+    space-to-depth final convolution).  conv (B, C*r*r, H/r, W/r) channels_last, a (B,C,H,W) NCHW, occ (B,1,H,W)."""
+    a, bias, occ = _req(a, "a"), _req(bias, "bias"), _req(occ, "occlusion")
+    if not (conv.is_cuda and conv.dtype == torch.float32 and conv.dim() == 4
+            and conv.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("mrfa_b200: final_blend_s2d expects a channels_last float32 CUDA convolution output")
+    B, C, H, W = a.shape
+    if conv.shape != (B, C * r * r, H // r, W // r) or H % r or W % r or bias.numel() != C:
+        raise RuntimeError("mrfa_b200: final_blend_s2d shape mismatch")
+    y = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        with _timed("final_blend_s2d", 4 * (conv.numel() + 2 * a.numel() + occ.numel())):
+            check(lib.mrfa_final_blend_s2d(_p(conv), _p(bias), _p(a), _p(occ), _p(y), B, C, H, W, r, _stream()),
+                  "mrfa_final_blend_s2d")
+    return y
+
+
+@final_blend_s2d.register_fake
+def _(conv, bias, a, occ, r):
+    return torch.empty_like(a)
+
+
 @torch.library.custom_op("mrfa::resize_bilinear", mutates_args=(), device_types="cuda")
 def resize_bilinear(x: Tensor, Ho: int, Wo: int, act: int, bias: Optional[Tensor] = None) -> Tensor:
     """act(F.interpolate(x, (Ho,Wo), mode='bilinear', align_corners=True) + bias[None, :, None, None]) with act 0 / 1 relu /

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops, sampling
-from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, conv_relu, fast_path, install_cache_hooks, invalidate_caches
+from .blocks import Hourglass, OcclusionAwareGenerator, _Cache, _small7_ok, conv_relu, fast_path, install_cache_hooks, invalidate_caches
 from .corr import CorrPyramid
 
 
@@ -251,7 +251,9 @@ class RaftFlow(nn.Module):
         if self.auto_channels_last and not self.channels_last and not self.training and img_full.is_cuda:
             self.channels_last_()
         cl = self.channels_last
-        if cl:
+        if cl and not (fast_path(self, img_full) and _small7_ok(self.generator.first.conv, img_full)):
+            # (the tcgen05 small-channel convolution reads any strides and writes NHWC: the 3-channel image then stays NCHW,
+            # which is also what the few-channel image warp at the end wants -- no NHWC copy and no copy back)
             img_full = img_full.contiguous(memory_format=torch.channels_last)
         feature = self.generator.encode(img_full)
         if img is None:

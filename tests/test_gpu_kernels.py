@@ -1296,6 +1296,21 @@ def test_small_conv_blocks_match_cudnn_path():
     rel_close(a2, b2, 5e-3)
 
 
+def test_final_blend_s2d_matches_op_chain():
+    """pixel shuffle + bias + sigmoid + the last occlusion blend (generator.py:61-63 behind the space-to-depth final
+    convolution) as one kernel against the op chain it replaces; non-square, several block sizes."""
+    mb()
+    torch.manual_seed(21)
+    for r, C, (Hb, Wb) in ((4, 3, (16, 20)), (2, 3, (9, 7)), (1, 2, (5, 6))):
+        B = 3
+        conv = torch.randn(B, C * r * r, Hb, Wb, device=DEV).contiguous(memory_format=torch.channels_last)
+        bias = torch.randn(C, device=DEV)
+        a = torch.rand(B, C, Hb * r, Wb * r, device=DEV)
+        occ = torch.rand(B, 1, Hb * r, Wb * r, device=DEV)
+        exp = a * occ + torch.sigmoid(F.pixel_shuffle(conv, r) + bias.view(1, -1, 1, 1)) * (1 - occ)
+        close(torch.ops.mrfa.final_blend_s2d(conv, bias, a, occ, r), exp, 1e-6)
+
+
 def test_blend_subpixel_space_to_depth_output_and_final_conv():
     """The r x r space-to-depth output of the last blend is a pure re-layout, and the generator's final 7x7
     convolution evaluated on it as a 3x3 convolution (blocks._final_s2d) equals the direct one."""
