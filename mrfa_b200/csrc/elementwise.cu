@@ -111,6 +111,36 @@ final_blend_s2d_kernel(const float* __restrict__ conv, const float* __restrict__
   }
 }
 
+// r == 4 (the production block size): one thread per run of four pixels of a row = the four consecutive floats of one
+// channel group in `conv`; every access is a 16-byte vector.
+__global__ void __launch_bounds__(256)
+final_blend_s2d_r4_kernel(const float* __restrict__ conv, const float* __restrict__ bias, const float4* __restrict__ a,
+                          const float4* __restrict__ occ, float4* __restrict__ y, int64_t runs, int C, int H, int W,
+                          FastDiv fwb, FastDiv fh) {
+  const int Wb = W >> 2, HW4 = (H * W) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < runs; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = (uint32_t)i;
+    const uint32_t row = fast_div(u, fwb);                      // b * H + Y
+    const int Xb = (int)(u - row * (uint32_t)Wb);
+    const uint32_t b = fast_div(row, fh);
+    const int Y = (int)(row - b * (uint32_t)H);
+    const float* cv = conv + (((int64_t)b * (H >> 2) + (Y >> 2)) * Wb + Xb) * ((int64_t)C * 16) + (Y & 3) * 4;
+    const float4 o = __ldg(occ + i);
+    const int64_t p0 = (int64_t)b * C * HW4 + (int64_t)Y * Wb + Xb;
+    for (int c = 0; c < C; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(cv + c * 16));
+      const float4 w = __ldg(a + p0 + (int64_t)c * HW4);
+      const float bc = __ldg(bias + c);
+      float4 out;
+      out.x = fmaf(1.f / (1.f + expf(-(v.x + bc))), 1.f - o.x, w.x * o.x);
+      out.y = fmaf(1.f / (1.f + expf(-(v.y + bc))), 1.f - o.y, w.y * o.y);
+      out.z = fmaf(1.f / (1.f + expf(-(v.z + bc))), 1.f - o.z, w.z * o.z);
+      out.w = fmaf(1.f / (1.f + expf(-(v.w + bc))), 1.f - o.w, w.w * o.w);
+      y[p0 + (int64_t)c * HW4] = out;
+    }
+  }
+}
+
 // Bilinear resize with align_corners=True (F.interpolate as used at raft.py:243) fused with an
 // optional activation: SURVEY.md 8(f) row N1.  A 1x1 convolution commutes with this resize, so
 // the decoder applies convc1 at the basic resolution and lets this kernel produce
@@ -621,6 +651,13 @@ extern "C" int mrfa_final_blend_s2d(const float* conv, const float* bias, const 
   MRFA_CHECK_SHAPE(H % r == 0 && W % r == 0 && (int64_t)B * H * W < ((int64_t)1 << 31));
   if (B == 0) return 0;
   const int64_t pixels = (int64_t)B * H * W;
+  if (r == 4 && ((reinterpret_cast<uintptr_t>(conv) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(occ) |
+                  reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    final_blend_s2d_r4_kernel<<<stream_blocks(pixels / 4), 256, 0, as_stream(stream)>>>(
+        conv, bias, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(occ), reinterpret_cast<float4*>(y),
+        pixels / 4, C, H, W, make_fastdiv((uint32_t)(W / 4)), make_fastdiv((uint32_t)H));
+    return MRFA_LAUNCH_RESULT();
+  }
   final_blend_s2d_kernel<<<stream_blocks(pixels), 256, 0, as_stream(stream)>>>(
       conv, bias, a, occ, y, pixels, C, H, W, r, make_fastdiv((uint32_t)W), make_fastdiv((uint32_t)H), make_fastdiv((uint32_t)r));
   return MRFA_LAUNCH_RESULT();
